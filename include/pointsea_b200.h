@@ -1,0 +1,131 @@
+/*
+ * pointsea_b200.h — C ABI of the B200-native point-geometry hot path.
+ *
+ * Drop-in boundary for shiyuan0806/SVDFormer_PointSea.  Every entry point replaces one
+ * launcher the reference binds through pybind11 (cited per function, paths relative to the
+ * reference tree).  The reference-side binding a maintainer adds is a ctypes / pybind stub
+ * that forwards `tensor.data_ptr()` + sizes + the current CUDA stream; see INTEGRATION.md.
+ *
+ * Conventions
+ *   - plain C: raw DEVICE pointers, int sizes, the CUDA device ordinal and a cudaStream_t
+ *     passed as void*.  No torch / ATen types cross this boundary.
+ *   - all tensors are dense, contiguous, fp32 / int32, laid out exactly as the reference's
+ *     (B,N,3) clouds, (B,C,N) features and (B,S,K) index tensors.
+ *   - the caller owns every buffer (the reference's pybind layer allocates with torch::zeros;
+ *     our Python layer allocates with torch.empty).  The library never retains a pointer.
+ *     Scratch, where a kernel needs it, is stream-ordered (cudaMallocAsync on `stream`).
+ *   - work is enqueued on `stream` and the call returns immediately (no host sync).
+ *   - return value: PS_OK (0) or a negative PS_ERR_* code; ps_last_error() gives a
+ *     thread-local message.  Nothing ever calls exit() (the reference's CUDA_CHECK_ERRORS
+ *     does: pointnet2_ops/_ext-src/include/cuda_utils.h:30-39) and no error is silently
+ *     dropped (the reference's Chamfer returns an int Python ignores: chamfer3D.cu:145-150).
+ *   - re-entrant: no global mutable state; safe to call concurrently from several host
+ *     threads on different devices (nn.DataParallel replica threads).
+ */
+#ifndef POINTSEA_B200_H
+#define POINTSEA_B200_H
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define PS_OK 0
+#define PS_ERR_INVALID_ARG (-1) /* null pointer, negative size, unsupported size */
+#define PS_ERR_CUDA (-2)        /* a CUDA runtime call or launch failed */
+#define PS_ERR_UNSUPPORTED (-3) /* shape outside what the kernels cover (message says which) */
+
+/* Library version: major*10000 + minor*100 + patch. */
+int ps_version(void);
+/* Thread-local, NUL-terminated description of the last error on this host thread. */
+const char* ps_last_error(void);
+/* SM count and compute capability of `dev` (used by the host layer to fail loudly off sm_100). */
+int ps_device_info(int dev, int* sm_count, int* cc_major, int* cc_minor);
+
+/* ---- Chamfer distance -------------------------------------------------------------------
+ * Replaces chamfer_cuda_forward  (metrics/CD/chamfer3D/chamfer3D.cu:136-154, kernel :12-134;
+ * pybind `chamfer_3D.forward`, chamfer_cuda.cpp:17-19,31).
+ *   xyz1 (B,N,3) f32, xyz2 (B,M,3) f32
+ *   dist1 (B,N) f32 = min_j |xyz1_i - xyz2_j|^2 ; idx1 (B,N) i32 = lowest argmin j
+ *   dist2 (B,M), idx2 (B,M): the same with the roles swapped.
+ * Arithmetic is the reference's SASS order d = fma(dz,dz, fma(dx,dx, dy*dy)), dx = target - query.
+ */
+int ps_chamfer_fwd(const float* xyz1, const float* xyz2, float* dist1, float* dist2, int* idx1,
+                   int* idx2, int B, int N, int M, int dev, void* stream);
+
+/* Replaces chamfer_cuda_backward (chamfer3D.cu:176-195, kernel :155-174; pybind `.backward`).
+ *   gradxyz1 (B,N,3), gradxyz2 (B,M,3) are OVERWRITTEN (the reference needs them pre-zeroed by
+ *   the caller, dist_chamfer_3D.py:56-60; here zero-filling is not required).
+ */
+int ps_chamfer_bwd(const float* xyz1, const float* xyz2, const float* graddist1,
+                   const float* graddist2, const int* idx1, const int* idx2, float* gradxyz1,
+                   float* gradxyz2, int B, int N, int M, int dev, void* stream);
+
+/* ---- Furthest point sampling ------------------------------------------------------------
+ * Replaces furthest_point_sampling_kernel_wrapper (pointnet2_ops/_ext-src/src/sampling_gpu.cu:175-229,
+ * kernel :69-173; pybind `_ext.furthest_point_sampling`, sampling.cpp:66-87).
+ *   xyz (B,N,3) f32 -> idx (B,npoint) i32.  No `temp` scratch is needed (the running
+ *   min-distance array lives in registers).  Tie-break and origin-skip rule are the reference's.
+ */
+int ps_fps(const float* xyz, int* idx, int B, int N, int npoint, int dev, void* stream);
+
+/* ---- gather / group ---------------------------------------------------------------------
+ * Replaces gather_points_kernel_wrapper (sampling_gpu.cu:22-30) / _grad_ (:49-57):
+ *   out[b,c,j] = features[b,c,idx[b,j]] ; features (B,C,N), idx (B,M) i32, out (B,C,M).
+ *   bwd: grad_features (B,C,N) is OVERWRITTEN with the scatter-add of grad_out (B,C,M).
+ */
+int ps_gather_fwd(const float* features, const int* idx, float* out, int B, int C, int N, int M,
+                  int dev, void* stream);
+int ps_gather_bwd(const float* grad_out, const int* idx, float* grad_features, int B, int C,
+                  int N, int M, int dev, void* stream);
+/* Replaces group_points_kernel_wrapper (group_points_gpu.cu:30-39) / _grad_ (:66-75):
+ *   out[b,c,s,k] = features[b,c,idx[b,s,k]] ; idx (B,S,K) i32, out (B,C,S,K).
+ */
+int ps_group_fwd(const float* features, const int* idx, float* out, int B, int C, int N, int S,
+                 int K, int dev, void* stream);
+int ps_group_bwd(const float* grad_out, const int* idx, float* grad_features, int B, int C, int N,
+                 int S, int K, int dev, void* stream);
+
+/* ---- neighbourhood queries --------------------------------------------------------------
+ * Replaces query_ball_point_kernel_wrapper (ball_query_gpu.cu:46-54, kernel :9-44; note the
+ * argument order of `_ext.ball_query(new_xyz, xyz, radius, nsample)`, ball_query.cpp:8-32).
+ *   new_xyz (B,S,3) centres, xyz (B,N,3) -> idx (B,S,nsample) i32: the first nsample indices
+ *   (ascending) with d2 < radius*radius, padded with the first hit; all zero when none.
+ */
+int ps_ball_query(const float* new_xyz, const float* xyz, int* idx, int B, int N, int S,
+                  float radius, int nsample, int dev, void* stream);
+
+/* Replaces the torch expression query_knn / square_distance (models/model_utils.py:258-286):
+ *   idx (B,S,k) i32 = indices of the k smallest of
+ *       dist[s,n] = ((-2*dot(new_xyz_s, xyz_n)) + |new_xyz_s|^2) + |xyz_n|^2   (fp32)
+ *   in ascending (dist, index) order, skipping the first `skip` (skip=1 <=> include_self=False).
+ *   No (B,S,N) matrix is materialised.
+ */
+int ps_knn(const float* xyz, const float* new_xyz, int* idx, int B, int N, int S, int k, int skip,
+           int dev, void* stream);
+
+/* ---- 3-NN + interpolation ---------------------------------------------
+ * Replaces three_nn_kernel_wrapper (interpolate_gpu.cu:61-68, kernel :9-59):
+ *   unknown (B,n,3), known (B,m,3) -> dist2 (B,n,3) f32 (squared), idx (B,n,3) i32.
+ * three_interpolate_kernel_wrapper (:103-112) / _grad_ (:145-154):
+ *   out[b,c,j] = sum_t points[b,c,idx[b,j,t]] * weight[b,j,t] ; points (B,C,m), out (B,C,n).
+ */
+int ps_three_nn(const float* unknown, const float* known, float* dist2, int* idx, int B, int n,
+                int m, int dev, void* stream);
+int ps_three_interpolate_fwd(const float* points, const int* idx, const float* weight, float* out,
+                             int B, int C, int m, int n, int dev, void* stream);
+int ps_three_interpolate_bwd(const float* grad_out, const int* idx, const float* weight,
+                             float* grad_points, int B, int C, int n, int m, int dev, void* stream);
+
+/* ---- measurement helpers (bench.py) ------------------------------------------------------
+ * Runs an FFMA2-only kernel on `dev` and returns the best-of-`reps` fp32 TFLOP/s: the live
+ * roofline denominator for the Chamfer kernel (MEASURED_PEAKS.json has no fp32 figure).
+ */
+int ps_measure_fp32_peak(int dev, int reps, double* tflops);
+/* Number of kernel launches issued by this library on the calling host thread since the
+ * last reset (bench.py reports it as gpu_launches). */
+long long ps_launch_count(int reset);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* POINTSEA_B200_H */

@@ -1,0 +1,339 @@
+/*
+ * pointsea_oracle.c — CPU restatement of the reference's point-geometry hot path.
+ *
+ * TEST INFRASTRUCTURE ONLY.  Imported by tests/, __graft_entry__.smoke() and bench.py's
+ * cpu_baseline / --impl reference legs as the CHECKER; the product package
+ * (svdformer_pointsea_b200/) never loads it and has no CPU fallback.
+ *
+ * Parity status: PINNED against tests/golden/ (npz files), which hold outputs of the reference's own
+ * CUDA kernels (oracle/_ref, built from /root/reference by oracle/build_ref.py) run on a B200
+ * by tests/golden/make_golden.py.  tests/test_oracle_golden.py checks every function here
+ * against those vectors bit-for-bit (indices) / exactly or to 1e-6 (floats).
+ * kNN is the one exception: its reference is a torch expression whose GEMM arithmetic lives
+ * in cuBLAS; the golden vectors there are torch-CUDA outputs (see DESIGN.md "kNN arithmetic").
+ *
+ * Every function restates one reference routine in scalar C, one loop nest per kernel, in the
+ * floating-point order nvcc emits for sm_100a (verified in SASS: the middle product of
+ * a*a + b*b + c*c is a plain FMUL, the first product is fused onto it, then the third):
+ *     d = fmaf(dz,dz, fmaf(dx,dx, dy*dy))
+ * Build with -ffp-contract=off so that gcc does not add contractions of its own.
+ * Paths below are relative to the reference tree.
+ */
+#include <math.h>
+#include <stdint.h>
+#include <stdlib.h>
+#include <string.h>
+
+static inline float dist2_ref(float dx, float dy, float dz) {
+  float t = dy * dy;
+  t = fmaf(dx, dx, t);
+  return fmaf(dz, dz, t);
+}
+
+/* ---- Chamfer forward: metrics/CD/chamfer3D/chamfer3D.cu:12-134 (NmDistanceKernel) ----------
+ * One direction: for each point of xyz (n), nearest point of xyz2 (m).  Restated with the
+ * reference's tile structure: targets in tiles of 512; inside a tile the first element is
+ * taken unconditionally and later ones on strict `d < best` (:36-70, :118-124); across tiles the
+ * stored result is replaced on strict `result > best` (:126-129).  dx = target - query (:33). */
+static void nm_distance(int b, int n, const float* xyz, int m, const float* xyz2, float* result,
+                        int* result_i) {
+  const int batch = 512;
+  for (int i = 0; i < b; i++) {
+    for (int k2 = 0; k2 < m; k2 += batch) {
+      const int end_k = (m < k2 + batch ? m : k2 + batch) - k2;
+      const float* buf = xyz2 + ((size_t)i * m + k2) * 3;
+      for (int j = 0; j < n; j++) {
+        const float x1 = xyz[((size_t)i * n + j) * 3 + 0];
+        const float y1 = xyz[((size_t)i * n + j) * 3 + 1];
+        const float z1 = xyz[((size_t)i * n + j) * 3 + 2];
+        int best_i = 0;
+        float best = 0;
+        for (int k = 0; k < end_k; k++) {
+          const float x2 = buf[k * 3 + 0] - x1;
+          const float y2 = buf[k * 3 + 1] - y1;
+          const float z2 = buf[k * 3 + 2] - z1;
+          const float d = dist2_ref(x2, y2, z2);
+          if (k == 0 || d < best) {
+            best = d;
+            best_i = k + k2;
+          }
+        }
+        if (k2 == 0 || result[(size_t)i * n + j] > best) {
+          result[(size_t)i * n + j] = best;
+          result_i[(size_t)i * n + j] = best_i;
+        }
+      }
+    }
+  }
+}
+
+/* chamfer_cuda_forward, chamfer3D.cu:136-154: two launches with the roles swapped. */
+void or_chamfer_fwd(const float* xyz1, const float* xyz2, float* dist1, float* dist2, int* idx1,
+                    int* idx2, int B, int N, int M) {
+  nm_distance(B, N, xyz1, M, xyz2, dist1, idx1);
+  nm_distance(B, M, xyz2, N, xyz1, dist2, idx2);
+}
+
+/* ---- Chamfer backward: chamfer3D.cu:155-174 (NmDistanceGradKernel), launches :184-185 -------
+ * g = 2*grad_dist; grad_xyz1[i] += g*(a-b); grad_xyz2[j] += -(g*(a-b)).  The reference
+ * accumulates with atomicAdd in nondeterministic order; here the order is i ascending, side 1
+ * then side 2 (parity is therefore 1e-5 relative, not bitwise).  Outputs are zeroed here (the
+ * reference's caller passes torch.zeros, dist_chamfer_3D.py:56-60). */
+static void nm_distance_grad(int b, int n, const float* xyz1, int m, const float* xyz2,
+                             const float* grad_dist1, const int* idx1, float* grad_xyz1,
+                             float* grad_xyz2) {
+  for (int i = 0; i < b; i++) {
+    for (int j = 0; j < n; j++) {
+      const size_t a = ((size_t)i * n + j) * 3;
+      const int j2 = idx1[(size_t)i * n + j];
+      const size_t t = ((size_t)i * m + j2) * 3;
+      const float g = grad_dist1[(size_t)i * n + j] * 2;
+      for (int c = 0; c < 3; c++) {
+        const float v = g * (xyz1[a + c] - xyz2[t + c]);
+        grad_xyz1[a + c] += v;
+        grad_xyz2[t + c] += -v;
+      }
+    }
+  }
+}
+
+void or_chamfer_bwd(const float* xyz1, const float* xyz2, const float* gd1, const float* gd2,
+                    const int* idx1, const int* idx2, float* g1, float* g2, int B, int N, int M) {
+  memset(g1, 0, sizeof(float) * (size_t)B * N * 3);
+  memset(g2, 0, sizeof(float) * (size_t)B * M * 3);
+  nm_distance_grad(B, N, xyz1, M, xyz2, gd1, idx1, g1, g2);
+  nm_distance_grad(B, M, xyz2, N, xyz1, gd2, idx2, g2, g1);
+}
+
+/* ---- FPS: pointnet2_ops/_ext-src/src/sampling_gpu.cu:69-173 ----------------------------------
+ * opt_n_threads: include/cuda_utils.h:15-19 (double log ratio, truncated, clamped to [1,512]). */
+int or_opt_n_threads(int work_size) {
+  const int pow_2 = (int)(log((double)work_size) / log(2.0));
+  int t = 1 << pow_2;
+  if (t > 512) t = 512;
+  if (t < 1) t = 1;
+  return t;
+}
+
+/* Literal simulation of the block: `bs` threads, thread tid scans k = tid, tid+bs, ... with
+ * strict `d2 > best` (:95-110), skips points with (double)mag <= 1e-3 (:100-101), then the
+ * shared-memory tree where __update keeps the left operand on ties (:59-65, :115-168).
+ * temp starts at 1e10 (sampling.cpp:74-76); idxs[0] = 0 (:84-85). */
+void or_fps(const float* xyz, int* idxs_all, int B, int N, int npoint) {
+  if (npoint <= 0) return;
+  const int bs = or_opt_n_threads(N);
+  float* temp = (float*)malloc(sizeof(float) * (size_t)N);
+  float* dists = (float*)malloc(sizeof(float) * (size_t)bs);
+  int* dists_i = (int*)malloc(sizeof(int) * (size_t)bs);
+  for (int bi = 0; bi < B; bi++) {
+    const float* dataset = xyz + (size_t)bi * N * 3;
+    int* idxs = idxs_all + (size_t)bi * npoint;
+    for (int k = 0; k < N; k++) temp[k] = 1e10f;
+    int old = 0;
+    idxs[0] = old;
+    for (int j = 1; j < npoint; j++) {
+      const float x1 = dataset[old * 3 + 0], y1 = dataset[old * 3 + 1], z1 = dataset[old * 3 + 2];
+      for (int tid = 0; tid < bs; tid++) {
+        int besti = 0;
+        float best = -1;
+        for (int k = tid; k < N; k += bs) {
+          const float x2 = dataset[k * 3 + 0], y2 = dataset[k * 3 + 1], z2 = dataset[k * 3 + 2];
+          const float mag = dist2_ref(x2, y2, z2);
+          if ((double)mag <= 1e-3) continue;
+          const float d = dist2_ref(x2 - x1, y2 - y1, z2 - z1);
+          const float d2 = fminf(d, temp[k]);
+          temp[k] = d2;
+          besti = d2 > best ? k : besti;
+          best = d2 > best ? d2 : best;
+        }
+        dists[tid] = best;
+        dists_i[tid] = besti;
+      }
+      for (int s = bs / 2; s >= 1; s /= 2) {
+        for (int tid = 0; tid < s; tid++) {
+          const float v1 = dists[tid], v2 = dists[tid + s];
+          const int i1 = dists_i[tid], i2 = dists_i[tid + s];
+          dists[tid] = v1 > v2 ? v1 : v2; /* max(v1, v2) */
+          dists_i[tid] = v2 > v1 ? i2 : i1;
+        }
+      }
+      old = dists_i[0];
+      idxs[j] = old;
+    }
+  }
+  free(temp);
+  free(dists);
+  free(dists_i);
+}
+
+/* ---- gather: sampling_gpu.cu:8-20 ; grad :34-47 (output zero-initialised, sampling.cpp:52-54) */
+void or_gather(const float* points, const int* idx, float* out, int B, int C, int N, int M) {
+  for (int i = 0; i < B; i++)
+    for (int l = 0; l < C; l++)
+      for (int j = 0; j < M; j++) {
+        const int a = idx[(size_t)i * M + j];
+        out[((size_t)i * C + l) * M + j] = points[((size_t)i * C + l) * N + a];
+      }
+}
+void or_gather_grad(const float* grad_out, const int* idx, float* grad_points, int B, int C, int N, int M) {
+  memset(grad_points, 0, sizeof(float) * (size_t)B * C * N);
+  for (int i = 0; i < B; i++)
+    for (int l = 0; l < C; l++)
+      for (int j = 0; j < M; j++) {
+        const int a = idx[(size_t)i * M + j];
+        grad_points[((size_t)i * C + l) * N + a] += grad_out[((size_t)i * C + l) * M + j];
+      }
+}
+
+/* ---- group: group_points_gpu.cu:8-28 ; grad :43-64 ------------------------------------------ */
+void or_group(const float* points, const int* idx, float* out, int B, int C, int N, int S, int K) {
+  for (int b = 0; b < B; b++)
+    for (int l = 0; l < C; l++)
+      for (int j = 0; j < S; j++)
+        for (int k = 0; k < K; k++) {
+          const int ii = idx[((size_t)b * S + j) * K + k];
+          out[(((size_t)b * C + l) * S + j) * K + k] = points[((size_t)b * C + l) * N + ii];
+        }
+}
+void or_group_grad(const float* grad_out, const int* idx, float* grad_points, int B, int C, int N, int S, int K) {
+  memset(grad_points, 0, sizeof(float) * (size_t)B * C * N);
+  for (int b = 0; b < B; b++)
+    for (int l = 0; l < C; l++)
+      for (int j = 0; j < S; j++)
+        for (int k = 0; k < K; k++) {
+          const int ii = idx[((size_t)b * S + j) * K + k];
+          grad_points[((size_t)b * C + l) * N + ii] += grad_out[(((size_t)b * C + l) * S + j) * K + k];
+        }
+}
+
+/* ---- ball query: ball_query_gpu.cu:9-44; idx zero-initialised (ball_query.cpp:19-21) ---------
+ * d2 uses dx = new - p (:30-31); radius2 = radius*radius in fp32 (:22). */
+void or_ball_query(const float* new_xyz, const float* xyz, int* idx, int B, int N, int S, float radius, int nsample) {
+  memset(idx, 0, sizeof(int) * (size_t)B * S * nsample);
+  const float radius2 = radius * radius;
+  for (int b = 0; b < B; b++)
+    for (int j = 0; j < S; j++) {
+      const float nx = new_xyz[((size_t)b * S + j) * 3 + 0];
+      const float ny = new_xyz[((size_t)b * S + j) * 3 + 1];
+      const float nz = new_xyz[((size_t)b * S + j) * 3 + 2];
+      int* o = idx + ((size_t)b * S + j) * nsample;
+      for (int k = 0, cnt = 0; k < N && cnt < nsample; ++k) {
+        const float x = xyz[((size_t)b * N + k) * 3 + 0];
+        const float y = xyz[((size_t)b * N + k) * 3 + 1];
+        const float z = xyz[((size_t)b * N + k) * 3 + 2];
+        const float d2 = dist2_ref(nx - x, ny - y, nz - z);
+        if (d2 < radius2) {
+          if (cnt == 0)
+            for (int l = 0; l < nsample; ++l) o[l] = k;
+          o[cnt] = k;
+          ++cnt;
+        }
+      }
+    }
+}
+
+/* ---- three_nn: interpolate_gpu.cu:9-59 (running bests in double, init 1e40, :27) ------------ */
+void or_three_nn(const float* unknown, const float* known, float* dist2, int* idx, int B, int n, int m) {
+  for (int b = 0; b < B; b++)
+    for (int j = 0; j < n; j++) {
+      const float ux = unknown[((size_t)b * n + j) * 3 + 0];
+      const float uy = unknown[((size_t)b * n + j) * 3 + 1];
+      const float uz = unknown[((size_t)b * n + j) * 3 + 2];
+      double best1 = 1e40, best2 = 1e40, best3 = 1e40;
+      int besti1 = 0, besti2 = 0, besti3 = 0;
+      for (int k = 0; k < m; ++k) {
+        const float x = known[((size_t)b * m + k) * 3 + 0];
+        const float y = known[((size_t)b * m + k) * 3 + 1];
+        const float z = known[((size_t)b * m + k) * 3 + 2];
+        const float d = dist2_ref(ux - x, uy - y, uz - z);
+        if (d < best1) {
+          best3 = best2; besti3 = besti2; best2 = best1; besti2 = besti1; best1 = d; besti1 = k;
+        } else if (d < best2) {
+          best3 = best2; besti3 = besti2; best2 = d; besti2 = k;
+        } else if (d < best3) {
+          best3 = d; besti3 = k;
+        }
+      }
+      float* od = dist2 + ((size_t)b * n + j) * 3;
+      int* oi = idx + ((size_t)b * n + j) * 3;
+      od[0] = (float)best1; od[1] = (float)best2; od[2] = (float)best3;
+      oi[0] = besti1; oi[1] = besti2; oi[2] = besti3;
+    }
+}
+
+/* ---- three_interpolate: interpolate_gpu.cu:72-101 ; grad :116-143 ----------------------------
+ * out = p1*w1 + p2*w2 + p3*w3 contracted by nvcc as fmaf(p3,w3, fmaf(p1,w1, p2*w2)) (SASS). */
+void or_three_interpolate(const float* points, const int* idx, const float* weight, float* out, int B, int C, int m, int n) {
+  for (int b = 0; b < B; b++)
+    for (int l = 0; l < C; l++)
+      for (int j = 0; j < n; j++) {
+        const float* w = weight + ((size_t)b * n + j) * 3;
+        const int* ix = idx + ((size_t)b * n + j) * 3;
+        const float* row = points + ((size_t)b * C + l) * m;
+        float t = row[ix[1]] * w[1];
+        t = fmaf(row[ix[0]], w[0], t);
+        out[((size_t)b * C + l) * n + j] = fmaf(row[ix[2]], w[2], t);
+      }
+}
+void or_three_interpolate_grad(const float* grad_out, const int* idx, const float* weight, float* grad_points, int B, int C, int n, int m) {
+  memset(grad_points, 0, sizeof(float) * (size_t)B * C * m);
+  for (int b = 0; b < B; b++)
+    for (int l = 0; l < C; l++)
+      for (int j = 0; j < n; j++) {
+        const float* w = weight + ((size_t)b * n + j) * 3;
+        const int* ix = idx + ((size_t)b * n + j) * 3;
+        float* row = grad_points + ((size_t)b * C + l) * m;
+        const float g = grad_out[((size_t)b * C + l) * n + j];
+        row[ix[0]] += g * w[0];
+        row[ix[1]] += g * w[1];
+        row[ix[2]] += g * w[2];
+      }
+}
+
+/* ---- kNN: models/model_utils.py:258-286 (square_distance + argsort[:, :, pad:k+pad]) ----------
+ * dist = ((-2*dot) + |q|^2) + |p|^2 in fp32; |.|^2 = (x*x + z*z) + y*y with separately rounded
+ * squares (torch.sum(src ** 2, -1) as torch's CUDA reduction orders it); dot accumulated as the K=3 fp32 GEMM does.  `variant`
+ * selects that accumulation order: 0 = fmaf(z,z', fmaf(y,y', x*x')), 1 = reverse, 2 = unfused.
+ * Order: ascending (dist, index), i.e. a stable sort of the row. */
+typedef struct { float d; int i; } knn_pair;
+static int knn_cmp(const void* a, const void* b) {
+  const knn_pair* x = (const knn_pair*)a;
+  const knn_pair* y = (const knn_pair*)b;
+  if (x->d < y->d) return -1;
+  if (x->d > y->d) return 1;
+  return (x->i > y->i) - (x->i < y->i);
+}
+static inline float sumsq_torch(float x, float y, float z) {
+  /* torch.sum(p ** 2, -1) on CUDA combines the three rounded squares as (x^2 + z^2) + y^2
+   * (measured on B200 with torch 2.11: tests/golden/knn.npz '*.qq'). */
+  float a = x * x, b = y * y, c = z * z;
+  float s = a + c;
+  return s + b;
+}
+void or_knn(const float* xyz, const float* new_xyz, int* idx, int B, int N, int S, int k, int skip, int variant) {
+  knn_pair* row = (knn_pair*)malloc(sizeof(knn_pair) * (size_t)N);
+  for (int b = 0; b < B; b++)
+    for (int s = 0; s < S; s++) {
+      const float qx = new_xyz[((size_t)b * S + s) * 3 + 0];
+      const float qy = new_xyz[((size_t)b * S + s) * 3 + 1];
+      const float qz = new_xyz[((size_t)b * S + s) * 3 + 2];
+      const float qq = sumsq_torch(qx, qy, qz);
+      for (int n = 0; n < N; n++) {
+        const float px = xyz[((size_t)b * N + n) * 3 + 0];
+        const float py = xyz[((size_t)b * N + n) * 3 + 1];
+        const float pz = xyz[((size_t)b * N + n) * 3 + 2];
+        float dot;
+        if (variant == 0) { dot = qx * px; dot = fmaf(qy, py, dot); dot = fmaf(qz, pz, dot); }
+        else if (variant == 1) { dot = qz * pz; dot = fmaf(qy, py, dot); dot = fmaf(qx, px, dot); }
+        else { float a = qx * px, c = qy * py, e = qz * pz; dot = a + c; dot = dot + e; }
+        float d = -2.0f * dot;
+        d = d + qq;
+        d = d + sumsq_torch(px, py, pz);
+        row[n].d = d;
+        row[n].i = n;
+      }
+      qsort(row, (size_t)N, sizeof(knn_pair), knn_cmp);
+      for (int e = 0; e < k; e++) idx[((size_t)b * S + s) * k + e] = row[e + skip].i;
+    }
+  free(row);
+}

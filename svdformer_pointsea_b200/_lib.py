@@ -1,0 +1,133 @@
+"""ctypes binding of the C ABI in include/pointsea_b200.h (libpointsea_b200.so).
+
+This is the whole Python<->native boundary: raw device pointers, sizes, the device ordinal
+and the current CUDA stream.  There is NO CPU fallback: if the shared library is missing or a
+tensor is not on a CUDA device the call raises.
+"""
+import ctypes
+import os
+import os.path as osp
+
+import torch
+
+_HERE = osp.dirname(osp.abspath(__file__))
+LIB_PATH = osp.join(_HERE, "lib", "libpointsea_b200.so")
+
+_c_int = ctypes.c_int
+_c_void_p = ctypes.c_void_p
+_c_float = ctypes.c_float
+
+# name -> argtypes (restype is int unless stated) — mirrors include/pointsea_b200.h 1:1
+_P = _c_void_p
+_SIGNATURES = {
+    "ps_chamfer_fwd": [_P, _P, _P, _P, _P, _P, _c_int, _c_int, _c_int, _c_int, _P],
+    "ps_chamfer_bwd": [_P, _P, _P, _P, _P, _P, _P, _P, _c_int, _c_int, _c_int, _c_int, _P],
+    "ps_fps": [_P, _P, _c_int, _c_int, _c_int, _c_int, _P],
+    "ps_gather_fwd": [_P, _P, _P, _c_int, _c_int, _c_int, _c_int, _c_int, _P],
+    "ps_gather_bwd": [_P, _P, _P, _c_int, _c_int, _c_int, _c_int, _c_int, _P],
+    "ps_group_fwd": [_P, _P, _P, _c_int, _c_int, _c_int, _c_int, _c_int, _c_int, _P],
+    "ps_group_bwd": [_P, _P, _P, _c_int, _c_int, _c_int, _c_int, _c_int, _c_int, _P],
+    "ps_ball_query": [_P, _P, _P, _c_int, _c_int, _c_int, _c_float, _c_int, _c_int, _P],
+    "ps_knn": [_P, _P, _P, _c_int, _c_int, _c_int, _c_int, _c_int, _c_int, _P],
+    "ps_three_nn": [_P, _P, _P, _P, _c_int, _c_int, _c_int, _c_int, _P],
+    "ps_three_interpolate_fwd": [_P, _P, _P, _P, _c_int, _c_int, _c_int, _c_int, _c_int, _P],
+    "ps_three_interpolate_bwd": [_P, _P, _P, _P, _c_int, _c_int, _c_int, _c_int, _c_int, _P],
+    "ps_device_info": [_c_int, ctypes.POINTER(_c_int), ctypes.POINTER(_c_int), ctypes.POINTER(_c_int)],
+    "ps_measure_fp32_peak": [_c_int, _c_int, ctypes.POINTER(ctypes.c_double)],
+}
+EXPORTED_SYMBOLS = sorted(list(_SIGNATURES) + ["ps_version", "ps_last_error", "ps_launch_count"])
+
+_lib = None
+
+
+class PointSeaError(RuntimeError):
+    """Raised for every non-zero return code of the native library."""
+
+
+def load():
+    """Load libpointsea_b200.so (once).  Raises if it has not been built."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not osp.exists(LIB_PATH):
+        raise PointSeaError(
+            f"{LIB_PATH} is missing: build it with `python __graft_entry__.py build` "
+            "(svdformer_pointsea_b200/csrc/build.sh). There is no CPU or PyTorch fallback.")
+    lib = ctypes.CDLL(LIB_PATH)
+    for name, argtypes in _SIGNATURES.items():
+        fn = getattr(lib, name)
+        fn.argtypes = argtypes
+        fn.restype = _c_int
+    lib.ps_version.argtypes = []
+    lib.ps_version.restype = _c_int
+    lib.ps_last_error.argtypes = []
+    lib.ps_last_error.restype = ctypes.c_char_p
+    lib.ps_launch_count.argtypes = [_c_int]
+    lib.ps_launch_count.restype = ctypes.c_longlong
+    _lib = lib
+    return lib
+
+
+def check(rc, what):
+    if rc != 0:
+        msg = load().ps_last_error().decode("utf-8", "replace")
+        raise PointSeaError(f"{what} failed (code {rc}): {msg}")
+
+
+_checked_devices = set()
+
+
+def _check_device(index):
+    """Fail loudly off sm_100: the kernels are built for sm_100a only."""
+    if index in _checked_devices:
+        return
+    sm, major, minor = _c_int(), _c_int(), _c_int()
+    check(load().ps_device_info(index, ctypes.byref(sm), ctypes.byref(major), ctypes.byref(minor)), "ps_device_info")
+    if major.value != 10:
+        raise PointSeaError(
+            f"cuda:{index} has compute capability {major.value}.{minor.value}; this library is sm_100a (B200) only")
+    _checked_devices.add(index)
+
+
+def require(t, name, dtype, ndim):
+    """The reference's CHECK_CONTIGUOUS / CHECK_IS_FLOAT / CHECK_IS_INT / CHECK_CUDA
+    (pointnet2_ops/_ext-src/include/utils.h:5-25) as RuntimeErrors."""
+    if not isinstance(t, torch.Tensor):
+        raise PointSeaError(f"{name} must be a torch.Tensor")
+    if not t.is_cuda:
+        raise PointSeaError(f"{name} must be a CUDA tensor (CPU not supported)")
+    if t.dtype != dtype:
+        raise PointSeaError(f"{name} must be a {'float' if dtype == torch.float32 else 'int'} tensor, got {t.dtype}")
+    if t.dim() != ndim:
+        raise PointSeaError(f"{name} must have {ndim} dimensions, got {tuple(t.shape)}")
+    if not t.is_contiguous():
+        raise PointSeaError(f"{name} must be a contiguous tensor")
+    return t
+
+
+def same_device(*ts):
+    dev = ts[0].device
+    for t in ts[1:]:
+        if t.device != dev:
+            raise PointSeaError(f"tensors are on different devices: {dev} vs {t.device}")
+    index = dev.index if dev.index is not None else torch.cuda.current_device()
+    _check_device(index)
+    return index
+
+
+def stream_ptr(index):
+    return _c_void_p(torch.cuda.current_stream(index).cuda_stream)
+
+
+def ptr(t):
+    return _c_void_p(t.data_ptr())
+
+
+def launch_count(reset=False):
+    return int(load().ps_launch_count(1 if reset else 0))
+
+
+def measure_fp32_peak(index=0, reps=5):
+    out = ctypes.c_double()
+    check(load().ps_measure_fp32_peak(index, reps, ctypes.byref(out)), "ps_measure_fp32_peak")
+    return out.value

@@ -1,0 +1,80 @@
+"""Chamfer distance: host-side mirror of metrics/CD/chamfer3D/dist_chamfer_3D.py.
+
+Same names, argument meaning and outputs as the reference's `chamfer_3DFunction` /
+`chamfer_3DDist` (dist_chamfer_3D.py:26-74); underneath, one C-ABI call per direction pair.
+Differences that are deliberate: outputs are allocated on the device directly
+(the reference allocates on the CPU and copies, :33-42), work is enqueued on the caller's
+current stream (the reference uses the legacy default stream), errors raise.
+"""
+import torch
+from torch import nn
+from torch.autograd import Function
+
+from . import _lib as L
+
+
+def chamfer_forward(xyz1, xyz2):
+    """(dist1, dist2, idx1, idx2) for xyz1 (B,N,3), xyz2 (B,M,3); no autograd."""
+    L.require(xyz1, "xyz1", torch.float32, 3)
+    L.require(xyz2, "xyz2", torch.float32, 3)
+    if xyz1.size(2) != 3 or xyz2.size(2) != 3 or xyz1.size(0) != xyz2.size(0):
+        raise L.PointSeaError(f"chamfer expects (B,N,3) and (B,M,3), got {tuple(xyz1.shape)} {tuple(xyz2.shape)}")
+    dev = L.same_device(xyz1, xyz2)
+    B, N, _ = xyz1.shape
+    M = xyz2.size(1)
+    dist1 = torch.empty(B, N, device=xyz1.device, dtype=torch.float32)
+    dist2 = torch.empty(B, M, device=xyz1.device, dtype=torch.float32)
+    idx1 = torch.empty(B, N, device=xyz1.device, dtype=torch.int32)
+    idx2 = torch.empty(B, M, device=xyz1.device, dtype=torch.int32)
+    rc = L.load().ps_chamfer_fwd(L.ptr(xyz1), L.ptr(xyz2), L.ptr(dist1), L.ptr(dist2), L.ptr(idx1), L.ptr(idx2),
+                                 B, N, M, dev, L.stream_ptr(dev))
+    L.check(rc, "ps_chamfer_fwd")
+    return dist1, dist2, idx1, idx2
+
+
+def chamfer_backward(xyz1, xyz2, graddist1, graddist2, idx1, idx2):
+    L.require(graddist1, "graddist1", torch.float32, 2)
+    L.require(graddist2, "graddist2", torch.float32, 2)
+    L.require(idx1, "idx1", torch.int32, 2)
+    L.require(idx2, "idx2", torch.int32, 2)
+    dev = L.same_device(xyz1, xyz2, graddist1, graddist2, idx1, idx2)
+    B, N, _ = xyz1.shape
+    M = xyz2.size(1)
+    gradxyz1 = torch.empty_like(xyz1)
+    gradxyz2 = torch.empty_like(xyz2)
+    rc = L.load().ps_chamfer_bwd(L.ptr(xyz1), L.ptr(xyz2), L.ptr(graddist1), L.ptr(graddist2), L.ptr(idx1),
+                                 L.ptr(idx2), L.ptr(gradxyz1), L.ptr(gradxyz2), B, N, M, dev, L.stream_ptr(dev))
+    L.check(rc, "ps_chamfer_bwd")
+    return gradxyz1, gradxyz2
+
+
+class chamfer_3DFunction(Function):
+    """Drop-in for dist_chamfer_3D.chamfer_3DFunction (dist_chamfer_3D.py:26-64)."""
+
+    @staticmethod
+    def forward(ctx, xyz1, xyz2):
+        dist1, dist2, idx1, idx2 = chamfer_forward(xyz1, xyz2)
+        ctx.save_for_backward(xyz1, xyz2, idx1, idx2)
+        return dist1, dist2, idx1, idx2
+
+    @staticmethod
+    def backward(ctx, graddist1, graddist2, gradidx1, gradidx2):
+        xyz1, xyz2, idx1, idx2 = ctx.saved_tensors
+        if graddist1 is None:
+            graddist1 = torch.zeros(idx1.shape, device=xyz1.device, dtype=torch.float32)
+        if graddist2 is None:
+            graddist2 = torch.zeros(idx2.shape, device=xyz1.device, dtype=torch.float32)
+        gradxyz1, gradxyz2 = chamfer_backward(xyz1, xyz2, graddist1.contiguous(), graddist2.contiguous(), idx1, idx2)
+        return gradxyz1, gradxyz2
+
+
+class chamfer_3DDist(nn.Module):
+    """Drop-in for dist_chamfer_3D.chamfer_3DDist (dist_chamfer_3D.py:67-74)."""
+
+    def __init__(self):
+        super(chamfer_3DDist, self).__init__()
+
+    def forward(self, input1, input2):
+        input1 = input1.contiguous()
+        input2 = input2.contiguous()
+        return chamfer_3DFunction.apply(input1, input2)

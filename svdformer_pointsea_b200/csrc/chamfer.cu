@@ -1,0 +1,339 @@
+// Chamfer distance forward/backward for sm_100a.
+//
+// Replaces NmDistanceKernel / NmDistanceGradKernel of the reference
+// (metrics/CD/chamfer3D/chamfer3D.cu:12-134, :155-174) behind the C ABI in pointsea_b200.h.
+//
+// Forward design (fp32 CUDA-core bound, no tensor cores: the contraction has K=3):
+//   * one launch covers BOTH directions; a CTA owns (direction, cloud, query tile, target split)
+//   * every thread keeps Q queries in registers; the target split is staged through shared
+//     memory as SoA tiles (x[], y[], z[]) so one broadcast LDS.128 per coordinate feeds
+//     4 targets x Q queries
+//   * distances are evaluated two targets at a time with the packed sm_100 instructions
+//     FADD2 / FMUL2 / FFMA2 in exactly the reference's rounding order
+//     d = fma(dz,dz, fma(dx,dx, dy*dy)), dx = target - query; the running minimum is one
+//     FMNMX3 per two pairs
+//   * the argmin index is recovered lazily: per 64-target chunk we only note whether the
+//     running minimum improved (strict <, so the EARLIEST chunk holding the final minimum is
+//     remembered); after the scan each thread re-evaluates that one chunk with the scalar
+//     expression and takes the first target whose distance equals the minimum bit-for-bit.
+//     This is the reference's "lowest index among exact minima" (strict < within a tile,
+//     chamfer3D.cu:36-70, strict > across tiles, :126).
+//   * when the targets are split across CTAs the partial results are merged with a 64-bit
+//     atomicMin on (dist_bits << 32 | idx): distances are >= 0 so the bit pattern is
+//     monotone, and equal distances resolve to the lower index.
+#include "common.cuh"
+
+namespace ps {
+
+constexpr int CH_THREADS = 256;
+constexpr int CH_TILE = 2048;  // targets per shared-memory tile (24 KB SoA)
+constexpr int CH_CHUNK = 64;   // argmin bookkeeping granularity
+
+struct ChamferDir {
+  const float* q;  // queries (B, nq, 3)
+  const float* t;  // targets (B, nt, 3)
+  float* dist;     // (B, nq)
+  int* idx;        // (B, nq)
+  u64* keys;       // (B, nq) merge scratch when nsplit > 1
+  int nq, nt;
+  int nqtiles;    // query tiles per cloud
+  int nsplit;     // target splits per cloud
+  int split_len;  // targets per split (multiple of CH_CHUNK)
+  int units;      // B * nqtiles * nsplit
+};
+struct ChamferParams {
+  ChamferDir d[2];
+};
+
+template <int Q>
+__global__ void __launch_bounds__(CH_THREADS) chamfer_nn_kernel(const ChamferParams p) {
+  __shared__ __align__(16) float sx[CH_TILE];
+  __shared__ __align__(16) float sy[CH_TILE];
+  __shared__ __align__(16) float sz[CH_TILE];
+
+  int unit = blockIdx.x;
+  const int dir = unit >= p.d[0].units ? 1 : 0;
+  if (dir) unit -= p.d[0].units;
+  // field-wise select keeps the parameter struct in constant space (no local copy)
+  struct {
+    const float *q, *t; float* dist; int* idx; u64* keys; int nq, nt, nqtiles, nsplit, split_len;
+  } D;
+  D.q = dir ? p.d[1].q : p.d[0].q;
+  D.t = dir ? p.d[1].t : p.d[0].t;
+  D.dist = dir ? p.d[1].dist : p.d[0].dist;
+  D.idx = dir ? p.d[1].idx : p.d[0].idx;
+  D.keys = dir ? p.d[1].keys : p.d[0].keys;
+  D.nq = dir ? p.d[1].nq : p.d[0].nq;
+  D.nt = dir ? p.d[1].nt : p.d[0].nt;
+  D.nqtiles = dir ? p.d[1].nqtiles : p.d[0].nqtiles;
+  D.nsplit = dir ? p.d[1].nsplit : p.d[0].nsplit;
+  D.split_len = dir ? p.d[1].split_len : p.d[0].split_len;
+  const int split = unit % D.nsplit;
+  const int rest = unit / D.nsplit;
+  const int qt = rest % D.nqtiles;
+  const int b = rest / D.nqtiles;
+  const int tid = threadIdx.x;
+  const int nq = D.nq, nt = D.nt;
+  const float INF = __int_as_float(0x7f800000);
+
+  // ---- queries into registers -------------------------------------------------------------
+  float qx[Q], qy[Q], qz[Q];
+  u64 nqx[Q], nqy[Q], nqz[Q];
+  float best[Q], cbest[Q];
+  int cchunk[Q];
+  const float* qbase = D.q + (size_t)b * nq * 3;
+#pragma unroll
+  for (int q = 0; q < Q; q++) {
+    const int qi = qt * (CH_THREADS * Q) + q * CH_THREADS + tid;
+    const bool valid = qi < nq;
+    qx[q] = valid ? __ldg(qbase + (size_t)qi * 3 + 0) : 0.f;
+    qy[q] = valid ? __ldg(qbase + (size_t)qi * 3 + 1) : 0.f;
+    qz[q] = valid ? __ldg(qbase + (size_t)qi * 3 + 2) : 0.f;
+    nqx[q] = pack2(-qx[q], -qx[q]);
+    nqy[q] = pack2(-qy[q], -qy[q]);
+    nqz[q] = pack2(-qz[q], -qz[q]);
+    best[q] = INF;
+    cbest[q] = INF;
+    cchunk[q] = 0;
+  }
+
+  const int t0 = split * D.split_len;
+  const int t1 = min(nt, t0 + D.split_len);
+  const float* tcloud = D.t + (size_t)b * nt * 3;
+
+  for (int ts = t0; ts < t1; ts += CH_TILE) {
+    const int cnt = min(CH_TILE, t1 - ts);
+    const int cnt_pad = (cnt + CH_CHUNK - 1) / CH_CHUNK * CH_CHUNK;
+    const float* tb = tcloud + (size_t)ts * 3;
+    const bool vec = (reinterpret_cast<uintptr_t>(tb) & 15) == 0;
+    __syncthreads();  // previous tile fully consumed
+    // ---- stage AoS (x,y,z) points as SoA; pad the last chunk with +inf targets ------------
+    for (int g = tid; g < cnt_pad / 4; g += CH_THREADS) {
+      float4 X, Y, Z;
+      if (vec && g * 4 + 4 <= cnt) {
+        const float4 a = __ldg(reinterpret_cast<const float4*>(tb + g * 12));
+        const float4 bb = __ldg(reinterpret_cast<const float4*>(tb + g * 12 + 4));
+        const float4 c = __ldg(reinterpret_cast<const float4*>(tb + g * 12 + 8));
+        X = make_float4(a.x, a.w, bb.z, c.y);
+        Y = make_float4(a.y, bb.x, bb.w, c.z);
+        Z = make_float4(a.z, bb.y, c.x, c.w);
+      } else {
+        float xs[4], ys[4], zs[4];
+#pragma unroll
+        for (int e = 0; e < 4; e++) {
+          const int pi = g * 4 + e;
+          const bool in = pi < cnt;
+          xs[e] = in ? __ldg(tb + pi * 3 + 0) : INF;
+          ys[e] = in ? __ldg(tb + pi * 3 + 1) : 0.f;
+          zs[e] = in ? __ldg(tb + pi * 3 + 2) : 0.f;
+        }
+        X = make_float4(xs[0], xs[1], xs[2], xs[3]);
+        Y = make_float4(ys[0], ys[1], ys[2], ys[3]);
+        Z = make_float4(zs[0], zs[1], zs[2], zs[3]);
+      }
+      *reinterpret_cast<float4*>(&sx[g * 4]) = X;
+      *reinterpret_cast<float4*>(&sy[g * 4]) = Y;
+      *reinterpret_cast<float4*>(&sz[g * 4]) = Z;
+    }
+    __syncthreads();
+
+    // ---- scan the tile ----------------------------------------------------------------------
+    const int chunk0 = (ts - t0) / CH_CHUNK;
+    for (int c = 0; c < cnt_pad / CH_CHUNK; c++) {
+      const int off = c * CH_CHUNK;
+#pragma unroll 4
+      for (int j = 0; j < CH_CHUNK; j += 4) {
+        const ulonglong2 X = *reinterpret_cast<const ulonglong2*>(&sx[off + j]);
+        const ulonglong2 Y = *reinterpret_cast<const ulonglong2*>(&sy[off + j]);
+        const ulonglong2 Z = *reinterpret_cast<const ulonglong2*>(&sz[off + j]);
+#pragma unroll
+        for (int q = 0; q < Q; q++) {
+          const u64 d01 = dist2x2(X.x, Y.x, Z.x, nqx[q], nqy[q], nqz[q]);
+          const u64 d23 = dist2x2(X.y, Y.y, Z.y, nqx[q], nqy[q], nqz[q]);
+          best[q] = min3(best[q], lo2(d01), hi2(d01));
+          best[q] = min3(best[q], lo2(d23), hi2(d23));
+        }
+      }
+#pragma unroll
+      for (int q = 0; q < Q; q++) {
+        if (best[q] < cbest[q]) cchunk[q] = chunk0 + c;
+        cbest[q] = best[q];
+      }
+    }
+  }
+
+  // ---- recover the argmin: first target of the remembered chunk that reproduces `best` -----
+#pragma unroll
+  for (int q = 0; q < Q; q++) {
+    const int qi = qt * (CH_THREADS * Q) + q * CH_THREADS + tid;
+    if (qi >= nq) continue;
+    const int base = t0 + cchunk[q] * CH_CHUNK;
+    const int n = min(CH_CHUNK, t1 - base);
+    const float* tp = tcloud + (size_t)base * 3;
+    int found = 0;
+#pragma unroll 8
+    for (int j = n - 1; j >= 0; j--) {
+      const float dx = __ldg(tp + j * 3 + 0) - qx[q];
+      const float dy = __ldg(tp + j * 3 + 1) - qy[q];
+      const float dz = __ldg(tp + j * 3 + 2) - qz[q];
+      if (dist2_ref(dx, dy, dz) == best[q]) found = j;
+    }
+    const int gi = base + found;
+    const size_t o = (size_t)b * nq + qi;
+    if (D.nsplit == 1) {
+      D.dist[o] = best[q];
+      D.idx[o] = gi;
+    } else {
+      atomicMin(&D.keys[o], ((u64)__float_as_uint(best[q]) << 32) | (unsigned)gi);
+    }
+  }
+}
+
+__global__ void chamfer_unpack_kernel(const u64* __restrict__ keys, float* __restrict__ dist,
+                                      int* __restrict__ idx, size_t n) {
+  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) {
+    const u64 k = keys[i];
+    dist[i] = __uint_as_float((unsigned)(k >> 32));
+    idx[i] = (int)(unsigned)k;
+  }
+}
+
+// ---- backward ---------------------------------------------------------------------------------
+// Pass A writes every point's own term with plain stores (covers both buffers completely, so the
+// caller does not have to zero them); pass B adds the scattered terms with RED.ADD.
+//   side 1: g = 2*gd1[i]; v = g*(a_i - b_j), j = idx1[i]; grad1[i] = v (A); grad2[j] += -v (B)
+//   side 2: symmetric with idx2 (reference launches the same kernel with the roles swapped,
+//   chamfer3D.cu:184-185).
+struct ChamferBwdParams {
+  const float *xyz1, *xyz2, *gd1, *gd2;
+  const int *idx1, *idx2;
+  float *g1, *g2;
+  int B, N, M;
+};
+
+template <bool SCATTER>
+__global__ void __launch_bounds__(256) chamfer_bwd_kernel(const ChamferBwdParams p) {
+  const size_t tot1 = (size_t)p.B * p.N, tot2 = (size_t)p.B * p.M;
+  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= tot1 + tot2) return;
+  const float *a, *bt, *gd;
+  const int* ix;
+  float *ga, *gb;
+  int na, nb;
+  if (i < tot1) {
+    a = p.xyz1; bt = p.xyz2; gd = p.gd1; ix = p.idx1; ga = p.g1; gb = p.g2; na = p.N; nb = p.M;
+  } else {
+    i -= tot1;
+    a = p.xyz2; bt = p.xyz1; gd = p.gd2; ix = p.idx2; ga = p.g2; gb = p.g1; na = p.M; nb = p.N;
+  }
+  const size_t b = i / na;
+  const int j = __ldg(ix + i);
+  const float* pa = a + i * 3;
+  const float* pb = bt + (b * nb + j) * 3;
+  const float g0 = __ldg(gd + i);
+  const float g = g0 + g0;  // reference: grad_dist*2 (SASS: FADD g,g)
+  const float vx = __fmul_rn(g, __ldg(pa + 0) - __ldg(pb + 0));
+  const float vy = __fmul_rn(g, __ldg(pa + 1) - __ldg(pb + 1));
+  const float vz = __fmul_rn(g, __ldg(pa + 2) - __ldg(pb + 2));
+  if (!SCATTER) {
+    ga[i * 3 + 0] = vx;
+    ga[i * 3 + 1] = vy;
+    ga[i * 3 + 2] = vz;
+  } else {
+    float* o = gb + (b * nb + j) * 3;
+    atomicAdd(o + 0, -vx);
+    atomicAdd(o + 1, -vy);
+    atomicAdd(o + 2, -vz);
+  }
+}
+
+static void plan_dir(ChamferDir& D, int B, int Q, int nsm) {
+  D.nqtiles = ceil_div(D.nq, CH_THREADS * Q);
+  // aim for >= ~6 CTAs per SM over the whole launch so the tail wave stays small, but keep
+  // at least 512 targets per split so the per-unit argmin rescan stays a few percent.
+  const long long base_units = (long long)B * D.nqtiles;
+  const long long want = (long long)nsm * 6;
+  int nsplit = (int)((want + base_units - 1) / base_units);
+  const int max_split = ceil_div(D.nt, 512);
+  if (nsplit > max_split) nsplit = max_split;
+  if (nsplit < 1) nsplit = 1;
+  int len = ceil_div(D.nt, nsplit);
+  len = (len + CH_CHUNK - 1) / CH_CHUNK * CH_CHUNK;
+  D.split_len = len;
+  D.nsplit = ceil_div(D.nt, len);
+  D.units = B * D.nqtiles * D.nsplit;
+}
+
+}  // namespace ps
+
+using namespace ps;
+
+extern "C" int ps_chamfer_fwd(const float* xyz1, const float* xyz2, float* dist1, float* dist2,
+                              int* idx1, int* idx2, int B, int N, int M, int dev, void* stream_) {
+  PS_REQUIRE(B >= 0 && N > 0 && M > 0, "ps_chamfer_fwd: bad sizes B=%d N=%d M=%d", B, N, M);
+  if (B == 0) return PS_OK;
+  PS_REQUIRE(xyz1 && xyz2 && dist1 && dist2 && idx1 && idx2, "ps_chamfer_fwd: null pointer");
+  PS_REQUIRE((long long)B * N < (1ll << 31) / 3 * 3 && (long long)B * M < (1ll << 31) / 3 * 3,
+             "ps_chamfer_fwd: B*N or B*M too large");
+  DeviceGuard guard(dev);
+  if (!guard.ok) return set_error(PS_ERR_CUDA, "ps_chamfer_fwd: cannot select device %d", dev);
+  cudaStream_t stream = (cudaStream_t)stream_;
+  const int nsm = sm_count(dev);
+
+  const int maxq = N > M ? N : M;
+  const int Q = maxq <= 256 ? 1 : (maxq <= 1024 ? 2 : 4);
+  ChamferParams p;
+  p.d[0].q = xyz1; p.d[0].t = xyz2; p.d[0].dist = dist1; p.d[0].idx = idx1; p.d[0].nq = N; p.d[0].nt = M;
+  p.d[1].q = xyz2; p.d[1].t = xyz1; p.d[1].dist = dist2; p.d[1].idx = idx2; p.d[1].nq = M; p.d[1].nt = N;
+  plan_dir(p.d[0], B, Q, nsm);
+  plan_dir(p.d[1], B, Q, nsm);
+
+  // merge scratch for split directions
+  size_t need[2] = {0, 0};
+  for (int d = 0; d < 2; d++)
+    if (p.d[d].nsplit > 1) need[d] = (size_t)B * p.d[d].nq;
+  u64* scratch = nullptr;
+  if (need[0] + need[1]) {
+    PS_CUDA(cudaMallocAsync((void**)&scratch, (need[0] + need[1]) * sizeof(u64), stream));
+    PS_CUDA(cudaMemsetAsync(scratch, 0xFF, (need[0] + need[1]) * sizeof(u64), stream));
+  }
+  p.d[0].keys = need[0] ? scratch : nullptr;
+  p.d[1].keys = need[1] ? scratch + need[0] : nullptr;
+
+  const int grid = p.d[0].units + p.d[1].units;
+  switch (Q) {
+    case 1: chamfer_nn_kernel<1><<<grid, CH_THREADS, 0, stream>>>(p); break;
+    case 2: chamfer_nn_kernel<2><<<grid, CH_THREADS, 0, stream>>>(p); break;
+    default: chamfer_nn_kernel<4><<<grid, CH_THREADS, 0, stream>>>(p); break;
+  }
+  PS_LAUNCH_CHECK();
+  for (int d = 0; d < 2; d++) {
+    if (!need[d]) continue;
+    chamfer_unpack_kernel<<<ceil_div(need[d], 256), 256, 0, stream>>>(p.d[d].keys, p.d[d].dist, p.d[d].idx, need[d]);
+    PS_LAUNCH_CHECK();
+  }
+  if (scratch) PS_CUDA(cudaFreeAsync(scratch, stream));
+  return PS_OK;
+}
+
+extern "C" int ps_chamfer_bwd(const float* xyz1, const float* xyz2, const float* graddist1,
+                              const float* graddist2, const int* idx1, const int* idx2,
+                              float* gradxyz1, float* gradxyz2, int B, int N, int M, int dev,
+                              void* stream_) {
+  PS_REQUIRE(B >= 0 && N > 0 && M > 0, "ps_chamfer_bwd: bad sizes B=%d N=%d M=%d", B, N, M);
+  if (B == 0) return PS_OK;
+  PS_REQUIRE(xyz1 && xyz2 && graddist1 && graddist2 && idx1 && idx2 && gradxyz1 && gradxyz2,
+             "ps_chamfer_bwd: null pointer");
+  DeviceGuard guard(dev);
+  if (!guard.ok) return set_error(PS_ERR_CUDA, "ps_chamfer_bwd: cannot select device %d", dev);
+  cudaStream_t stream = (cudaStream_t)stream_;
+  ChamferBwdParams p{xyz1, xyz2, graddist1, graddist2, idx1, idx2, gradxyz1, gradxyz2, B, N, M};
+  const size_t tot = (size_t)B * N + (size_t)B * M;
+  const int grid = ceil_div(tot, 256);
+  chamfer_bwd_kernel<false><<<grid, 256, 0, stream>>>(p);
+  PS_LAUNCH_CHECK();
+  chamfer_bwd_kernel<true><<<grid, 256, 0, stream>>>(p);
+  PS_LAUNCH_CHECK();
+  return PS_OK;
+}

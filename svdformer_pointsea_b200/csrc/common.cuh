@@ -1,0 +1,112 @@
+// Shared host/device helpers for the pointsea_b200 kernels (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <cstdint>
+#include <cstdio>
+#include <cstdarg>
+
+#include "../../include/pointsea_b200.h"
+
+#if defined(__CUDA_ARCH__) && (__CUDA_ARCH__ < 1000)
+#error "pointsea_b200 kernels are written for sm_100a (B200) only"
+#endif
+
+namespace ps {
+
+typedef unsigned long long u64;
+
+// ---- error plumbing -------------------------------------------------------------------------
+char* err_buf();                 // thread-local 512-byte buffer
+long long& launch_counter();     // thread-local launch counter
+int set_error(int code, const char* fmt, ...);
+
+#define PS_CUDA(call)                                                                        \
+  do {                                                                                       \
+    cudaError_t _e = (call);                                                                 \
+    if (_e != cudaSuccess)                                                                   \
+      return ps::set_error(PS_ERR_CUDA, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(_e), \
+                           __FILE__, __LINE__);                                              \
+  } while (0)
+
+#define PS_REQUIRE(cond, ...)                                        \
+  do {                                                               \
+    if (!(cond)) return ps::set_error(PS_ERR_INVALID_ARG, __VA_ARGS__); \
+  } while (0)
+
+// Counts the launch and converts a launch error into PS_ERR_CUDA.
+#define PS_LAUNCH_CHECK()                                                                    \
+  do {                                                                                       \
+    ps::launch_counter()++;                                                                  \
+    cudaError_t _e = cudaGetLastError();                                                     \
+    if (_e != cudaSuccess)                                                                   \
+      return ps::set_error(PS_ERR_CUDA, "kernel launch failed: %s (%s:%d)",                  \
+                           cudaGetErrorString(_e), __FILE__, __LINE__);                      \
+  } while (0)
+
+// RAII device guard: the reference needs torch.cuda.set_device around Chamfer
+// (dist_chamfer_3D.py:43); here every entry point switches and restores explicitly.
+struct DeviceGuard {
+  int prev = -1;
+  bool ok = true;
+  explicit DeviceGuard(int dev) {
+    if (cudaGetDevice(&prev) != cudaSuccess) { ok = false; return; }
+    if (prev != dev && cudaSetDevice(dev) != cudaSuccess) ok = false;
+  }
+  ~DeviceGuard() {
+    int cur = -1;
+    if (prev >= 0 && cudaGetDevice(&cur) == cudaSuccess && cur != prev) cudaSetDevice(prev);
+  }
+};
+
+int sm_count(int dev);
+
+static inline int ceil_div(long long a, long long b) { return (int)((a + b - 1) / b); }
+
+// ---- device arithmetic ----------------------------------------------------------------------
+#ifdef __CUDACC__
+
+// The reference's squared distance as nvcc contracts it for every kernel on this path
+// (verified in the sm_100a SASS of chamfer3D.cu:34-37, sampling_gpu.cu:103-104,
+// ball_query_gpu.cu:30-31, interpolate_gpu.cu:33): FMUL on y, FFMA on x, FFMA on z.
+__device__ __forceinline__ float dist2_ref(float dx, float dy, float dz) {
+  return __fmaf_rn(dz, dz, __fmaf_rn(dx, dx, __fmul_rn(dy, dy)));
+}
+
+// Packed fp32x2 arithmetic (sm_100 FADD2 / FMUL2 / FFMA2).  Each half rounds exactly like the
+// scalar .rn instruction, so results are bit-identical to the scalar expression above.
+__device__ __forceinline__ u64 add2(u64 a, u64 b) { u64 d; asm("add.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b)); return d; }
+__device__ __forceinline__ u64 mul2(u64 a, u64 b) { u64 d; asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b)); return d; }
+__device__ __forceinline__ u64 fma2(u64 a, u64 b, u64 c) { u64 d; asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c)); return d; }
+__device__ __forceinline__ u64 pack2(float lo, float hi) { u64 d; asm("mov.b64 %0, {%1, %2};" : "=l"(d) : "f"(lo), "f"(hi)); return d; }
+__device__ __forceinline__ float lo2(u64 v) { return __uint_as_float((unsigned)v); }
+__device__ __forceinline__ float hi2(u64 v) { return __uint_as_float((unsigned)(v >> 32)); }
+// 3-input min / max (sm_100 FMNMX3); NaN handling as fminf/fmaxf (returns the non-NaN operand).
+__device__ __forceinline__ float min3(float a, float b, float c) { float d; asm("min.f32 %0, %1, %2, %3;" : "=f"(d) : "f"(a), "f"(b), "f"(c)); return d; }
+__device__ __forceinline__ float max3(float a, float b, float c) { float d; asm("max.f32 %0, %1, %2, %3;" : "=f"(d) : "f"(a), "f"(b), "f"(c)); return d; }
+
+// packed squared distance of one query against two targets: d = {dist2(b0-q), dist2(b1-q)}
+// nq* hold the NEGATED query coordinate in both halves (b + (-q) == b - q exactly).
+__device__ __forceinline__ u64 dist2x2(u64 bx, u64 by, u64 bz, u64 nqx, u64 nqy, u64 nqz) {
+  u64 dx = add2(bx, nqx), dy = add2(by, nqy), dz = add2(bz, nqz);
+  return fma2(dz, dz, fma2(dx, dx, mul2(dy, dy)));
+}
+
+__device__ __forceinline__ unsigned smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
+
+// ---- thread-block cluster primitives ---------------------------------------------------------
+__device__ __forceinline__ unsigned cluster_ctarank() { unsigned r; asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r)); return r; }
+__device__ __forceinline__ unsigned cluster_nctarank() { unsigned r; asm volatile("mov.u32 %0, %%cluster_nctarank;" : "=r"(r)); return r; }
+__device__ __forceinline__ unsigned cluster_id_x() { unsigned r; asm volatile("mov.u32 %0, %%clusterid.x;" : "=r"(r)); return r; }
+__device__ __forceinline__ void cluster_arrive_release() { asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory"); }
+__device__ __forceinline__ void cluster_wait_acquire() { asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory"); }
+__device__ __forceinline__ unsigned mapa_shared(unsigned addr, unsigned rank) { unsigned r; asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(addr), "r"(rank)); return r; }
+__device__ __forceinline__ void st_cluster_v4(unsigned addr, unsigned a, unsigned b, unsigned c, unsigned d) {
+  asm volatile("st.shared::cluster.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
+}
+__device__ __forceinline__ void st_cluster_v2(unsigned addr, unsigned a, unsigned b) {
+  asm volatile("st.shared::cluster.v2.b32 [%0], {%1, %2};" ::"r"(addr), "r"(a), "r"(b) : "memory");
+}
+
+#endif  // __CUDACC__
+
+}  // namespace ps

@@ -1,0 +1,323 @@
+// gather_operation / grouping_operation forward + backward for sm_100a (HBM-bound).
+//
+// Replaces gather_points(_grad)_kernel (pointnet2_ops/_ext-src/src/sampling_gpu.cu:8-57) and
+// group_points(_grad)_kernel (group_points_gpu.cu:8-75).  Grouping IS gathering with the
+// (S,K) index tensor flattened to M' = S*K positions, so both ops share the kernels below.
+//
+//   forward   out[b,c,p] = feat[b,c,idx[b,p]]             feat (B,C,N), idx (B,M'), out (B,C,M')
+//   backward  gfeat[b,c,idx[b,p]] += gout[b,c,p]
+//
+// Algorithmic HBM bytes: 4*(B*M' + B*C*N + B*C*M') for group, 4*(B*M' + 2*B*C*M')
+// for a sparse gather.  The reference launches only B blocks for group_points and writes 4-byte
+// stores nsample floats apart; here:
+//   * "staged" kernel (output >> input): a CTA owns (cloud, CT-channel tile, position slice).
+//     The CT feature rows (contiguous N floats each) are pulled into shared memory with 1-D bulk
+//     async copies (cp.async.bulk, i.e. the TMA engine, completion on an mbarrier); every
+//     thread then loads 4 consecutive indices once (128-bit), gathers from shared memory and
+//     emits one 128-bit coalesced store per channel.  The feature tensor is read from HBM
+//     once, the index tensor once per channel tile, the output is written once.
+//   * "direct" kernel (sparse gather, or rows too long for shared memory): same thread
+//     mapping, gathers through L1/L2 with read-only loads.
+//   * backward mirrors it: the CT accumulator rows live in shared memory (RED.shared adds),
+//     and are written out once with plain coalesced stores (no global atomics, no pre-zeroed
+//     buffer); rows too long for shared memory fall back to memset + global RED.
+#include "common.cuh"
+
+namespace ps {
+
+constexpr int GG_THREADS = 256;
+
+__device__ __forceinline__ void mbar_init(unsigned bar, unsigned cnt) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(cnt) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(unsigned bar, unsigned bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(unsigned bar, unsigned parity) {
+  unsigned ok;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
+  return ok != 0;
+}
+__device__ __forceinline__ void bulk_g2s(unsigned dst, const void* src, unsigned bytes, unsigned bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+               ::"r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");
+}
+
+// ---- forward, shared-memory staged -----------------------------------------------------------
+// grid = (position slices, channel tiles, B); dynamic smem = CT * Npad floats (+ mbarrier)
+template <int CT>
+__global__ void __launch_bounds__(GG_THREADS) gather_staged_kernel(
+    const float* __restrict__ feat, const int* __restrict__ idx, float* __restrict__ out, int C,
+    int N, int Mp, int slice_len, int use_bulk, int vec_ok) {
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  u64* bar = reinterpret_cast<u64*>(smem_raw);
+  float* rows = reinterpret_cast<float*>(smem_raw + 128);
+  const int b = blockIdx.z, c0 = blockIdx.y * CT, tid = threadIdx.x;
+  const int nrows = min(CT, C - c0);
+  const float* src = feat + ((size_t)b * C + c0) * N;
+
+  if (use_bulk) {
+    if (tid == 0) {
+      mbar_init(smem_u32(bar), 1);
+      asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+    if (tid == 0) {
+      mbar_arrive_expect_tx(smem_u32(bar), (unsigned)(nrows * N * 4));
+      // rows are contiguous in global memory: one bulk copy per row keeps each request <= 64 KB
+      for (int r = 0; r < nrows; r++)
+        bulk_g2s(smem_u32(rows + (size_t)r * N), src + (size_t)r * N, (unsigned)(N * 4), smem_u32(bar));
+    }
+  } else {
+    for (int i = tid; i < nrows * N; i += GG_THREADS) rows[i] = __ldg(src + i);
+  }
+
+  // indices for this thread's 4 positions (loaded while the bulk copies are in flight)
+  const int p_begin = blockIdx.x * slice_len;
+  const int p_end = min(Mp, p_begin + slice_len);
+  const int* ib = idx + (size_t)b * Mp;
+  const bool vec = vec_ok != 0;  // Mp % 4 == 0 and 16-byte aligned idx/out bases (host-checked)
+
+  if (use_bulk) {
+    while (!mbar_try_wait(smem_u32(bar), 0)) {}
+  } else {
+    __syncthreads();
+  }
+
+  for (int p = p_begin + tid * 4; p < p_end; p += GG_THREADS * 4) {
+    int i0, i1, i2, i3;
+    const bool full = vec && (p + 4 <= p_end);
+    if (full) {
+      const int4 v = __ldg(reinterpret_cast<const int4*>(ib + p));
+      i0 = v.x; i1 = v.y; i2 = v.z; i3 = v.w;
+    } else {
+      i0 = __ldg(ib + p);
+      i1 = p + 1 < p_end ? __ldg(ib + p + 1) : 0;
+      i2 = p + 2 < p_end ? __ldg(ib + p + 2) : 0;
+      i3 = p + 3 < p_end ? __ldg(ib + p + 3) : 0;
+    }
+    float* ob = out + ((size_t)b * C + c0) * Mp + p;
+#pragma unroll
+    for (int r = 0; r < CT; r++) {
+      if (r < nrows) {
+        const float* row = rows + (size_t)r * N;
+        const float4 v = make_float4(row[i0], row[i1], row[i2], row[i3]);
+        float* o = ob + (size_t)r * Mp;
+        if (full) {
+          __stcs(reinterpret_cast<float4*>(o), v);  // streaming store: output is written once
+        } else {
+          o[0] = v.x;
+          if (p + 1 < p_end) o[1] = v.y;
+          if (p + 2 < p_end) o[2] = v.z;
+          if (p + 3 < p_end) o[3] = v.w;
+        }
+      }
+    }
+  }
+}
+
+// ---- forward, direct ----------------------------------------------------------------------------
+// grid = (position blocks, channel tiles, B)
+template <int CT>
+__global__ void __launch_bounds__(GG_THREADS) gather_direct_kernel(
+    const float* __restrict__ feat, const int* __restrict__ idx, float* __restrict__ out, int C,
+    int N, int Mp, int vec_ok) {
+  const int b = blockIdx.z, c0 = blockIdx.y * CT;
+  const int p = (blockIdx.x * GG_THREADS + threadIdx.x) * 4;
+  if (p >= Mp) return;
+  const int nrows = min(CT, C - c0);
+  const int* ib = idx + (size_t)b * Mp;
+  const bool full = (vec_ok != 0) && (p + 4 <= Mp);
+  int i0, i1, i2, i3;
+  if (full) {
+    const int4 v = __ldg(reinterpret_cast<const int4*>(ib + p));
+    i0 = v.x; i1 = v.y; i2 = v.z; i3 = v.w;
+  } else {
+    i0 = __ldg(ib + p);
+    i1 = p + 1 < Mp ? __ldg(ib + p + 1) : 0;
+    i2 = p + 2 < Mp ? __ldg(ib + p + 2) : 0;
+    i3 = p + 3 < Mp ? __ldg(ib + p + 3) : 0;
+  }
+  const float* src = feat + ((size_t)b * C + c0) * N;
+  float* ob = out + ((size_t)b * C + c0) * Mp + p;
+#pragma unroll
+  for (int r = 0; r < CT; r++) {
+    if (r < nrows) {
+      const float* row = src + (size_t)r * N;
+      const float4 v = make_float4(__ldg(row + i0), __ldg(row + i1), __ldg(row + i2), __ldg(row + i3));
+      float* o = ob + (size_t)r * Mp;
+      if (full) {
+        *reinterpret_cast<float4*>(o) = v;
+      } else {
+        o[0] = v.x;
+        if (p + 1 < Mp) o[1] = v.y;
+        if (p + 2 < Mp) o[2] = v.z;
+        if (p + 3 < Mp) o[3] = v.w;
+      }
+    }
+  }
+}
+
+// ---- backward, shared-memory accumulators -------------------------------------------------------
+// grid = (1, channel tiles, B); dynamic smem = CT * N floats
+template <int CT>
+__global__ void __launch_bounds__(GG_THREADS) scatter_staged_kernel(
+    const float* __restrict__ gout, const int* __restrict__ idx, float* __restrict__ gfeat, int C,
+    int N, int Mp, int vec_ok) {
+  extern __shared__ __align__(16) float acc[];
+  const int b = blockIdx.z, c0 = blockIdx.y * CT, tid = threadIdx.x;
+  const int nrows = min(CT, C - c0);
+  for (int i = tid; i < nrows * N; i += GG_THREADS) acc[i] = 0.f;
+  __syncthreads();
+  const int* ib = idx + (size_t)b * Mp;
+  const bool vec = vec_ok != 0;
+  for (int p = tid * 4; p < Mp; p += GG_THREADS * 4) {
+    int ii[4];
+    const bool full = vec && (p + 4 <= Mp);
+    if (full) {
+      const int4 v = __ldg(reinterpret_cast<const int4*>(ib + p));
+      ii[0] = v.x; ii[1] = v.y; ii[2] = v.z; ii[3] = v.w;
+    } else {
+#pragma unroll
+      for (int e = 0; e < 4; e++) ii[e] = p + e < Mp ? __ldg(ib + p + e) : -1;
+    }
+    const float* gb = gout + ((size_t)b * C + c0) * Mp + p;
+#pragma unroll
+    for (int r = 0; r < CT; r++) {
+      if (r < nrows) {
+        float v[4];
+        if (full) {
+          const float4 t = __ldcs(reinterpret_cast<const float4*>(gb + (size_t)r * Mp));
+          v[0] = t.x; v[1] = t.y; v[2] = t.z; v[3] = t.w;
+        } else {
+#pragma unroll
+          for (int e = 0; e < 4; e++) v[e] = p + e < Mp ? gb[(size_t)r * Mp + e] : 0.f;
+        }
+#pragma unroll
+        for (int e = 0; e < 4; e++)
+          if (ii[e] >= 0) atomicAdd(&acc[(size_t)r * N + ii[e]], v[e]);
+      }
+    }
+  }
+  __syncthreads();
+  float* dst = gfeat + ((size_t)b * C + c0) * N;
+  for (int i = tid; i < nrows * N; i += GG_THREADS) dst[i] = acc[i];
+}
+
+// ---- backward, global atomics (rows too long for shared memory; gfeat pre-zeroed by us) --------
+__global__ void __launch_bounds__(GG_THREADS) scatter_direct_kernel(
+    const float* __restrict__ gout, const int* __restrict__ idx, float* __restrict__ gfeat, int C,
+    int N, int Mp) {
+  const int b = blockIdx.z, c = blockIdx.y;
+  const int p = blockIdx.x * GG_THREADS + threadIdx.x;
+  if (p >= Mp) return;
+  const int i = __ldg(idx + (size_t)b * Mp + p);
+  atomicAdd(gfeat + ((size_t)b * C + c) * N + i, __ldg(gout + ((size_t)b * C + c) * Mp + p));
+}
+
+static const size_t GG_SMEM_MAX = 200 * 1024;
+
+static int gather_fwd_impl(const float* feat, const int* idx, float* out, int B, int C, int N,
+                           int Mp, int dev, cudaStream_t stream, const char* who) {
+  PS_REQUIRE(B >= 0 && C >= 0 && N > 0 && Mp >= 0, "%s: bad sizes B=%d C=%d N=%d M=%d", who, B, C, N, Mp);
+  if (B == 0 || C == 0 || Mp == 0) return PS_OK;
+  PS_REQUIRE(feat && idx && out, "%s: null pointer", who);
+  PS_REQUIRE(B <= 65535, "%s: B=%d exceeds the grid z limit", who, B);
+  DeviceGuard guard(dev);
+  if (!guard.ok) return set_error(PS_ERR_CUDA, "%s: cannot select device %d", who, dev);
+  const int nsm = sm_count(dev);
+  const int vec_ok = ((Mp & 3) == 0) && ((reinterpret_cast<uintptr_t>(idx) & 15) == 0) && ((reinterpret_cast<uintptr_t>(out) & 15) == 0);
+  // Stage through shared memory when each feature element is reused (output >= 2x the input)
+  // and 8 rows fit; otherwise gather straight from L1/L2.
+  constexpr int CT = 8;
+  const size_t row_bytes = (size_t)N * 4;
+  const bool staged = (long long)Mp >= 2ll * N && row_bytes * CT + 128 <= GG_SMEM_MAX / 2 && C >= 2;
+  if (staged) {
+    const size_t smem = 128 + row_bytes * CT;
+    const int ctiles = ceil_div(C, CT);
+    // slices so that the grid covers ~4 CTAs per SM; each slice a multiple of 1024 positions
+    int nslice = ceil_div((long long)nsm * 4, (long long)B * ctiles);
+    const int max_slice = ceil_div(Mp, GG_THREADS * 4 * 2);
+    if (nslice > max_slice) nslice = max_slice;
+    if (nslice < 1) nslice = 1;
+    int slice_len = ceil_div(Mp, nslice);
+    slice_len = (slice_len + 1023) / 1024 * 1024;
+    nslice = ceil_div(Mp, slice_len);
+    const int use_bulk = ((N & 3) == 0) && ((reinterpret_cast<uintptr_t>(feat) & 15) == 0) && row_bytes <= 65536 * 4;
+    auto kern = gather_staged_kernel<CT>;
+    PS_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    kern<<<dim3(nslice, ctiles, B), GG_THREADS, smem, stream>>>(feat, idx, out, C, N, Mp, slice_len, use_bulk, vec_ok);
+    PS_LAUNCH_CHECK();
+  } else {
+    constexpr int CTD = 4;
+    gather_direct_kernel<CTD><<<dim3(ceil_div(Mp, GG_THREADS * 4), ceil_div(C, CTD), B), GG_THREADS, 0, stream>>>(feat, idx, out, C, N, Mp, vec_ok);
+    PS_LAUNCH_CHECK();
+  }
+  return PS_OK;
+}
+
+static int gather_bwd_impl(const float* gout, const int* idx, float* gfeat, int B, int C, int N,
+                           int Mp, int dev, cudaStream_t stream, const char* who) {
+  PS_REQUIRE(B >= 0 && C >= 0 && N > 0 && Mp >= 0, "%s: bad sizes B=%d C=%d N=%d M=%d", who, B, C, N, Mp);
+  if (B == 0 || C == 0) return PS_OK;
+  PS_REQUIRE(gfeat && (Mp == 0 || (gout && idx)), "%s: null pointer", who);
+  PS_REQUIRE(B <= 65535 && C <= 65535, "%s: B or C exceeds the grid limit", who);
+  DeviceGuard guard(dev);
+  if (!guard.ok) return set_error(PS_ERR_CUDA, "%s: cannot select device %d", who, dev);
+  const size_t row_bytes = (size_t)N * 4;
+  if (Mp == 0) {
+    PS_CUDA(cudaMemsetAsync(gfeat, 0, (size_t)B * C * row_bytes, stream));
+    return PS_OK;
+  }
+  const int vec_ok = ((Mp & 3) == 0) && ((reinterpret_cast<uintptr_t>(idx) & 15) == 0) && ((reinterpret_cast<uintptr_t>(gout) & 15) == 0);
+  int ct = 0;
+  if (row_bytes * 8 <= GG_SMEM_MAX / 2) ct = 8;
+  else if (row_bytes * 4 <= GG_SMEM_MAX) ct = 4;
+  else if (row_bytes * 2 <= GG_SMEM_MAX) ct = 2;
+  else if (row_bytes <= GG_SMEM_MAX) ct = 1;
+  if (ct) {
+    const size_t smem = row_bytes * ct;
+    const dim3 grid(1, ceil_div(C, ct), B);
+#define PS_SCATTER(CTV)                                                                          \
+  {                                                                                              \
+    auto kern = scatter_staged_kernel<CTV>;                                                      \
+    PS_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+    kern<<<grid, GG_THREADS, smem, stream>>>(gout, idx, gfeat, C, N, Mp, vec_ok);                        \
+  }
+    if (ct == 8) PS_SCATTER(8) else if (ct == 4) PS_SCATTER(4) else if (ct == 2) PS_SCATTER(2) else PS_SCATTER(1)
+#undef PS_SCATTER
+    PS_LAUNCH_CHECK();
+  } else {
+    PS_CUDA(cudaMemsetAsync(gfeat, 0, (size_t)B * C * row_bytes, stream));
+    scatter_direct_kernel<<<dim3(ceil_div(Mp, GG_THREADS), C, B), GG_THREADS, 0, stream>>>(gout, idx, gfeat, C, N, Mp);
+    PS_LAUNCH_CHECK();
+  }
+  return PS_OK;
+}
+
+}  // namespace ps
+
+using namespace ps;
+
+extern "C" int ps_gather_fwd(const float* features, const int* idx, float* out, int B, int C,
+                             int N, int M, int dev, void* stream) {
+  return gather_fwd_impl(features, idx, out, B, C, N, M, dev, (cudaStream_t)stream, "ps_gather_fwd");
+}
+extern "C" int ps_gather_bwd(const float* grad_out, const int* idx, float* grad_features, int B,
+                             int C, int N, int M, int dev, void* stream) {
+  return gather_bwd_impl(grad_out, idx, grad_features, B, C, N, M, dev, (cudaStream_t)stream, "ps_gather_bwd");
+}
+extern "C" int ps_group_fwd(const float* features, const int* idx, float* out, int B, int C, int N,
+                            int S, int K, int dev, void* stream) {
+  PS_REQUIRE(S >= 0 && K >= 0 && (long long)S * K < (1ll << 31), "ps_group_fwd: bad S=%d K=%d", S, K);
+  return gather_fwd_impl(features, idx, out, B, C, N, S * K, dev, (cudaStream_t)stream, "ps_group_fwd");
+}
+extern "C" int ps_group_bwd(const float* grad_out, const int* idx, float* grad_features, int B,
+                            int C, int N, int S, int K, int dev, void* stream) {
+  PS_REQUIRE(S >= 0 && K >= 0 && (long long)S * K < (1ll << 31), "ps_group_bwd: bad S=%d K=%d", S, K);
+  return gather_bwd_impl(grad_out, idx, grad_features, B, C, N, S * K, dev, (cudaStream_t)stream, "ps_group_bwd");
+}

@@ -1,0 +1,104 @@
+// Library plumbing: error strings, device queries, launch counter, fp32 peak probe.
+#include "common.cuh"
+
+#include <cstring>
+
+namespace ps {
+
+char* err_buf() {
+  static thread_local char buf[512] = {0};
+  return buf;
+}
+long long& launch_counter() {
+  static thread_local long long n = 0;
+  return n;
+}
+int set_error(int code, const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(err_buf(), 512, fmt, ap);
+  va_end(ap);
+  return code;
+}
+
+int sm_count(int dev) {
+  // per-device cache; benign race (every writer stores the same value)
+  static int cache[64] = {0};
+  if (dev >= 0 && dev < 64 && cache[dev]) return cache[dev];
+  int n = 0;
+  if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0) n = 148;
+  if (dev >= 0 && dev < 64) cache[dev] = n;
+  return n;
+}
+
+// FFMA2-only kernel: 16 independent packed accumulators per thread.
+constexpr int PEAK_ITERS = 2048;
+__global__ void __launch_bounds__(256) fp32_peak_kernel(float* out, float a, float b) {
+  u64 acc[16];
+  const u64 a2 = pack2(a, a), b2 = pack2(b, b);
+#pragma unroll
+  for (int i = 0; i < 16; i++) acc[i] = pack2(threadIdx.x * 0.001f + i, (float)i);
+  for (int it = 0; it < PEAK_ITERS; it++) {
+#pragma unroll
+    for (int i = 0; i < 16; i++) asm volatile("fma.rn.f32x2 %0, %0, %1, %2;" : "+l"(acc[i]) : "l"(a2), "l"(b2));
+  }
+  float s = 0.f;
+#pragma unroll
+  for (int i = 0; i < 16; i++) s += lo2(acc[i]) + hi2(acc[i]);
+  out[blockIdx.x * blockDim.x + threadIdx.x] = s;
+}
+
+}  // namespace ps
+
+using namespace ps;
+
+extern "C" int ps_version(void) { return 100; }  // 0.1.0
+
+extern "C" const char* ps_last_error(void) { return err_buf(); }
+
+extern "C" int ps_device_info(int dev, int* sm, int* major, int* minor) {
+  int a = 0, b = 0, c = 0;
+  PS_CUDA(cudaDeviceGetAttribute(&a, cudaDevAttrMultiProcessorCount, dev));
+  PS_CUDA(cudaDeviceGetAttribute(&b, cudaDevAttrComputeCapabilityMajor, dev));
+  PS_CUDA(cudaDeviceGetAttribute(&c, cudaDevAttrComputeCapabilityMinor, dev));
+  if (sm) *sm = a;
+  if (major) *major = b;
+  if (minor) *minor = c;
+  return PS_OK;
+}
+
+extern "C" long long ps_launch_count(int reset) {
+  const long long n = launch_counter();
+  if (reset) launch_counter() = 0;
+  return n;
+}
+
+extern "C" int ps_measure_fp32_peak(int dev, int reps, double* tflops) {
+  PS_REQUIRE(tflops != nullptr && reps > 0, "ps_measure_fp32_peak: bad arguments");
+  DeviceGuard guard(dev);
+  if (!guard.ok) return set_error(PS_ERR_CUDA, "ps_measure_fp32_peak: cannot select device %d", dev);
+  const int grid = sm_count(dev) * 16, threads = 256;
+  float* out = nullptr;
+  PS_CUDA(cudaMalloc((void**)&out, (size_t)grid * threads * sizeof(float)));
+  cudaEvent_t e0, e1;
+  PS_CUDA(cudaEventCreate(&e0));
+  PS_CUDA(cudaEventCreate(&e1));
+  fp32_peak_kernel<<<grid, threads>>>(out, 1.0001f, 0.5f);
+  PS_CUDA(cudaDeviceSynchronize());
+  float best = 1e30f;
+  for (int r = 0; r < reps; r++) {
+    PS_CUDA(cudaEventRecord(e0));
+    fp32_peak_kernel<<<grid, threads>>>(out, 1.0001f, 0.5f);
+    PS_CUDA(cudaEventRecord(e1));
+    PS_CUDA(cudaEventSynchronize(e1));
+    float ms = 0.f;
+    PS_CUDA(cudaEventElapsedTime(&ms, e0, e1));
+    if (ms < best) best = ms;
+  }
+  cudaEventDestroy(e0);
+  cudaEventDestroy(e1);
+  cudaFree(out);
+  const double flops = (double)grid * threads * PEAK_ITERS * 16.0 * 4.0;  // 2 lanes x (mul+add)
+  *tflops = flops / (best * 1e-3) / 1e12;
+  return PS_OK;
+}
