@@ -1,0 +1,82 @@
+"""Batch sharding + the single loss/metric reduction.
+
+Every op on the hot path is independent per cloud, so ranks never exchange points: rank r owns
+clouds [B*r//G, B*(r+1)//G).  The only collective is ONE all-reduce(sum) of a small vector of
+partial sums and element counts (utils/loss_utils.py:10-19,50-57 define what is summed); the
+division happens after the reduce so uneven shards stay exact.  Backend: NCCL over
+NVLink/NVSwitch on GPUs, gloo in the CPU tests.
+"""
+import torch
+import torch.distributed as dist
+
+
+def shard_bounds(B, rank, world):
+    """Clouds [lo, hi) of a batch of B owned by `rank` out of `world` (uneven shards allowed)."""
+    return (B * rank) // world, (B * (rank + 1)) // world
+
+
+def shard_batch(t, rank=None, world=None):
+    """Contiguous batch shard of a tensor whose dim 0 is the cloud index."""
+    if rank is None:
+        rank = dist.get_rank() if dist.is_initialized() else 0
+    if world is None:
+        world = dist.get_world_size() if dist.is_initialized() else 1
+    lo, hi = shard_bounds(t.size(0), rank, world)
+    return t[lo:hi].contiguous()
+
+
+class LossSums:
+    """Accumulates named (sum, count) pairs on the device and reduces them with one all-reduce.
+
+    add("cd2.d1", values) records sum(values) and values.numel(); reduce() all-reduces the whole
+    vector once (enqueued on the current stream, no host sync) and returns {name: global mean}.
+    """
+
+    def __init__(self, device, dtype=torch.float32):
+        self.device, self.dtype = device, dtype
+        self.names, self.parts = [], []
+
+    def add(self, name, values):
+        self.names.append(name)
+        self.parts.append(values.sum(dtype=self.dtype).reshape(1))
+        self.parts.append(torch.full((1,), float(values.numel()), device=self.device, dtype=self.dtype))
+
+    def reduce(self, group=None):
+        vec = torch.cat(self.parts) if self.parts else torch.zeros(0, device=self.device, dtype=self.dtype)
+        if dist.is_initialized() and dist.get_world_size(group) > 1 and vec.numel():
+            dist.all_reduce(vec, op=dist.ReduceOp.SUM, group=group)
+        out = {}
+        for i, name in enumerate(self.names):
+            out[name] = vec[2 * i] / vec[2 * i + 1]
+        return out
+
+
+def chamfer_loss_terms(sums, name, d1, d2, sqrt=True):
+    """Registers the two directional means of one Chamfer term (chamfer / chamfer_sqrt,
+    utils/loss_utils.py:10-19)."""
+    sums.add(name + ".d1", torch.sqrt(d1) if sqrt else d1)
+    sums.add(name + ".d2", torch.sqrt(d2) if sqrt else d2)
+
+
+def combine_chamfer(means, name, sqrt=True):
+    m1, m2 = means[name + ".d1"], means[name + ".d2"]
+    return (m1 + m2) / 2 if sqrt else m1 + m2
+
+
+def get_loss_sharded(pcds_pred, gt, sqrt=True, alpha1=1, alpha2=1, group=None):
+    """utils/loss_utils.get_loss (:33-58) on a batch shard: identical value on every rank, equal
+    to the single-process loss over the concatenated batch.  Gradients flow through the local
+    Chamfer terms (scale by world size is already contained in the global mean)."""
+    from .chamfer import chamfer_3DFunction
+    from .pointnet2_utils import fps_subsample
+
+    Pc, P1, P2 = pcds_pred
+    gt_1 = fps_subsample(gt, P1.shape[1])
+    gt_c = fps_subsample(gt_1, Pc.shape[1])
+    sums = LossSums(gt.device)
+    for name, (p, q) in {"cdc": (Pc, gt_c), "cd1": (P1, gt_1), "cd2": (P2, gt)}.items():
+        d1, d2, _, _ = chamfer_3DFunction.apply(p.contiguous(), q.contiguous())
+        chamfer_loss_terms(sums, name, d1, d2, sqrt)
+    means = sums.reduce(group)
+    cdc, cd1, cd2 = (combine_chamfer(means, n, sqrt) for n in ("cdc", "cd1", "cd2"))
+    return cdc + alpha1 * cd1 + alpha2 * cd2, [cdc, cd1, cd2]
