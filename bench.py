@@ -1,0 +1,425 @@
+#!/usr/bin/env python
+"""bench.py — headline measurement of the point-geometry hot path on B200.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
+
+Workload (BASELINE.json configs[0], "C1"): Chamfer L2 forward + backward, B=32 clouds per GPU,
+partial 2048 points vs ground truth 16384 points, fp32, synthetic `rand - 0.5` clouds.
+  step   = chamfer forward (both directions, argmin indices) + loss partial sums
+           (+ ONE NCCL all-reduce of those sums when N > 1) + chamfer backward
+  value  = 2*B*N*M pair evaluations per step (the reference evaluates both directions) * N_gpus
+           / max-over-ranks device time, in Gpair/s, inputs resident in HBM
+  e2e    = the same through the public API with HOST (pinned) buffers: H2D of both clouds and
+           the upstream gradients, the step, D2H of dist/idx/gradients, all inside the timed region
+  ops    = the other hot-path ops at their BASELINE configs (C2 FPS+gather, C3 kNN+group),
+           each timed with CUDA events: sampled pts/s, query pts/s, GB/s
+  roofline = dominant kernel (chamfer_nn_kernel): algorithmic 8 flop per pair evaluation over
+           the forward's device time against the fp32 FFMA2 peak measured live in this run
+           (MEASURED_PEAKS.json carries no fp32 figure); roofline_hbm = group forward against
+           MEASURED_PEAKS.json hbm_gbs.
+  cpu_baseline = pure-PyTorch re-expression on the host cores (oracle/oracle.py), bounded sample.
+`--impl reference` times that CPU expression alone (the reference has no CPU kernel of its own;
+metrics/CD/chamfer_python.py is its pure-torch restatement) on the same config/metric.
+"""
+import argparse
+import json
+import os
+import os.path as osp
+import statistics
+import sys
+import threading
+import time
+
+ROOT = osp.dirname(osp.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+import torch  # noqa: E402
+
+C1 = dict(B=32, N=2048, M=16384)
+C2 = dict(B=32, N=16384, npoint=2048)
+C3 = dict(B=32, N=2048, S=2048, k=16, C=128)
+FLOP_PER_PAIR = 8  # 3 sub, 1 mul, 2 fma
+WORKLOAD = "C1 chamfer L2 fwd+bwd B=32/GPU, 2048 vs 16384 pts, fp32 (PCN eval shape)"
+
+
+def measured_peaks():
+    p = osp.join(ROOT, "MEASURED_PEAKS.json")
+    if osp.exists(p):
+        with open(p) as f:
+            return json.load(f), "MEASURED_PEAKS.json"
+    return {"hbm_gbs": 6650.0}, "fallback (B200_PROFILING.md)"
+
+
+def make_cloud(g, B, N):
+    return (torch.rand(B, N, 3, generator=g) - 0.5).contiguous()
+
+
+class ClockSampler(threading.Thread):
+    """Samples SM clock + throttle reasons through NVML while the timed region runs."""
+
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index, self.samples, self.reasons, self.max_mhz = index, [], set(), None
+        self._stop_evt = threading.Event()
+        self.ok = False
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            # NVML enumerates physical devices; honour CUDA_VISIBLE_DEVICES when it is a plain list
+            vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+            phys = index
+            if vis:
+                try:
+                    phys = int(vis.split(",")[index])
+                except Exception:
+                    phys = index
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(phys)
+            self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)
+            self.ok = True
+        except Exception:
+            self.ok = False
+
+    def run(self):
+        if not self.ok:
+            return
+        nv = self.nv
+        names = {
+            getattr(nv, "nvmlClocksEventReasonHwSlowdown", 0x8): "hw_slowdown",
+            getattr(nv, "nvmlClocksEventReasonHwThermalSlowdown", 0x40): "hw_thermal_slowdown",
+            getattr(nv, "nvmlClocksEventReasonSwThermalSlowdown", 0x20): "sw_thermal_slowdown",
+            getattr(nv, "nvmlClocksEventReasonSwPowerCap", 0x4): "sw_power_cap",
+            getattr(nv, "nvmlClocksEventReasonHwPowerBrakeSlowdown", 0x80): "hw_power_brake",
+        }
+        while not self._stop_evt.is_set():
+            try:
+                self.samples.append(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM))
+                try:
+                    r = nv.nvmlDeviceGetCurrentClocksEventReasons(self.h)
+                except Exception:
+                    r = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+                for bit, name in names.items():
+                    if r & bit:
+                        self.reasons.add(name)
+            except Exception:
+                pass
+            time.sleep(0.02)
+
+    def stop(self):
+        self._stop_evt.set()
+        if self.is_alive():
+            self.join(timeout=1.0)
+        busy = [s for s in self.samples if s > 300] or self.samples
+        return {"sm_mhz": statistics.median(busy) if busy else None, "sm_max_mhz": self.max_mhz,
+                "reasons": sorted(self.reasons), "samples": len(self.samples)}
+
+
+def timed(fn, iters, warmup, flush):
+    """CUDA-event timing of fn() on the current stream: list of ms, L2 flushed between iterations."""
+    for _ in range(warmup):
+        fn()
+    torch.cuda.synchronize()
+    out = []
+    for _ in range(iters):
+        flush()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        fn()
+        e1.record()
+        e1.synchronize()
+        out.append(e0.elapsed_time(e1))
+    return out
+
+
+# ------------------------------------------------------------------------------------------------
+def run_ours(args):
+    import torch.distributed as dist
+    import svdformer_pointsea_b200 as ps
+    from svdformer_pointsea_b200 import _lib as L
+    from svdformer_pointsea_b200 import pointnet2_utils as pu
+    from svdformer_pointsea_b200.dist import LossSums, chamfer_loss_terms
+
+    rank = int(os.environ.get("RANK", 0))
+    local_rank = int(os.environ.get("LOCAL_RANK", 0))
+    world = int(os.environ.get("WORLD_SIZE", 1))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device; the product path has no CPU fallback")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    ps.load_library()
+    peaks, peaks_src = measured_peaks()
+
+    B, N, M = C1["B"], C1["N"], C1["M"]
+    g = torch.Generator().manual_seed(1234 + 1 + rank)
+    h_x1, h_x2 = make_cloud(g, B, N).pin_memory(), make_cloud(g, B, M).pin_memory()
+    h_gd1, h_gd2 = torch.randn(B, N, generator=g).pin_memory(), torch.randn(B, M, generator=g).pin_memory()
+    x1, x2, gd1, gd2 = (t.to(dev) for t in (h_x1, h_x2, h_gd1, h_gd2))
+    flush_buf = torch.empty(256 << 20, dtype=torch.uint8, device=dev)  # 256 MB > 126 MB L2
+
+    def flush():
+        flush_buf.zero_()
+
+    fwd_ms = []
+
+    def step(record_fwd=False):
+        if record_fwd:
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+        d1, d2, i1, i2 = ps.chamfer_forward(x1, x2)
+        if record_fwd:
+            e1.record()
+            fwd_ms.append((e0, e1))
+        sums = LossSums(dev)
+        chamfer_loss_terms(sums, "cd", d1, d2, sqrt=True)
+        means = sums.reduce()  # ONE all-reduce when world > 1
+        g1, g2 = ps.chamfer_backward(x1, x2, gd1, gd2, i1, i2)
+        return means, g1, g2
+
+    # ---- warm-up, fp32 peak, then the timed K steps -------------------------------------------
+    for _ in range(max(args.warmup, 3)):
+        step()
+    torch.cuda.synchronize()
+    fp32_peak = L.measure_fp32_peak(local_rank, 5)
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    L.launch_count(reset=True)
+    evs = []
+    for _ in range(args.steps):
+        flush()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        step(record_fwd=True)
+        e1.record()
+        evs.append((e0, e1))
+    torch.cuda.synchronize()
+    launches = L.launch_count(reset=True)
+    if world > 1:
+        dist.barrier()
+    total_ms = sum(a.elapsed_time(b) for a, b in evs)
+    fwd_avg_ms = sum(a.elapsed_time(b) for a, b in fwd_ms) / len(fwd_ms)
+    tt = torch.tensor([total_ms], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+    total_ms = float(tt.item())
+    ms_per_step = total_ms / args.steps
+    pairs_per_step = 2.0 * B * N * M
+    value = pairs_per_step * world / (ms_per_step * 1e-3) / 1e9  # Gpair/s, whole job
+
+    # ---- e2e: host buffers in, host buffers out -----------------------------------------------
+    h_out = [torch.empty(B, N).pin_memory(), torch.empty(B, M).pin_memory(),
+             torch.empty(B, N, dtype=torch.int32).pin_memory(), torch.empty(B, M, dtype=torch.int32).pin_memory(),
+             torch.empty(B, N, 3).pin_memory(), torch.empty(B, M, 3).pin_memory()]
+    h2d = sum(t.numel() * t.element_size() for t in (h_x1, h_x2, h_gd1, h_gd2))
+    d2h = sum(t.numel() * t.element_size() for t in h_out)
+
+    def e2e_step():
+        a = h_x1.to(dev, non_blocking=True)
+        b = h_x2.to(dev, non_blocking=True)
+        ga = h_gd1.to(dev, non_blocking=True)
+        gb = h_gd2.to(dev, non_blocking=True)
+        d1, d2, i1, i2 = ps.chamfer_forward(a, b)
+        g1, g2 = ps.chamfer_backward(a, b, ga, gb, i1, i2)
+        for dst, src in zip(h_out, (d1, d2, i1, i2, g1, g2)):
+            dst.copy_(src, non_blocking=True)
+
+    e2e_ms = timed(e2e_step, args.steps, max(args.warmup, 3), flush)
+    te = torch.tensor([sum(e2e_ms)], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(te, op=dist.ReduceOp.MAX)
+    e2e_value = pairs_per_step * world / (float(te.item()) / args.steps * 1e-3) / 1e9
+    clocks = sampler.stop()
+
+    result = {
+        "metric": "chamfer_fwd_bwd_gpair_per_s", "value": round(value, 2), "unit": "Gpair/s",
+        "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": round(ms_per_step, 4),
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": WORKLOAD, "B_per_gpu": B, "N": N, "M": M,
+                   "l2": "256 MB buffer written between timed iterations (L2 flush)",
+                   "collective": "one all-reduce(sum) of 4 loss partial sums per step" if world > 1 else "none (1 GPU)",
+                   "parallelism": f"batch-sharded x{world}"},
+        "e2e": {"value": round(e2e_value, 2), "unit": "Gpair/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
+        "gpu_launches": int(launches),
+        "clocks": clocks,
+        "roofline": {"kernel": "chamfer_nn_kernel (forward, both directions)", "bound": "fp32",
+                     "achieved": round(pairs_per_step * FLOP_PER_PAIR / (fwd_avg_ms * 1e-3) / 1e12, 2),
+                     "peak": round(fp32_peak, 2), "unit": "TFLOP/s",
+                     "frac": round(pairs_per_step * FLOP_PER_PAIR / (fwd_avg_ms * 1e-3) / 1e12 / fp32_peak, 4),
+                     "peak_source": "FFMA2 microkernel measured live in this run (MEASURED_PEAKS.json has no fp32 figure)",
+                     "structural_ceiling_frac": round(8.0 / 12.0, 4),
+                     "fwd_ms": round(fwd_avg_ms, 4), "gpair_per_s_fwd": round(pairs_per_step / (fwd_avg_ms * 1e-3) / 1e9, 1),
+                     "traffic": None},
+    }
+
+    # ---- the other hot-path ops at their own configs (rank-local, device-timed) ---------------
+    if not args.no_ops:
+        result["ops"] = bench_ops(ps, pu, dev, flush, peaks, peaks_src, rank)
+        result["roofline_hbm"] = result["ops"]["group_fwd"]["roofline"]
+    if rank == 0 and world == 1 and not args.no_cpu:
+        result["cpu_baseline"] = cpu_chamfer_baseline(budget_s=12.0)
+        if "ops" in result:
+            result["ops"]["cpu"] = cpu_ops_baseline()
+    if rank == 0:
+        print(json.dumps(result))
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+def bench_ops(ps, pu, dev, flush, peaks, peaks_src, rank):
+    from svdformer_pointsea_b200 import _lib as L
+    out = {}
+    g = torch.Generator().manual_seed(1234 + 2 + rank)
+    # C2: FPS + gather
+    xyz = make_cloud(g, C2["B"], C2["N"]).to(dev)
+    xyz_t = xyz.transpose(1, 2).contiguous()
+    holder = {}
+
+    def fps_fn():
+        holder["idx"] = ps.furthest_point_sample(xyz, C2["npoint"])
+
+    ms = timed(fps_fn, 5, 2, flush)
+    t = min(ms) * 1e-3
+    out["fps"] = {"config": "C2 B=32 N=16384 -> 2048", "ms": round(min(ms), 4), "ms_median": round(statistics.median(ms), 4),
+                  "sampled_pts_per_s": round(C2["B"] * C2["npoint"] / t, 1),
+                  "gpair_per_s": round(C2["B"] * (C2["npoint"] - 1) * C2["N"] / t / 1e9, 2),
+                  "us_per_iteration": round(t * 1e6 / (C2["npoint"] - 1), 4)}
+    idx = holder["idx"]
+    ms = timed(lambda: ps.gather_operation(xyz_t, idx), 20, 3, flush)
+    byts = 4 * (C2["B"] * C2["npoint"] + 2 * C2["B"] * 3 * C2["npoint"])
+    out["gather_fwd"] = {"config": "C2 (32,3,16384) -> (32,3,2048)", "ms": round(min(ms), 4),
+                         "gbs": round(byts / (min(ms) * 1e-3) / 1e9, 2), "note": "launch-latency bound (1.8 MB)"}
+    # C3: kNN + group
+    g = torch.Generator().manual_seed(1234 + 3 + rank)
+    pts = make_cloud(g, C3["B"], C3["N"]).to(dev)
+    feat = torch.randn(C3["B"], C3["C"], C3["N"], generator=g).to(dev)
+
+    def knn_fn():
+        holder["knn"] = ps.query_knn(C3["k"], pts, pts)
+
+    ms = timed(knn_fn, 10, 3, flush)
+    t = min(ms) * 1e-3
+    out["knn"] = {"config": "C3 B=32 N=S=2048 k=16", "ms": round(min(ms), 4), "ms_median": round(statistics.median(ms), 4),
+                  "query_pts_per_s": round(C3["B"] * C3["S"] / t, 1),
+                  "gpair_per_s": round(C3["B"] * C3["S"] * C3["N"] / t / 1e9, 2)}
+    kidx = holder["knn"]
+
+    def grp_fn():
+        holder["grp"] = pu.group_raw(feat, kidx)
+
+    ms = timed(grp_fn, 20, 3, flush)
+    byts = 4 * (C3["B"] * C3["S"] * C3["k"] + C3["B"] * C3["C"] * C3["N"] + C3["B"] * C3["C"] * C3["S"] * C3["k"])
+    t = statistics.median(ms) * 1e-3
+    out["group_fwd"] = {"config": "C3 (32,128,2048) x idx (32,2048,16) -> (32,128,2048,16)", "ms": round(min(ms), 4),
+                        "ms_median": round(statistics.median(ms), 4),
+                        "roofline": {"kernel": "gather_staged_kernel (grouping_operation forward)", "bound": "hbm",
+                                     "achieved": round(byts / t / 1e9, 1), "peak": peaks["hbm_gbs"], "unit": "GB/s",
+                                     "frac": round(byts / t / 1e9 / peaks["hbm_gbs"], 4), "peak_source": peaks_src,
+                                     "algorithmic_bytes": byts, "traffic": None}}
+    go = torch.randn_like(holder["grp"])
+    ms = timed(lambda: pu.group_grad_raw(go, kidx, C3["N"]), 20, 3, flush)
+    t = statistics.median(ms) * 1e-3
+    out["group_bwd"] = {"ms": round(min(ms), 4), "ms_median": round(statistics.median(ms), 4),
+                        "gbs": round(byts / t / 1e9, 1), "frac_hbm": round(byts / t / 1e9 / peaks["hbm_gbs"], 4)}
+    del go, holder
+    return out
+
+
+# ------------------------------------------------------------------------------------------------
+def _cpu_chamfer_once(bs, seed=1234 + 1):
+    from oracle import oracle as O
+    g = torch.Generator().manual_seed(seed)
+    a, b = make_cloud(g, bs, C1["N"]), make_cloud(g, bs, C1["M"])
+    gd1, gd2 = torch.randn(bs, C1["N"], generator=g), torch.randn(bs, C1["M"], generator=g)
+    t0 = time.perf_counter()
+    O.torch_chamfer_fwd_bwd(a, b, gd1, gd2)
+    return time.perf_counter() - t0
+
+
+def cpu_chamfer_baseline(budget_s=12.0):
+    """Pure-torch direct-form Chamfer fwd+bwd on the host cores, bounded sample of C1."""
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    _cpu_chamfer_once(1)  # warm the allocator / thread pool
+    t1 = _cpu_chamfer_once(1)
+    bs = int(max(1, min(C1["B"], budget_s / max(t1, 1e-3))))
+    t = _cpu_chamfer_once(bs)
+    pairs = 2.0 * bs * C1["N"] * C1["M"]
+    return {"value": round(pairs / t / 1e9, 4), "unit": "Gpair/s", "cores": torch.get_num_threads(), "kind": "port",
+            "sample": f"{bs} of the 32 C1 clouds (2048 vs 16384), pure-torch direct-form fwd+bwd (autograd), {t:.2f} s"}
+
+
+def cpu_ops_baseline():
+    from oracle import oracle as O
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    out = {"cores": torch.get_num_threads()}
+    g = torch.Generator().manual_seed(1234 + 2)
+    xyz = make_cloud(g, C2["B"], C2["N"])
+    npnt = 128  # iterations have uniform cost: time 127 of the 2047 and scale
+    t0 = time.perf_counter(); O.torch_fps(xyz, npnt); t = time.perf_counter() - t0
+    full = t * (C2["npoint"] - 1) / (npnt - 1)
+    out["fps"] = {"sampled_pts_per_s": round(C2["B"] * C2["npoint"] / full, 1),
+                  "sample": f"127 of 2047 iterations at B=32 N=16384 ({t:.2f} s), scaled"}
+    g = torch.Generator().manual_seed(1234 + 3)
+    pts = make_cloud(g, 8, C3["N"])
+    t0 = time.perf_counter(); kidx = O.torch_knn(C3["k"], pts, pts); t = time.perf_counter() - t0
+    out["knn"] = {"query_pts_per_s": round(8 * C3["S"] / t, 1), "sample": f"8 of 32 clouds ({t:.2f} s)"}
+    feat = torch.randn(8, C3["C"], C3["N"], generator=g)
+    t0 = time.perf_counter(); O.torch_group(feat, kidx); t = time.perf_counter() - t0
+    byts = 4 * (8 * C3["S"] * C3["k"] + 8 * C3["C"] * C3["N"] + 8 * C3["C"] * C3["S"] * C3["k"])
+    out["group_fwd"] = {"gbs": round(byts / t / 1e9, 2), "sample": f"8 of 32 clouds ({t:.2f} s)"}
+    return out
+
+
+def run_reference(args):
+    """Reference arm: the path's CPU expression (pure torch, all host threads) on C1's metric."""
+    rank = int(os.environ.get("RANK", 0))
+    if rank != 0:
+        return
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    bs = 2  # bounded sample per step: 2 of the 32 clouds
+    warm = max(args.warmup, 1)
+    for _ in range(warm):
+        _cpu_chamfer_once(bs)
+    ts = [_cpu_chamfer_once(bs) for _ in range(args.steps)]
+    pairs = 2.0 * bs * C1["N"] * C1["M"]
+    value = pairs * len(ts) / sum(ts) / 1e9
+    sample = f"{bs} of the 32 C1 clouds per step, pure-torch direct-form fwd+bwd on {torch.get_num_threads()} threads"
+    print(json.dumps({
+        "impl": "reference", "metric": "chamfer_fwd_bwd_gpair_per_s", "value": round(value, 4), "unit": "Gpair/s",
+        "n_gpus": int(os.environ.get("WORLD_SIZE", args.gpus)), "steps": args.steps, "warmup": warm,
+        "ms_per_step": round(sum(ts) / len(ts) * 1e3, 2), "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": WORKLOAD, "B_per_step": bs, "N": C1["N"], "M": C1["M"]},
+        "cpu_baseline": {"value": round(value, 4), "unit": "Gpair/s", "cores": torch.get_num_threads(), "kind": "port",
+                         "sample": sample},
+        "e2e": {"value": round(value, 4), "unit": "Gpair/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--no-ops", action="store_true", help="skip the FPS/kNN/gather/group section")
+    ap.add_argument("--no-cpu", action="store_true", help="skip the CPU baseline legs")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -25,6 +25,23 @@ def shard_batch(t, rank=None, world=None):
     return t[lo:hi].contiguous()
 
 
+class _AllReduceSum(torch.autograd.Function):
+    """all-reduce(sum) that autograd can cross.  Backward is the identity: every rank holds the
+    same replicated loss, and we want the gradient of ONE copy of it, so each rank keeps the
+    gradient w.r.t. its own partial sums; parameter gradients are then SUMMED (not averaged)
+    across ranks."""
+
+    @staticmethod
+    def forward(ctx, vec, group):
+        out = vec.clone()
+        dist.all_reduce(out, op=dist.ReduceOp.SUM, group=group)
+        return out
+
+    @staticmethod
+    def backward(ctx, grad):
+        return grad, None
+
+
 class LossSums:
     """Accumulates named (sum, count) pairs on the device and reduces them with one all-reduce.
 
@@ -44,7 +61,7 @@ class LossSums:
     def reduce(self, group=None):
         vec = torch.cat(self.parts) if self.parts else torch.zeros(0, device=self.device, dtype=self.dtype)
         if dist.is_initialized() and dist.get_world_size(group) > 1 and vec.numel():
-            dist.all_reduce(vec, op=dist.ReduceOp.SUM, group=group)
+            vec = _AllReduceSum.apply(vec, group)
         out = {}
         for i, name in enumerate(self.names):
             out[name] = vec[2 * i] / vec[2 * i + 1]
