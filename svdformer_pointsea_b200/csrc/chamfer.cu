@@ -163,21 +163,44 @@ __global__ void __launch_bounds__(CH_THREADS) chamfer_nn_kernel(const ChamferPar
   }
 
   // ---- recover the argmin: first target of the remembered chunk that reproduces `best` -----
+  // The last tile of the split is still resident in shared memory; chunks inside it are
+  // re-evaluated there.  Every lane works on its own chunk, so the scan starts at a
+  // lane-dependent offset (2*lane): lane l touches bank (2l + 2i) mod 32, which keeps the LDS.64
+  // accesses to 2-way conflicts instead of 32-way.  Earlier tiles (multi-tile splits only) are
+  // re-read from global memory (L2-resident).
+  const int last_ts = t0 + ((t1 - t0 - 1) / CH_TILE) * CH_TILE;
+  const int last_chunk0 = (last_ts - t0) / CH_CHUNK;
+  const int lane = tid & 31;
 #pragma unroll
   for (int q = 0; q < Q; q++) {
     const int qi = qt * (CH_THREADS * Q) + q * CH_THREADS + tid;
-    if (qi >= nq) continue;
     const int base = t0 + cchunk[q] * CH_CHUNK;
-    const int n = min(CH_CHUNK, t1 - base);
-    const float* tp = tcloud + (size_t)base * 3;
-    int found = 0;
+    int found = CH_CHUNK;
+    if (cchunk[q] >= last_chunk0) {
+      const int off = (cchunk[q] - last_chunk0) * CH_CHUNK;
+#pragma unroll 4
+      for (int i = 0; i < CH_CHUNK / 2; i++) {
+        const int j = (2 * i + 2 * lane) & (CH_CHUNK - 1);
+        const u64 X = *reinterpret_cast<const u64*>(&sx[off + j]);
+        const u64 Y = *reinterpret_cast<const u64*>(&sy[off + j]);
+        const u64 Z = *reinterpret_cast<const u64*>(&sz[off + j]);
+        const u64 d = dist2x2(X, Y, Z, nqx[q], nqy[q], nqz[q]);
+        if (hi2(d) == best[q]) found = min(found, j + 1);
+        if (lo2(d) == best[q]) found = min(found, j);
+      }
+    } else {
+      const int n = min(CH_CHUNK, t1 - base);
+      const float* tp = tcloud + (size_t)base * 3;
 #pragma unroll 8
-    for (int j = n - 1; j >= 0; j--) {
-      const float dx = __ldg(tp + j * 3 + 0) - qx[q];
-      const float dy = __ldg(tp + j * 3 + 1) - qy[q];
-      const float dz = __ldg(tp + j * 3 + 2) - qz[q];
-      if (dist2_ref(dx, dy, dz) == best[q]) found = j;
+      for (int j = n - 1; j >= 0; j--) {
+        const float dx = __ldg(tp + j * 3 + 0) - qx[q];
+        const float dy = __ldg(tp + j * 3 + 1) - qy[q];
+        const float dz = __ldg(tp + j * 3 + 2) - qz[q];
+        if (dist2_ref(dx, dy, dz) == best[q]) found = j;
+      }
     }
+    if (qi >= nq) continue;
+    if (found >= CH_CHUNK) found = 0;  // only reachable with non-finite inputs
     const int gi = base + found;
     const size_t o = (size_t)b * nq + qi;
     if (D.nsplit == 1) {
@@ -295,7 +318,7 @@ extern "C" int ps_chamfer_fwd(const float* xyz1, const float* xyz2, float* dist1
     if (p.d[d].nsplit > 1) need[d] = (size_t)B * p.d[d].nq;
   u64* scratch = nullptr;
   if (need[0] + need[1]) {
-    PS_CUDA(cudaMallocAsync((void**)&scratch, (need[0] + need[1]) * sizeof(u64), stream));
+    if (int rc = scratch_alloc((void**)&scratch, (need[0] + need[1]) * sizeof(u64), dev, stream)) return rc;
     PS_CUDA(cudaMemsetAsync(scratch, 0xFF, (need[0] + need[1]) * sizeof(u64), stream));
   }
   p.d[0].keys = need[0] ? scratch : nullptr;

@@ -59,6 +59,8 @@ struct DeviceGuard {
 };
 
 int sm_count(int dev);
+// stream-ordered scratch allocation (pool keeps freed blocks cached); free with cudaFreeAsync
+int scratch_alloc(void** ptr, size_t bytes, int dev, cudaStream_t stream);
 
 static inline int ceil_div(long long a, long long b) { return (int)((a + b - 1) / b); }
 

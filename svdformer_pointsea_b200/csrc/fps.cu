@@ -39,13 +39,14 @@ namespace ps {
 constexpr int FPS_T = 512;
 constexpr int FPS_WARPS = FPS_T / 32;
 
-struct __align__(16) FpsEntry {  // 32 bytes, written with st.v4 + st.v2
+struct __align__(16) FpsEntry {  // two 16-byte vectors, each written by ONE st.v4 and carrying a tag
   int tb;          // distance bits (signed compare)
   unsigned rank;   // tie-break rank, smaller wins
-  float x, y;
-  float z;
+  float x;
+  unsigned tag_a;  // iteration number (flag-polling modes)
+  float y, z;
   int k;           // point index
-  int pad0, pad1;
+  unsigned tag_b;
 };
 
 struct FpsArgs {
@@ -76,21 +77,57 @@ __device__ __forceinline__ int warp_argbest(int tb, unsigned rank, int& tb_max) 
   return __ffs(m) - 1;
 }
 
+// ---- st.async + mbarrier: the remote store and its completion signal travel together -------------
+__device__ __forceinline__ void fps_mbar_init(unsigned bar, unsigned cnt) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(cnt) : "memory");
+}
+__device__ __forceinline__ void fps_mbar_expect_tx(unsigned bar, unsigned bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ bool fps_mbar_try_wait(unsigned bar, unsigned parity) {
+  unsigned ok;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%1], %2;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
+  return ok != 0;
+}
+__device__ __forceinline__ void st_async_v4(unsigned raddr, unsigned rbar, unsigned a, unsigned b, unsigned c, unsigned d) {
+  asm volatile("st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.v4.b32 [%0], {%1, %2, %3, %4}, [%5];"
+               ::"r"(raddr), "r"(a), "r"(b), "r"(c), "r"(d), "r"(rbar) : "memory");
+}
+
+// MODE 0: single CTA, __syncthreads.
+// MODE 1: cluster, every warp pushes to all CTAs, barrier.cluster per iteration.
+// MODE 2: cluster, CTA-level reduce then one push per CTA, barrier.cluster per iteration.
+// MODE 3: as 1 but NO cluster barrier (barrier.cluster.arrive.release costs a MEMBAR.ALL.GPU per
+//         iteration): candidates are pushed with st.async, whose completion is counted in bytes
+//         on the DESTINATION CTA's mbarrier; every warp sleeps on its own CTA's mbarrier
+//         (try_wait) until all 16*C candidates of the iteration have landed.
+// MODE 4: as 2 with the cluster exchange done by st.async + mbarrier.
+// Slot reuse is safe with two buffers in every mode: a writer can only be at iteration j+2 after
+// it has consumed every candidate of iteration j+1, and each reader sends its j+1 candidate only
+// after it has finished reading the slots of iteration j.
 template <int P, int MODE>
 __global__ void __launch_bounds__(FPS_T, 1) fps_kernel(const FpsArgs a) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
-  // layout: px[P*T] py[P*T] pz[P*T] | slots[2][E] (FpsEntry) | wslots[2][16] (MODE 0/2)
+  // layout: px[P*T] py[P*T] pz[P*T] | mbar[2] (16 B) | slots[2][E] | wslots[2][16] (MODE 2/4)
   float* px = reinterpret_cast<float*>(smem_raw);
   float* py = px + P * FPS_T;
   float* pz = py + P * FPS_T;
-  FpsEntry* slots = reinterpret_cast<FpsEntry*>(pz + P * FPS_T);
+  u64* mbar = reinterpret_cast<u64*>(pz + P * FPS_T);
+  FpsEntry* slots = reinterpret_cast<FpsEntry*>(mbar + 2);
 
-  const unsigned C = (MODE == 0) ? 1u : cluster_nctarank();
-  const unsigned crank = (MODE == 0) ? 0u : cluster_ctarank();
-  const int b = (MODE == 0) ? blockIdx.x : (int)cluster_id_x();
+  constexpr bool CLUSTER = MODE != 0;
+  constexpr bool DIRECT = MODE == 1 || MODE == 3;
+  constexpr bool POLL = MODE == 3 || MODE == 4;
+  const unsigned C = CLUSTER ? cluster_nctarank() : 1u;
+  const unsigned crank = CLUSTER ? cluster_ctarank() : 0u;
+  const int b = CLUSTER ? (int)cluster_id_x() : (int)blockIdx.x;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const int E = (MODE == 1) ? FPS_WARPS * (int)C : (MODE == 2 ? (int)C : FPS_WARPS);
-  FpsEntry* wslots = slots + 2 * E;  // only MODE 2 (CTA-level staging)
+  const int E = DIRECT ? FPS_WARPS * (int)C : (CLUSTER ? (int)C : FPS_WARPS);
+  FpsEntry* wslots = slots + 2 * E;  // CTA-level staging (MODE 2/4)
 
   const int N = a.N;
   const float* cloud = a.xyz + (size_t)b * N * 3;
@@ -98,73 +135,101 @@ __global__ void __launch_bounds__(FPS_T, 1) fps_kernel(const FpsArgs a) {
   const int g = (int)crank * FPS_T + tid;
   const int stride = (int)C * FPS_T;
 
-  float x[P], y[P], z[P], t[P];
+  constexpr int PP = (P + 1) / 2;  // packed pairs (P == 1 keeps its second half inert)
+  u64 x2[PP], y2[PP], z2[PP];
+  float t[2 * PP];
 #pragma unroll
-  for (int i = 0; i < P; i++) {
+  for (int i = 0; i < 2 * PP; i++) {
     const int k = g + i * stride;
-    if (k < N) {
-      x[i] = __ldg(cloud + (size_t)k * 3 + 0);
-      y[i] = __ldg(cloud + (size_t)k * 3 + 1);
-      z[i] = __ldg(cloud + (size_t)k * 3 + 2);
-      const float mag = dist2_ref(x[i], y[i], z[i]);
+    float xv = 0.f, yv = 0.f, zv = 0.f;
+    t[i] = -1.0f;
+    if (i < P && k < N) {
+      xv = __ldg(cloud + (size_t)k * 3 + 0);
+      yv = __ldg(cloud + (size_t)k * 3 + 1);
+      zv = __ldg(cloud + (size_t)k * 3 + 2);
+      const float mag = dist2_ref(xv, yv, zv);
       t[i] = ((double)mag <= 1e-3) ? -1.0f : 1e10f;
-    } else {
-      x[i] = y[i] = z[i] = 0.f;
-      t[i] = -1.0f;
     }
-    px[i * FPS_T + tid] = x[i];
-    py[i * FPS_T + tid] = y[i];
-    pz[i * FPS_T + tid] = z[i];
+    if (i < P) {
+      px[i * FPS_T + tid] = xv;
+      py[i * FPS_T + tid] = yv;
+      pz[i * FPS_T + tid] = zv;
+    }
+    if (i & 1) {
+      x2[i / 2] = pack2(lo2(x2[i / 2]), xv); y2[i / 2] = pack2(lo2(y2[i / 2]), yv); z2[i / 2] = pack2(lo2(z2[i / 2]), zv);
+    } else {
+      x2[i / 2] = pack2(xv, 0.f); y2[i / 2] = pack2(yv, 0.f); z2[i / 2] = pack2(zv, 0.f);
+    }
+  }
+  if (POLL && tid == 0) {
+    // one local arrive (the expect_tx below) + E*32 bytes of st.async traffic complete a phase
+    fps_mbar_init(smem_u32(&mbar[0]), 1);
+    fps_mbar_init(smem_u32(&mbar[1]), 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    fps_mbar_expect_tx(smem_u32(&mbar[0]), (unsigned)E * 32u);
+    fps_mbar_expect_tx(smem_u32(&mbar[1]), (unsigned)E * 32u);
   }
   const float p0x = __ldg(cloud + 0), p0y = __ldg(cloud + 1), p0z = __ldg(cloud + 2);
   float lx = p0x, ly = p0y, lz = p0z;
   if (g == 0 && a.npoint > 0) out[0] = 0;
-  if (MODE != 0) { cluster_arrive_release(); cluster_wait_acquire(); }  // all CTAs resident before DSMEM traffic
+  if (CLUSTER) { cluster_arrive_release(); cluster_wait_acquire(); }  // peers resident, tags cleared
   else __syncthreads();
 
   for (int j = 1; j < a.npoint; j++) {
-    // ---- per-thread update + best ---------------------------------------------------------
+    // ---- per-thread update + best: d = |p - last|^2 two points at a time (FADD2/FMUL2/FFMA2) --
+    const u64 nlx = pack2(-lx, -lx), nly = pack2(-ly, -ly), nlz = pack2(-lz, -lz);
     float best = -1.0f;
     int bi = 0;
 #pragma unroll
-    for (int i = 0; i < P; i++) {
-      const float d = dist2_ref(x[i] - lx, y[i] - ly, z[i] - lz);
-      t[i] = fminf(d, t[i]);
-      if (t[i] > best) { best = t[i]; bi = i; }
+    for (int i = 0; i < PP; i++) {
+      const u64 d = dist2x2(x2[i], y2[i], z2[i], nlx, nly, nlz);
+      t[2 * i] = fminf(lo2(d), t[2 * i]);
+      t[2 * i + 1] = fminf(hi2(d), t[2 * i + 1]);  // inert halves stay at -1
+      if (t[2 * i] > best) { best = t[2 * i]; bi = 2 * i; }
+      if (t[2 * i + 1] > best) { best = t[2 * i + 1]; bi = 2 * i + 1; }
     }
     const int k_mine = g + bi * stride;
-    int tb = __float_as_int(best);
-    unsigned rk = fps_rank(k_mine, a.L, a.nper);
+    const int tb = __float_as_int(best);
+    const unsigned rk = fps_rank(k_mine, a.L, a.nper);
     int tbw;
     const int wl = warp_argbest(tb, rk, tbw);
     const int buf = j & 1;
+    const unsigned tag = (unsigned)j;
 
-    if (MODE == 1) {
+    if (DIRECT) {
       // the winning lane pushes its candidate to slot (crank*16+warp) of every CTA
       if (lane == wl) {
         const unsigned e = crank * FPS_WARPS + warp;
         const unsigned local = smem_u32(&slots[buf * E + e]);
-        const float wx = px[bi * FPS_T + tid], wy = py[bi * FPS_T + tid], wz = pz[bi * FPS_T + tid];
+        const int pi = (bi < P ? bi : 0) * FPS_T + tid;
+        const float wx = px[pi], wy = py[pi], wz = pz[pi];
+        const unsigned lbar = smem_u32(&mbar[buf]);
         for (unsigned c = 0; c < C; c++) {
           const unsigned ra = mapa_shared(local, c);
-          st_cluster_v4(ra, (unsigned)tb, rk, __float_as_uint(wx), __float_as_uint(wy));
-          st_cluster_v2(ra + 16, __float_as_uint(wz), (unsigned)k_mine);
+          if (POLL) {
+            const unsigned rb = mapa_shared(lbar, c);
+            st_async_v4(ra, rb, (unsigned)tb, rk, __float_as_uint(wx), tag);
+            st_async_v4(ra + 16, rb, __float_as_uint(wy), __float_as_uint(wz), (unsigned)k_mine, tag);
+          } else {
+            st_cluster_v4(ra, (unsigned)tb, rk, __float_as_uint(wx), tag);
+            st_cluster_v4(ra + 16, __float_as_uint(wy), __float_as_uint(wz), (unsigned)k_mine, tag);
+          }
         }
       }
-      cluster_arrive_release();
-      cluster_wait_acquire();
+      if (!POLL) { cluster_arrive_release(); cluster_wait_acquire(); }
     } else {
       // CTA-level staging
-      FpsEntry* ws = (MODE == 0 ? slots : wslots) + buf * FPS_WARPS;
+      FpsEntry* ws = (CLUSTER ? wslots : slots) + buf * FPS_WARPS;
       if (lane == wl) {
+        const int pi = (bi < P ? bi : 0) * FPS_T + tid;
         FpsEntry en;
         en.tb = tb; en.rank = rk; en.k = k_mine;
-        en.x = px[bi * FPS_T + tid]; en.y = py[bi * FPS_T + tid]; en.z = pz[bi * FPS_T + tid];
-        en.pad0 = en.pad1 = 0;
+        en.x = px[pi]; en.y = py[pi]; en.z = pz[pi];
+        en.tag_a = en.tag_b = tag;
         ws[warp] = en;
       }
       __syncthreads();
-      if (MODE == 2) {
+      if (CLUSTER) {
         // every warp reduces the 16 warp winners; warp 0 forwards the CTA winner to all CTAs
         FpsEntry en;
         en.tb = (int)0x80000000; en.rank = 0xffffffffu; en.x = en.y = en.z = 0.f; en.k = 0;
@@ -180,12 +245,17 @@ __global__ void __launch_bounds__(FPS_T, 1) fps_kernel(const FpsArgs a) {
           const unsigned sk = __shfl_sync(0xffffffffu, (unsigned)en.k, cl);
           if ((unsigned)lane < C) {
             const unsigned ra = mapa_shared(smem_u32(&slots[buf * E + crank]), (unsigned)lane);
-            st_cluster_v4(ra, stb, srk, sx, sy);
-            st_cluster_v2(ra + 16, sz, sk);
+            if (POLL) {
+              const unsigned rb = mapa_shared(smem_u32(&mbar[buf]), (unsigned)lane);
+              st_async_v4(ra, rb, stb, srk, sx, tag);
+              st_async_v4(ra + 16, rb, sy, sz, sk, tag);
+            } else {
+              st_cluster_v4(ra, stb, srk, sx, tag);
+              st_cluster_v4(ra + 16, sy, sz, sk, tag);
+            }
           }
         }
-        cluster_arrive_release();
-        cluster_wait_acquire();
+        if (!POLL) { cluster_arrive_release(); cluster_wait_acquire(); }
       }
     }
 
@@ -195,12 +265,20 @@ __global__ void __launch_bounds__(FPS_T, 1) fps_kernel(const FpsArgs a) {
     float fx = 0.f, fy = 0.f, fz = 0.f;
     int fk = 0;
     const FpsEntry* sl = slots + buf * E;
+    if (POLL) {
+      // buffer `buf` is used by iterations buf, buf+2, ... (buf=1: j=1,3,..; buf=0: j=2,4,..)
+      const unsigned parity = (unsigned)((j - 1) >> 1) & 1u;
+      while (!fps_mbar_try_wait(smem_u32(&mbar[buf]), parity)) {}
+      // re-arm for iteration j+2.  Safe before our other warps have observed this phase: the next
+      // phase cannot complete until they have sent their j+1 and j+2 candidates.
+      if (tid == 0) fps_mbar_expect_tx(smem_u32(&mbar[buf]), (unsigned)E * 32u);
+    }
     for (int e = lane; e < E; e += 32) {
-      const int4 v = *reinterpret_cast<const int4*>(&sl[e]);
-      const int2 w = *reinterpret_cast<const int2*>(reinterpret_cast<const char*>(&sl[e]) + 16);
-      if (fps_better(v.x, (unsigned)v.y, ftb, frk)) {
-        ftb = v.x; frk = (unsigned)v.y; fx = __int_as_float(v.z); fy = __int_as_float(v.w);
-        fz = __int_as_float(w.x); fk = w.y;
+      const int4 va = *reinterpret_cast<const int4*>(&sl[e]);
+      const int4 vb = *reinterpret_cast<const int4*>(reinterpret_cast<const char*>(&sl[e]) + 16);
+      if (fps_better(va.x, (unsigned)va.y, ftb, frk)) {
+        ftb = va.x; frk = (unsigned)va.y; fx = __int_as_float(va.z);
+        fy = __int_as_float(vb.x); fz = __int_as_float(vb.y); fk = vb.z;
       }
     }
     int tbf;
@@ -214,7 +292,7 @@ __global__ void __launch_bounds__(FPS_T, 1) fps_kernel(const FpsArgs a) {
     }
     if (g == 0) out[j] = kf;
   }
-  if (MODE != 0) { cluster_arrive_release(); cluster_wait_acquire(); }  // no CTA exits while peers may still write to it
+  if (CLUSTER) { cluster_arrive_release(); cluster_wait_acquire(); }  // no CTA exits while peers may still write to it
 }
 
 // Generic fallback for clouds too large for the register-resident kernel: one CTA per cloud,
@@ -250,7 +328,7 @@ __global__ void __launch_bounds__(FPS_T, 1) fps_generic_kernel(const FpsArgs a, 
       FpsEntry en;
       en.tb = __float_as_int(best); en.rank = rk; en.k = bk;
       en.x = cloud[bk * 3 + 0]; en.y = cloud[bk * 3 + 1]; en.z = cloud[bk * 3 + 2];
-      en.pad0 = en.pad1 = 0;
+      en.tag_a = en.tag_b = 0u;
       ws[buf][warp] = en;
     }
     __syncthreads();
@@ -282,9 +360,9 @@ static int ref_block_log2(int n) {
 
 template <int P, int MODE>
 static int launch_fps(const FpsArgs& a, int B, int C, cudaStream_t stream) {
-  const int E = (MODE == 1) ? FPS_WARPS * C : (MODE == 2 ? C : FPS_WARPS);
-  const size_t smem = (size_t)3 * P * FPS_T * sizeof(float) + (size_t)2 * E * sizeof(FpsEntry) +
-                      (MODE == 2 ? (size_t)2 * FPS_WARPS * sizeof(FpsEntry) : 0);
+  const int E = (MODE == 1 || MODE == 3) ? FPS_WARPS * C : (MODE == 0 ? FPS_WARPS : C);
+  const size_t smem = (size_t)3 * P * FPS_T * sizeof(float) + 16 + (size_t)2 * E * sizeof(FpsEntry) +
+                      ((MODE == 2 || MODE == 4) ? (size_t)2 * FPS_WARPS * sizeof(FpsEntry) : 0);
   auto kern = fps_kernel<P, MODE>;
   if (smem > 48 * 1024) PS_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   if (MODE == 0) {
@@ -363,7 +441,7 @@ extern "C" int ps_fps(const float* xyz, int* idx, int B, int N, int npoint, int 
   if (ceil_div(N, 16 * FPS_T) > 16) {
     // beyond the register-resident kernels: generic one-CTA-per-cloud path with global scratch
     float* temp = nullptr;
-    PS_CUDA(cudaMallocAsync((void**)&temp, (size_t)B * N * sizeof(float), stream));
+    if (int rc = scratch_alloc((void**)&temp, (size_t)B * N * sizeof(float), dev, stream)) return rc;
     fps_generic_kernel<<<B, FPS_T, 0, stream>>>(a, temp);
     PS_LAUNCH_CHECK();
     PS_CUDA(cudaFreeAsync(temp, stream));
@@ -372,7 +450,10 @@ extern "C" int ps_fps(const float* xyz, int* idx, int B, int N, int npoint, int 
   const int C = choose_cluster(B, N, nsm);
   int P = 1;
   while (P * C * FPS_T < N) P *= 2;
+  // PS_FPS_SYNC=barrier selects the barrier.cluster variants (kept for A/B measurements)
+  const char* sync_env = getenv("PS_FPS_SYNC");
+  const bool poll = !(sync_env && sync_env[0] == 'b');
   if (C == 1) return dispatch_p<0>(P, a, B, C, stream);
-  if (C <= 4) return dispatch_p<1>(P, a, B, C, stream);
-  return dispatch_p<2>(P, a, B, C, stream);
+  if (C <= 4) return poll ? dispatch_p<3>(P, a, B, C, stream) : dispatch_p<1>(P, a, B, C, stream);
+  return poll ? dispatch_p<4>(P, a, B, C, stream) : dispatch_p<2>(P, a, B, C, stream);
 }

@@ -31,6 +31,23 @@ int sm_count(int dev) {
   return n;
 }
 
+// Stream-ordered scratch.  The default mempool gives memory back to the driver at every
+// synchronisation unless a release threshold is set, which turns each cudaMallocAsync after a
+// sync into a real (100+ us) allocation; keep freed scratch cached in the pool instead.
+int scratch_alloc(void** ptr, size_t bytes, int dev, cudaStream_t stream) {
+  static bool configured[64] = {false};
+  if (dev >= 0 && dev < 64 && !configured[dev]) {
+    cudaMemPool_t pool;
+    if (cudaDeviceGetDefaultMemPool(&pool, dev) == cudaSuccess) {
+      unsigned long long thr = ~0ull;
+      cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &thr);
+    }
+    configured[dev] = true;
+  }
+  PS_CUDA(cudaMallocAsync(ptr, bytes, stream));
+  return PS_OK;
+}
+
 // FFMA2-only kernel: 16 independent packed accumulators per thread.
 constexpr int PEAK_ITERS = 2048;
 __global__ void __launch_bounds__(256) fp32_peak_kernel(float* out, float a, float b) {

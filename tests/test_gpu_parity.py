@@ -134,13 +134,20 @@ def test_fps_vs_oracle(B, N, npoint, dup, no):
     assert np.array_equal(got.cpu().numpy(), O.fps(x.numpy(), npoint))
 
 
+@pytest.mark.parametrize("sync", ["poll", "barrier"])
 @pytest.mark.parametrize("cluster", [1, 2, 4, 8, 16])
-def test_fps_every_cluster_size(cluster, monkeypatch):
+def test_fps_every_cluster_size(cluster, sync, monkeypatch):
+    """Every exchange variant of the kernel (single CTA, DSMEM push + barrier.cluster, DSMEM push +
+    flag polling, two-level) must give the reference's indices, ties included."""
     monkeypatch.setenv("PS_FPS_CLUSTER", str(cluster))
+    monkeypatch.setenv("PS_FPS_SYNC", sync)
     g = torch.Generator().manual_seed(300 + cluster)
     x = make_cloud(g, 3, 4096, dup=500, near_origin=5)
     got = ps.furthest_point_sample(x.to(DEV), 256)
     assert np.array_equal(got.cpu().numpy(), O.fps(x.numpy(), 256))
+    x = make_cloud(g, 2, min(20000, 8192 * cluster), dup=3000, near_origin=9)  # P > 1 at every cluster size
+    got = ps.furthest_point_sample(x.to(DEV), 300)
+    assert np.array_equal(got.cpu().numpy(), O.fps(x.numpy(), 300))
 
 
 def test_fps_all_points_inside_skip_ball():
