@@ -12,22 +12,25 @@
 //     FADD2 / FMUL2 / FFMA2 in exactly the reference's rounding order
 //     d = fma(dz,dz, fma(dx,dx, dy*dy)), dx = target - query; the running minimum is one
 //     FMNMX3 per two pairs
-//   * the argmin index is recovered lazily: per 64-target chunk we only note whether the
-//     running minimum improved (strict <, so the EARLIEST chunk holding the final minimum is
-//     remembered); after the scan each thread re-evaluates that one chunk with the scalar
-//     expression and takes the first target whose distance equals the minimum bit-for-bit.
-//     This is the reference's "lowest index among exact minima" (strict < within a tile,
-//     chamfer3D.cu:36-70, strict > across tiles, :126).
+//   * the argmin index is recovered lazily: per 4-target step we only note whether the running
+//     minimum improved (strict <, so the EARLIEST step holding the final minimum is remembered;
+//     one FSETP + one SEL on the otherwise idle ALU pipe, the FP32 pipe is the bottleneck);
+//     after the scan each thread re-evaluates that one step and takes the first of its four
+//     targets whose distance equals the minimum bit-for-bit.  This is the reference's "lowest
+//     index among exact minima" (strict < within a tile, chamfer3D.cu:36-70, strict > across
+//     tiles, :126).
 //   * when the targets are split across CTAs the partial results are merged with a 64-bit
 //     atomicMin on (dist_bits << 32 | idx): distances are >= 0 so the bit pattern is
 //     monotone, and equal distances resolve to the lower index.
 #include "common.cuh"
 
+#include <cstdlib>
+
 namespace ps {
 
 constexpr int CH_THREADS = 256;
 constexpr int CH_TILE = 2048;  // targets per shared-memory tile (24 KB SoA)
-constexpr int CH_CHUNK = 64;   // argmin bookkeeping granularity
+constexpr int CH_STEP = 4;     // targets per inner step = argmin bookkeeping granularity
 
 struct ChamferDir {
   const float* q;  // queries (B, nq, 3)
@@ -38,7 +41,7 @@ struct ChamferDir {
   int nq, nt;
   int nqtiles;    // query tiles per cloud
   int nsplit;     // target splits per cloud
-  int split_len;  // targets per split (multiple of CH_CHUNK)
+  int split_len;  // targets per split (multiple of CH_STEP)
   int units;      // B * nqtiles * nsplit
 };
 struct ChamferParams {
@@ -79,8 +82,8 @@ __global__ void __launch_bounds__(CH_THREADS) chamfer_nn_kernel(const ChamferPar
   // ---- queries into registers -------------------------------------------------------------
   float qx[Q], qy[Q], qz[Q];
   u64 nqx[Q], nqy[Q], nqz[Q];
-  float best[Q], cbest[Q];
-  int cchunk[Q];
+  float best[Q];
+  int cstep[Q];
   const float* qbase = D.q + (size_t)b * nq * 3;
 #pragma unroll
   for (int q = 0; q < Q; q++) {
@@ -93,8 +96,7 @@ __global__ void __launch_bounds__(CH_THREADS) chamfer_nn_kernel(const ChamferPar
     nqy[q] = pack2(-qy[q], -qy[q]);
     nqz[q] = pack2(-qz[q], -qz[q]);
     best[q] = INF;
-    cbest[q] = INF;
-    cchunk[q] = 0;
+    cstep[q] = 0;
   }
 
   const int t0 = split * D.split_len;
@@ -103,11 +105,11 @@ __global__ void __launch_bounds__(CH_THREADS) chamfer_nn_kernel(const ChamferPar
 
   for (int ts = t0; ts < t1; ts += CH_TILE) {
     const int cnt = min(CH_TILE, t1 - ts);
-    const int cnt_pad = (cnt + CH_CHUNK - 1) / CH_CHUNK * CH_CHUNK;
+    const int cnt_pad = (cnt + CH_STEP - 1) / CH_STEP * CH_STEP;
     const float* tb = tcloud + (size_t)ts * 3;
     const bool vec = (reinterpret_cast<uintptr_t>(tb) & 15) == 0;
     __syncthreads();  // previous tile fully consumed
-    // ---- stage AoS (x,y,z) points as SoA; pad the last chunk with +inf targets ------------
+    // ---- stage AoS (x,y,z) points as SoA; pad the last step with +inf targets ---------------
     for (int g = tid; g < cnt_pad / 4; g += CH_THREADS) {
       float4 X, Y, Z;
       if (vec && g * 4 + 4 <= cnt) {
@@ -137,70 +139,56 @@ __global__ void __launch_bounds__(CH_THREADS) chamfer_nn_kernel(const ChamferPar
     }
     __syncthreads();
 
-    // ---- scan the tile ----------------------------------------------------------------------
-    const int chunk0 = (ts - t0) / CH_CHUNK;
-    for (int c = 0; c < cnt_pad / CH_CHUNK; c++) {
-      const int off = c * CH_CHUNK;
+    // ---- scan the tile: 4 targets x Q queries per step ----------------------------------------
+    int step = (ts - t0) / CH_STEP;
 #pragma unroll 4
-      for (int j = 0; j < CH_CHUNK; j += 4) {
-        const ulonglong2 X = *reinterpret_cast<const ulonglong2*>(&sx[off + j]);
-        const ulonglong2 Y = *reinterpret_cast<const ulonglong2*>(&sy[off + j]);
-        const ulonglong2 Z = *reinterpret_cast<const ulonglong2*>(&sz[off + j]);
-#pragma unroll
-        for (int q = 0; q < Q; q++) {
-          const u64 d01 = dist2x2(X.x, Y.x, Z.x, nqx[q], nqy[q], nqz[q]);
-          const u64 d23 = dist2x2(X.y, Y.y, Z.y, nqx[q], nqy[q], nqz[q]);
-          best[q] = min3(best[q], lo2(d01), hi2(d01));
-          best[q] = min3(best[q], lo2(d23), hi2(d23));
-        }
-      }
+    for (int j = 0; j < cnt_pad; j += CH_STEP, step++) {
+      const ulonglong2 X = *reinterpret_cast<const ulonglong2*>(&sx[j]);
+      const ulonglong2 Y = *reinterpret_cast<const ulonglong2*>(&sy[j]);
+      const ulonglong2 Z = *reinterpret_cast<const ulonglong2*>(&sz[j]);
 #pragma unroll
       for (int q = 0; q < Q; q++) {
-        if (best[q] < cbest[q]) cchunk[q] = chunk0 + c;
-        cbest[q] = best[q];
+        const u64 d01 = dist2x2(X.x, Y.x, Z.x, nqx[q], nqy[q], nqz[q]);
+        const u64 d23 = dist2x2(X.y, Y.y, Z.y, nqx[q], nqy[q], nqz[q]);
+        float nb = min3(best[q], lo2(d01), hi2(d01));
+        nb = min3(nb, lo2(d23), hi2(d23));
+        if (nb < best[q]) cstep[q] = step;
+        best[q] = nb;
       }
     }
   }
 
-  // ---- recover the argmin: first target of the remembered chunk that reproduces `best` -----
-  // The last tile of the split is still resident in shared memory; chunks inside it are
-  // re-evaluated there.  Every lane works on its own chunk, so the scan starts at a
-  // lane-dependent offset (2*lane): lane l touches bank (2l + 2i) mod 32, which keeps the LDS.64
-  // accesses to 2-way conflicts instead of 32-way.  Earlier tiles (multi-tile splits only) are
-  // re-read from global memory (L2-resident).
+  // ---- recover the argmin: first target of the remembered step that reproduces `best` --------
+  // Steps inside the last tile of the split are re-evaluated from shared memory (still resident);
+  // earlier tiles (multi-tile splits only) are re-read from global memory (L2-resident).
   const int last_ts = t0 + ((t1 - t0 - 1) / CH_TILE) * CH_TILE;
-  const int last_chunk0 = (last_ts - t0) / CH_CHUNK;
-  const int lane = tid & 31;
 #pragma unroll
   for (int q = 0; q < Q; q++) {
     const int qi = qt * (CH_THREADS * Q) + q * CH_THREADS + tid;
-    const int base = t0 + cchunk[q] * CH_CHUNK;
-    int found = CH_CHUNK;
-    if (cchunk[q] >= last_chunk0) {
-      const int off = (cchunk[q] - last_chunk0) * CH_CHUNK;
-#pragma unroll 4
-      for (int i = 0; i < CH_CHUNK / 2; i++) {
-        const int j = (2 * i + 2 * lane) & (CH_CHUNK - 1);
-        const u64 X = *reinterpret_cast<const u64*>(&sx[off + j]);
-        const u64 Y = *reinterpret_cast<const u64*>(&sy[off + j]);
-        const u64 Z = *reinterpret_cast<const u64*>(&sz[off + j]);
-        const u64 d = dist2x2(X, Y, Z, nqx[q], nqy[q], nqz[q]);
-        if (hi2(d) == best[q]) found = min(found, j + 1);
-        if (lo2(d) == best[q]) found = min(found, j);
-      }
+    const int base = t0 + cstep[q] * CH_STEP;
+    u64 d01, d23;
+    if (base >= last_ts) {
+      const int off = base - last_ts;
+      const ulonglong2 X = *reinterpret_cast<const ulonglong2*>(&sx[off]);
+      const ulonglong2 Y = *reinterpret_cast<const ulonglong2*>(&sy[off]);
+      const ulonglong2 Z = *reinterpret_cast<const ulonglong2*>(&sz[off]);
+      d01 = dist2x2(X.x, Y.x, Z.x, nqx[q], nqy[q], nqz[q]);
+      d23 = dist2x2(X.y, Y.y, Z.y, nqx[q], nqy[q], nqz[q]);
     } else {
-      const int n = min(CH_CHUNK, t1 - base);
+      // earlier tiles are full (CH_TILE is a multiple of CH_STEP), so all four targets exist
       const float* tp = tcloud + (size_t)base * 3;
-#pragma unroll 8
-      for (int j = n - 1; j >= 0; j--) {
-        const float dx = __ldg(tp + j * 3 + 0) - qx[q];
-        const float dy = __ldg(tp + j * 3 + 1) - qy[q];
-        const float dz = __ldg(tp + j * 3 + 2) - qz[q];
-        if (dist2_ref(dx, dy, dz) == best[q]) found = j;
-      }
+      float px[4], py[4], pz[4];
+#pragma unroll
+      for (int e = 0; e < 4; e++) { px[e] = __ldg(tp + e * 3 + 0); py[e] = __ldg(tp + e * 3 + 1); pz[e] = __ldg(tp + e * 3 + 2); }
+      d01 = dist2x2(pack2(px[0], px[1]), pack2(py[0], py[1]), pack2(pz[0], pz[1]), nqx[q], nqy[q], nqz[q]);
+      d23 = dist2x2(pack2(px[2], px[3]), pack2(py[2], py[3]), pack2(pz[2], pz[3]), nqx[q], nqy[q], nqz[q]);
     }
+    int found = 0;  // stays 0 only for non-finite inputs
+    if (hi2(d23) == best[q]) found = 3;
+    if (lo2(d23) == best[q]) found = 2;
+    if (hi2(d01) == best[q]) found = 1;
+    if (lo2(d01) == best[q]) found = 0;
     if (qi >= nq) continue;
-    if (found >= CH_CHUNK) found = 0;  // only reachable with non-finite inputs
     const int gi = base + found;
     const size_t o = (size_t)b * nq + qi;
     if (D.nsplit == 1) {
@@ -271,21 +259,50 @@ __global__ void __launch_bounds__(256) chamfer_bwd_kernel(const ChamferBwdParams
   }
 }
 
-static void plan_dir(ChamferDir& D, int B, int Q, int nsm) {
+// Unit planning.  A unit = (cloud, tile of 256*Q queries, split of L targets).  All units of a
+// launch get (nearly) the same L so they take the same time; L is chosen so that the unit count
+// lands just below a whole number of waves of resident CTAs (the tail wave otherwise costs up to a
+// full unit time) while the per-unit fixed cost (query load, staging, merge atomics) stays small.
+static void set_split(ChamferDir& D, int B, int Q, int L) {
   D.nqtiles = ceil_div(D.nq, CH_THREADS * Q);
-  // aim for >= ~6 CTAs per SM over the whole launch so the tail wave stays small, but keep
-  // at least 512 targets per split so the per-unit argmin rescan stays a few percent.
-  const long long base_units = (long long)B * D.nqtiles;
-  const long long want = (long long)nsm * 6;
-  int nsplit = (int)((want + base_units - 1) / base_units);
-  const int max_split = ceil_div(D.nt, 512);
-  if (nsplit > max_split) nsplit = max_split;
-  if (nsplit < 1) nsplit = 1;
+  int nsplit = ceil_div(D.nt, L);
   int len = ceil_div(D.nt, nsplit);
-  len = (len + CH_CHUNK - 1) / CH_CHUNK * CH_CHUNK;
+  len = (len + CH_STEP - 1) / CH_STEP * CH_STEP;
   D.split_len = len;
   D.nsplit = ceil_div(D.nt, len);
   D.units = B * D.nqtiles * D.nsplit;
+}
+
+static void plan_units(ChamferParams& p, int B, int Q, int nsm) {
+  const int slots = nsm * 4;  // 64 registers x 256 threads -> 4 CTAs per SM
+  const int maxt = p.d[0].nt > p.d[1].nt ? p.d[0].nt : p.d[1].nt;
+  int bestL = maxt;
+  double best_score = -1.0;
+  for (int L = 256; L <= 16384; L += 256) {
+    ChamferDir a = p.d[0], b = p.d[1];
+    set_split(a, B, Q, L);
+    set_split(b, B, Q, L);
+    // work in units of (queries x targets); waves by the longest-processing-time bound
+    const double w0 = (double)a.split_len, w1 = (double)b.split_len;
+    const double total = a.units * w0 + b.units * w1;
+    const double wmax = w0 > w1 ? w0 : w1;
+    const double units = (double)a.units + b.units;
+    double makespan;
+    if (units <= slots) makespan = wmax;
+    else {
+      const double waves = units / slots;
+      const double avg = total / units;
+      makespan = ((double)(long long)waves + ((waves > (long long)waves) ? 1.0 : 0.0)) * avg;
+      if (makespan < total / slots) makespan = total / slots;
+    }
+    const double fixed = 48.0;  // per-unit fixed cost expressed in "targets"
+    const double score = (total / slots) / (makespan * (1.0 + fixed / (w0 < w1 ? w0 : w1)));
+    if (score > best_score + 1e-9) { best_score = score; bestL = L; }
+    if (L >= maxt) break;
+  }
+  if (const char* e = getenv("PS_CHAMFER_SPLIT")) { const int v = atoi(e); if (v >= CH_STEP) bestL = v; }
+  set_split(p.d[0], B, Q, bestL);
+  set_split(p.d[1], B, Q, bestL);
 }
 
 }  // namespace ps
@@ -309,8 +326,7 @@ extern "C" int ps_chamfer_fwd(const float* xyz1, const float* xyz2, float* dist1
   ChamferParams p;
   p.d[0].q = xyz1; p.d[0].t = xyz2; p.d[0].dist = dist1; p.d[0].idx = idx1; p.d[0].nq = N; p.d[0].nt = M;
   p.d[1].q = xyz2; p.d[1].t = xyz1; p.d[1].dist = dist2; p.d[1].idx = idx2; p.d[1].nq = M; p.d[1].nt = N;
-  plan_dir(p.d[0], B, Q, nsm);
-  plan_dir(p.d[1], B, Q, nsm);
+  plan_units(p, B, Q, nsm);
 
   // merge scratch for split directions
   size_t need[2] = {0, 0};

@@ -5,30 +5,38 @@
 // The reference keeps the running min-distance array `temp` in GLOBAL memory and re-reads the
 // coordinates every iteration (sampling_gpu.cu:95-110), with one 512-thread block per cloud and
 // a 9-level __syncthreads tree per iteration.  Here:
-//   * a cluster of C CTAs x 512 threads owns one cloud; thread g = ctarank*512 + tid owns the
-//     points k = g + i*C*512 (i < P); their coordinates AND their running min distance live in
-//     registers for the whole kernel.  Global memory is read once.
-//   * per iteration every thread updates its P distances and keeps its best; a warp resolves
-//     its best with two REDUX ops (max of the distance bits, then min of the tie-break rank);
+//   * a cluster of C CTAs x T threads owns one cloud; every thread owns P = 2*PP points whose
+//     coordinates AND running min distance live in registers for the whole kernel (global memory
+//     is read once); distances are evaluated two points at a time with FADD2/FMUL2/FFMA2;
+//   * few fat threads (T = 128 or 256, up to 32 points each) rather than many thin ones: the
+//     per-warp cost of the exchange (~90 instructions) is what limits the iteration rate, so it
+//     is paid by 4-8 warps per SM instead of 16;
+//   * per iteration a warp resolves its best with two REDUX ops (max of the distance bits, then
+//     min of the tie-break rank);
 //   * MODE 0 (C == 1): warp winners meet in shared memory, one __syncthreads per iteration;
 //   * MODE 1 (C <= 4): every warp winner is pushed straight into the slot arrays of ALL CTAs of
-//     the cluster through distributed shared memory (st.shared::cluster), then ONE
-//     barrier.cluster (arrive.release / wait.acquire) per iteration, then every warp reduces the
-//     16*C candidates redundantly, so no second exchange is needed;
-//   * MODE 2 (C >= 8): CTA-level reduce first (one __syncthreads), then one candidate per CTA is
-//     pushed to all CTAs, then the cluster barrier.
-//   The message carries the winner's coordinates, so the next iteration starts without touching
-//   global memory.
+//     the cluster with st.async (distributed shared memory); the bytes are counted on the
+//     DESTINATION CTA's mbarrier, on which every warp of that CTA sleeps (try_wait) until all
+//     (T/32)*C candidates of the iteration have landed, then reduces them redundantly.  No
+//     barrier.cluster in the loop: its .release costs a MEMBAR.ALL.GPU per iteration (measured,
+//     profiles/fps_r1_notes.md);
+//   * MODE 2 (C >= 8): CTA-level reduce first (one __syncthreads), then one st.async per CTA pair.
+//   The message carries the winner's coordinates, so the next iteration never touches global
+//   memory.  Two slot buffers suffice: a writer can only be at iteration j+2 after consuming all
+//   candidates of j+1, and a reader sends its j+1 candidate only after reading the slots of j.
 //
 // Bit-exact tie-breaking.  The reference's winner among equal distances is decided by its
 // per-thread strict `>` scan (lowest k within thread tid = k mod bs) followed by the shared-
 // memory tree whose __update keeps the LEFT operand on ties (sampling_gpu.cu:59-65,115-168):
-// the tied thread with the smallest bit-reversed tid wins.  We reproduce that order with
-//     rank(k) = bitrev_L(k mod bs) * ceil(N / bs) + floor(k / bs),   bs = 2^L = opt_n_threads(N)
-// and select (distance desc, rank asc).  Points with |p|^2 <= 1e-3 (compared in double, as
-// the reference does, sampling_gpu.cu:100-101) never update and are never selected; they are
-// carried as distance -1, which orders below every real distance when the fp32 bit patterns
-// are compared as signed integers.
+// the tied thread with the smallest bit-reversed tid wins.  That order is
+//     rank(k) = bitrev_L(k mod bs) * nper + floor(k / bs),  bs = 2^L = opt_n_threads(N),
+//     nper = ceil(N / bs),
+// and we select (distance desc, rank asc).  Points are DEALT TO THREADS IN RANK ORDER: thread g
+// owns ranks [g*P, (g+1)*P), so the rank of its i-th point is g*P + i, the lowest i on a tie is
+// the lowest rank, and no bit reversal is needed inside the loop.  Points with |p|^2 <= 1e-3
+// (compared in double, as the reference does, sampling_gpu.cu:100-101) never update and are never
+// selected; they are carried as distance -1, which orders below every real distance when the
+// fp32 bit patterns are compared as signed integers.
 #include "common.cuh"
 
 #include <cmath>
@@ -36,17 +44,14 @@
 
 namespace ps {
 
-constexpr int FPS_T = 512;
-constexpr int FPS_WARPS = FPS_T / 32;
-
-struct __align__(16) FpsEntry {  // two 16-byte vectors, each written by ONE st.v4 and carrying a tag
+struct __align__(16) FpsEntry {  // two 16-byte vectors, each written by ONE st.async.v4
   int tb;          // distance bits (signed compare)
   unsigned rank;   // tie-break rank, smaller wins
   float x;
-  unsigned tag_a;  // iteration number (flag-polling modes)
+  unsigned pad_a;
   float y, z;
   int k;           // point index
-  unsigned tag_b;
+  unsigned pad_b;
 };
 
 struct FpsArgs {
@@ -57,10 +62,11 @@ struct FpsArgs {
   int nper;  // ceil(N / bs)
 };
 
-__device__ __forceinline__ unsigned fps_rank(int k, int L, int nper) {
-  const unsigned low = (unsigned)k & ((1u << L) - 1u);
-  const unsigned rev = L ? (__brev(low) >> (32 - L)) : 0u;
-  return rev * (unsigned)nper + ((unsigned)k >> L);
+// rank -> point index (may be >= N for the padding ranks of the last rows)
+__device__ __forceinline__ int fps_rank_to_k(unsigned rank, int L, int nper) {
+  const unsigned cls = rank / (unsigned)nper, m = rank % (unsigned)nper;
+  const unsigned r = L ? (__brev(cls) >> (32 - L)) : 0u;
+  return (int)(r + (m << L));
 }
 
 // lexicographic "a better than b": larger tb, then smaller rank
@@ -84,11 +90,13 @@ __device__ __forceinline__ void fps_mbar_init(unsigned bar, unsigned cnt) {
 __device__ __forceinline__ void fps_mbar_expect_tx(unsigned bar, unsigned bytes) {
   asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
 }
+// default (.acquire.cta) wait, as for TMA loads: the cluster-scope acquire would add a CCTL.IVALL
+// (L1 invalidate) per iteration, and only shared memory is read after the wait.
 __device__ __forceinline__ bool fps_mbar_try_wait(unsigned bar, unsigned parity) {
   unsigned ok;
   asm volatile(
       "{\n\t.reg .pred p;\n\t"
-      "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%1], %2;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
       "selp.u32 %0, 1, 0, p;\n\t}"
       : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
   return ok != 0;
@@ -98,71 +106,64 @@ __device__ __forceinline__ void st_async_v4(unsigned raddr, unsigned rbar, unsig
                ::"r"(raddr), "r"(a), "r"(b), "r"(c), "r"(d), "r"(rbar) : "memory");
 }
 
-// MODE 0: single CTA, __syncthreads.
-// MODE 1: cluster, every warp pushes to all CTAs, barrier.cluster per iteration.
-// MODE 2: cluster, CTA-level reduce then one push per CTA, barrier.cluster per iteration.
-// MODE 3: as 1 but NO cluster barrier (barrier.cluster.arrive.release costs a MEMBAR.ALL.GPU per
-//         iteration): candidates are pushed with st.async, whose completion is counted in bytes
-//         on the DESTINATION CTA's mbarrier; every warp sleeps on its own CTA's mbarrier
-//         (try_wait) until all 16*C candidates of the iteration have landed.
-// MODE 4: as 2 with the cluster exchange done by st.async + mbarrier.
-// Slot reuse is safe with two buffers in every mode: a writer can only be at iteration j+2 after
-// it has consumed every candidate of iteration j+1, and each reader sends its j+1 candidate only
-// after it has finished reading the slots of iteration j.
-template <int P, int MODE>
-__global__ void __launch_bounds__(FPS_T, 1) fps_kernel(const FpsArgs a) {
+template <int PP, int T, int MODE>
+__global__ void __launch_bounds__(T, 1) fps_kernel(const FpsArgs a) {
+  constexpr int P = 2 * PP;
+  constexpr int WARPS = T / 32;
+  constexpr bool CLUSTER = MODE != 0;
+  constexpr bool DIRECT = MODE == 1;
   extern __shared__ __align__(16) unsigned char smem_raw[];
-  // layout: px[P*T] py[P*T] pz[P*T] | mbar[2] (16 B) | slots[2][E] | wslots[2][16] (MODE 2/4)
+  // layout: px[P*T] py[P*T] pz[P*T] pk[P*T] | mbar[2] (16 B) | slots[2][E] | wslots[2][WARPS] (MODE 2)
   float* px = reinterpret_cast<float*>(smem_raw);
-  float* py = px + P * FPS_T;
-  float* pz = py + P * FPS_T;
-  u64* mbar = reinterpret_cast<u64*>(pz + P * FPS_T);
+  float* py = px + P * T;
+  float* pz = py + P * T;
+  int* pk = reinterpret_cast<int*>(pz + P * T);
+  u64* mbar = reinterpret_cast<u64*>(pk + P * T);
   FpsEntry* slots = reinterpret_cast<FpsEntry*>(mbar + 2);
 
-  constexpr bool CLUSTER = MODE != 0;
-  constexpr bool DIRECT = MODE == 1 || MODE == 3;
-  constexpr bool POLL = MODE == 3 || MODE == 4;
   const unsigned C = CLUSTER ? cluster_nctarank() : 1u;
   const unsigned crank = CLUSTER ? cluster_ctarank() : 0u;
   const int b = CLUSTER ? (int)cluster_id_x() : (int)blockIdx.x;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const int E = DIRECT ? FPS_WARPS * (int)C : (CLUSTER ? (int)C : FPS_WARPS);
-  FpsEntry* wslots = slots + 2 * E;  // CTA-level staging (MODE 2/4)
+  const int E = DIRECT ? WARPS * (int)C : (CLUSTER ? (int)C : WARPS);
+  FpsEntry* wslots = slots + 2 * E;  // CTA-level staging (MODE 2)
 
   const int N = a.N;
   const float* cloud = a.xyz + (size_t)b * N * 3;
   int* out = a.idx + (size_t)b * a.npoint;
-  const int g = (int)crank * FPS_T + tid;
-  const int stride = (int)C * FPS_T;
+  const int g = (int)crank * T + tid;
+  const unsigned rank0 = (unsigned)g * P;  // this thread owns ranks [rank0, rank0 + P)
+  const unsigned R = (unsigned)a.nper << a.L;
 
-  constexpr int PP = (P + 1) / 2;  // packed pairs (P == 1 keeps its second half inert)
   u64 x2[PP], y2[PP], z2[PP];
-  float t[2 * PP];
+  float t[P];
 #pragma unroll
-  for (int i = 0; i < 2 * PP; i++) {
-    const int k = g + i * stride;
+  for (int i = 0; i < P; i++) {
     float xv = 0.f, yv = 0.f, zv = 0.f;
+    int k = 0;
     t[i] = -1.0f;
-    if (i < P && k < N) {
-      xv = __ldg(cloud + (size_t)k * 3 + 0);
-      yv = __ldg(cloud + (size_t)k * 3 + 1);
-      zv = __ldg(cloud + (size_t)k * 3 + 2);
-      const float mag = dist2_ref(xv, yv, zv);
-      t[i] = ((double)mag <= 1e-3) ? -1.0f : 1e10f;
+    if (rank0 + i < R) {
+      k = fps_rank_to_k(rank0 + i, a.L, a.nper);
+      if (k < N) {
+        xv = __ldg(cloud + (size_t)k * 3 + 0);
+        yv = __ldg(cloud + (size_t)k * 3 + 1);
+        zv = __ldg(cloud + (size_t)k * 3 + 2);
+        const float mag = dist2_ref(xv, yv, zv);
+        t[i] = ((double)mag <= 1e-3) ? -1.0f : 1e10f;
+      }
     }
-    if (i < P) {
-      px[i * FPS_T + tid] = xv;
-      py[i * FPS_T + tid] = yv;
-      pz[i * FPS_T + tid] = zv;
-    }
+    px[i * T + tid] = xv;
+    py[i * T + tid] = yv;
+    pz[i * T + tid] = zv;
+    pk[i * T + tid] = k;
     if (i & 1) {
       x2[i / 2] = pack2(lo2(x2[i / 2]), xv); y2[i / 2] = pack2(lo2(y2[i / 2]), yv); z2[i / 2] = pack2(lo2(z2[i / 2]), zv);
     } else {
       x2[i / 2] = pack2(xv, 0.f); y2[i / 2] = pack2(yv, 0.f); z2[i / 2] = pack2(zv, 0.f);
     }
   }
-  if (POLL && tid == 0) {
-    // one local arrive (the expect_tx below) + E*32 bytes of st.async traffic complete a phase
+  if (CLUSTER && tid == 0) {
+    // one local arrive (the expect_tx) + E*32 bytes of st.async traffic complete a phase
     fps_mbar_init(smem_u32(&mbar[0]), 1);
     fps_mbar_init(smem_u32(&mbar[1]), 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -172,100 +173,80 @@ __global__ void __launch_bounds__(FPS_T, 1) fps_kernel(const FpsArgs a) {
   const float p0x = __ldg(cloud + 0), p0y = __ldg(cloud + 1), p0z = __ldg(cloud + 2);
   float lx = p0x, ly = p0y, lz = p0z;
   if (g == 0 && a.npoint > 0) out[0] = 0;
-  if (CLUSTER) { cluster_arrive_release(); cluster_wait_acquire(); }  // peers resident, tags cleared
+  if (CLUSTER) { cluster_arrive_release(); cluster_wait_acquire(); }  // peers resident, mbarriers armed
   else __syncthreads();
 
   for (int j = 1; j < a.npoint; j++) {
     // ---- per-thread update + best: d = |p - last|^2 two points at a time (FADD2/FMUL2/FFMA2) --
     const u64 nlx = pack2(-lx, -lx), nly = pack2(-ly, -ly), nlz = pack2(-lz, -lz);
     float best = -1.0f;
-    int bi = 0;
 #pragma unroll
     for (int i = 0; i < PP; i++) {
       const u64 d = dist2x2(x2[i], y2[i], z2[i], nlx, nly, nlz);
       t[2 * i] = fminf(lo2(d), t[2 * i]);
-      t[2 * i + 1] = fminf(hi2(d), t[2 * i + 1]);  // inert halves stay at -1
-      if (t[2 * i] > best) { best = t[2 * i]; bi = 2 * i; }
-      if (t[2 * i + 1] > best) { best = t[2 * i + 1]; bi = 2 * i + 1; }
+      t[2 * i + 1] = fminf(hi2(d), t[2 * i + 1]);  // padding / skipped points stay at -1
+      best = max3(best, t[2 * i], t[2 * i + 1]);    // one FMNMX3 per two points
     }
-    const int k_mine = g + bi * stride;
+    // lowest i holding the maximum == lowest rank among this thread's ties
+    int bi = 0;
+#pragma unroll
+    for (int i = P - 1; i >= 0; i--)
+      if (t[i] == best) bi = i;
     const int tb = __float_as_int(best);
-    const unsigned rk = fps_rank(k_mine, a.L, a.nper);
+    const unsigned rk = rank0 + (unsigned)bi;
     int tbw;
     const int wl = warp_argbest(tb, rk, tbw);
     const int buf = j & 1;
-    const unsigned tag = (unsigned)j;
+
+    // winner's payload to every lane of the warp
+    float wx = 0.f, wy = 0.f, wz = 0.f;
+    int wk = 0;
+    if (lane == wl) { const int pi = bi * T + tid; wx = px[pi]; wy = py[pi]; wz = pz[pi]; wk = pk[pi]; }
+    const unsigned s_rk = __shfl_sync(0xffffffffu, rk, wl);
+    const unsigned s_x = __shfl_sync(0xffffffffu, __float_as_uint(wx), wl);
+    const unsigned s_y = __shfl_sync(0xffffffffu, __float_as_uint(wy), wl);
+    const unsigned s_z = __shfl_sync(0xffffffffu, __float_as_uint(wz), wl);
+    const unsigned s_k = __shfl_sync(0xffffffffu, (unsigned)wk, wl);
 
     if (DIRECT) {
-      // the winning lane pushes its candidate to slot (crank*16+warp) of every CTA
-      if (lane == wl) {
-        const unsigned e = crank * FPS_WARPS + warp;
-        const unsigned local = smem_u32(&slots[buf * E + e]);
-        const int pi = (bi < P ? bi : 0) * FPS_T + tid;
-        const float wx = px[pi], wy = py[pi], wz = pz[pi];
-        const unsigned lbar = smem_u32(&mbar[buf]);
-        for (unsigned c = 0; c < C; c++) {
-          const unsigned ra = mapa_shared(local, c);
-          if (POLL) {
-            const unsigned rb = mapa_shared(lbar, c);
-            st_async_v4(ra, rb, (unsigned)tb, rk, __float_as_uint(wx), tag);
-            st_async_v4(ra + 16, rb, __float_as_uint(wy), __float_as_uint(wz), (unsigned)k_mine, tag);
-          } else {
-            st_cluster_v4(ra, (unsigned)tb, rk, __float_as_uint(wx), tag);
-            st_cluster_v4(ra + 16, __float_as_uint(wy), __float_as_uint(wz), (unsigned)k_mine, tag);
-          }
-        }
+      // lane c pushes the warp's candidate to slot (crank*WARPS+warp) of CTA c: C pushes in flight
+      if ((unsigned)lane < C) {
+        const unsigned e = crank * WARPS + warp;
+        const unsigned ra = mapa_shared(smem_u32(&slots[buf * E + e]), (unsigned)lane);
+        const unsigned rb = mapa_shared(smem_u32(&mbar[buf]), (unsigned)lane);
+        st_async_v4(ra, rb, (unsigned)tbw, s_rk, s_x, 0u);
+        st_async_v4(ra + 16, rb, s_y, s_z, s_k, 0u);
       }
-      if (!POLL) { cluster_arrive_release(); cluster_wait_acquire(); }
     } else {
-      // CTA-level staging
-      FpsEntry* ws = (CLUSTER ? wslots : slots) + buf * FPS_WARPS;
-      if (lane == wl) {
-        const int pi = (bi < P ? bi : 0) * FPS_T + tid;
+      FpsEntry* ws = (CLUSTER ? wslots : slots) + buf * WARPS;
+      if (lane == 0) {
         FpsEntry en;
-        en.tb = tb; en.rank = rk; en.k = k_mine;
-        en.x = px[pi]; en.y = py[pi]; en.z = pz[pi];
-        en.tag_a = en.tag_b = tag;
+        en.tb = tbw; en.rank = s_rk; en.x = __uint_as_float(s_x); en.y = __uint_as_float(s_y);
+        en.z = __uint_as_float(s_z); en.k = (int)s_k; en.pad_a = en.pad_b = 0u;
         ws[warp] = en;
       }
       __syncthreads();
-      if (CLUSTER) {
-        // every warp reduces the 16 warp winners; warp 0 forwards the CTA winner to all CTAs
+      if (CLUSTER && warp == 0) {
+        // warp 0 reduces the warp winners and forwards the CTA winner to every CTA
         FpsEntry en;
         en.tb = (int)0x80000000; en.rank = 0xffffffffu; en.x = en.y = en.z = 0.f; en.k = 0;
-        if (lane < FPS_WARPS) en = ws[lane];
+        if (lane < WARPS) en = ws[lane];
         int tbc;
         const int cl = warp_argbest(en.tb, en.rank, tbc);
-        if (warp == 0) {
-          const unsigned stb = (unsigned)tbc;
-          const unsigned srk = __shfl_sync(0xffffffffu, en.rank, cl);
-          const unsigned sx = __shfl_sync(0xffffffffu, __float_as_uint(en.x), cl);
-          const unsigned sy = __shfl_sync(0xffffffffu, __float_as_uint(en.y), cl);
-          const unsigned sz = __shfl_sync(0xffffffffu, __float_as_uint(en.z), cl);
-          const unsigned sk = __shfl_sync(0xffffffffu, (unsigned)en.k, cl);
-          if ((unsigned)lane < C) {
-            const unsigned ra = mapa_shared(smem_u32(&slots[buf * E + crank]), (unsigned)lane);
-            if (POLL) {
-              const unsigned rb = mapa_shared(smem_u32(&mbar[buf]), (unsigned)lane);
-              st_async_v4(ra, rb, stb, srk, sx, tag);
-              st_async_v4(ra + 16, rb, sy, sz, sk, tag);
-            } else {
-              st_cluster_v4(ra, stb, srk, sx, tag);
-              st_cluster_v4(ra + 16, sy, sz, sk, tag);
-            }
-          }
+        const unsigned c_rk = __shfl_sync(0xffffffffu, en.rank, cl);
+        const unsigned c_x = __shfl_sync(0xffffffffu, __float_as_uint(en.x), cl);
+        const unsigned c_y = __shfl_sync(0xffffffffu, __float_as_uint(en.y), cl);
+        const unsigned c_z = __shfl_sync(0xffffffffu, __float_as_uint(en.z), cl);
+        const unsigned c_k = __shfl_sync(0xffffffffu, (unsigned)en.k, cl);
+        if ((unsigned)lane < C) {
+          const unsigned ra = mapa_shared(smem_u32(&slots[buf * E + crank]), (unsigned)lane);
+          const unsigned rb = mapa_shared(smem_u32(&mbar[buf]), (unsigned)lane);
+          st_async_v4(ra, rb, (unsigned)tbc, c_rk, c_x, 0u);
+          st_async_v4(ra + 16, rb, c_y, c_z, c_k, 0u);
         }
-        if (!POLL) { cluster_arrive_release(); cluster_wait_acquire(); }
       }
     }
-
-    // ---- final reduce over the E candidates (identical in every warp of every CTA) --------
-    int ftb = (int)0x80000000;
-    unsigned frk = 0xffffffffu;
-    float fx = 0.f, fy = 0.f, fz = 0.f;
-    int fk = 0;
-    const FpsEntry* sl = slots + buf * E;
-    if (POLL) {
+    if (CLUSTER) {
       // buffer `buf` is used by iterations buf, buf+2, ... (buf=1: j=1,3,..; buf=0: j=2,4,..)
       const unsigned parity = (unsigned)((j - 1) >> 1) & 1u;
       while (!fps_mbar_try_wait(smem_u32(&mbar[buf]), parity)) {}
@@ -273,20 +254,30 @@ __global__ void __launch_bounds__(FPS_T, 1) fps_kernel(const FpsArgs a) {
       // phase cannot complete until they have sent their j+1 and j+2 candidates.
       if (tid == 0) fps_mbar_expect_tx(smem_u32(&mbar[buf]), (unsigned)E * 32u);
     }
-    for (int e = lane; e < E; e += 32) {
-      const int4 va = *reinterpret_cast<const int4*>(&sl[e]);
-      const int4 vb = *reinterpret_cast<const int4*>(reinterpret_cast<const char*>(&sl[e]) + 16);
-      if (fps_better(va.x, (unsigned)va.y, ftb, frk)) {
-        ftb = va.x; frk = (unsigned)va.y; fx = __int_as_float(va.z);
-        fy = __int_as_float(vb.x); fz = __int_as_float(vb.y); fk = vb.z;
+
+    // ---- final reduce over the E candidates (identical in every warp of every CTA) --------
+    const FpsEntry* sl = slots + buf * E;
+    constexpr int MAXE = DIRECT ? (WARPS * 4 + 31) / 32 : 1;  // entries per lane (C <= 4 when DIRECT)
+    int4 va[MAXE], vb[MAXE];
+#pragma unroll
+    for (int u = 0; u < MAXE; u++) {
+      const int e = lane + 32 * u;
+      va[u] = make_int4((int)0x80000000, -1, 0, 0);
+      vb[u] = make_int4(0, 0, 0, 0);
+      if (e < E) {
+        va[u] = *reinterpret_cast<const int4*>(&sl[e]);
+        vb[u] = *reinterpret_cast<const int4*>(reinterpret_cast<const char*>(&sl[e]) + 16);
       }
     }
+#pragma unroll
+    for (int u = 1; u < MAXE; u++)
+      if (fps_better(va[u].x, (unsigned)va[u].y, va[0].x, (unsigned)va[0].y)) { va[0] = va[u]; vb[0] = vb[u]; }
     int tbf;
-    const int fl = warp_argbest(ftb, frk, tbf);
-    lx = __shfl_sync(0xffffffffu, fx, fl);
-    ly = __shfl_sync(0xffffffffu, fy, fl);
-    lz = __shfl_sync(0xffffffffu, fz, fl);
-    int kf = __shfl_sync(0xffffffffu, fk, fl);
+    const int fl = warp_argbest(va[0].x, (unsigned)va[0].y, tbf);
+    lx = __shfl_sync(0xffffffffu, __int_as_float(va[0].z), fl);
+    ly = __shfl_sync(0xffffffffu, __int_as_float(vb[0].x), fl);
+    lz = __shfl_sync(0xffffffffu, __int_as_float(vb[0].y), fl);
+    int kf = __shfl_sync(0xffffffffu, vb[0].z, fl);
     if (tbf < 0) {  // no eligible point anywhere: the reference's tree returns thread 0's besti = 0
       kf = 0; lx = p0x; ly = p0y; lz = p0z;
     }
@@ -297,14 +288,21 @@ __global__ void __launch_bounds__(FPS_T, 1) fps_kernel(const FpsArgs a) {
 
 // Generic fallback for clouds too large for the register-resident kernel: one CTA per cloud,
 // running min distances in a global scratch array (still the exact reference order).
-__global__ void __launch_bounds__(FPS_T, 1) fps_generic_kernel(const FpsArgs a, float* temp_all) {
-  __shared__ FpsEntry ws[2][FPS_WARPS];
+constexpr int FPS_GT = 512;
+__device__ __forceinline__ unsigned fps_k_to_rank(int k, int L, int nper) {
+  const unsigned low = (unsigned)k & ((1u << L) - 1u);
+  const unsigned rev = L ? (__brev(low) >> (32 - L)) : 0u;
+  return rev * (unsigned)nper + ((unsigned)k >> L);
+}
+__global__ void __launch_bounds__(FPS_GT, 1) fps_generic_kernel(const FpsArgs a, float* temp_all) {
+  constexpr int WARPS = FPS_GT / 32;
+  __shared__ FpsEntry ws[2][WARPS];
   const int b = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int N = a.N;
   const float* cloud = a.xyz + (size_t)b * N * 3;
   float* temp = temp_all + (size_t)b * N;
   int* out = a.idx + (size_t)b * a.npoint;
-  for (int k = tid; k < N; k += FPS_T) {
+  for (int k = tid; k < N; k += FPS_GT) {
     const float mag = dist2_ref(cloud[k * 3 + 0], cloud[k * 3 + 1], cloud[k * 3 + 2]);
     temp[k] = ((double)mag <= 1e-3) ? -1.0f : 1e10f;
   }
@@ -312,29 +310,31 @@ __global__ void __launch_bounds__(FPS_T, 1) fps_generic_kernel(const FpsArgs a, 
   if (tid == 0 && a.npoint > 0) out[0] = 0;
   __syncthreads();
   for (int j = 1; j < a.npoint; j++) {
+    // stride FPS_GT is a multiple of bs, so k mod bs is constant per thread and the first maximum
+    // in k order is the lowest rank
     float best = -1.0f;
     int bk = tid < N ? tid : 0;
-    for (int k = tid; k < N; k += FPS_T) {
+    for (int k = tid; k < N; k += FPS_GT) {
       const float d = dist2_ref(cloud[k * 3 + 0] - lx, cloud[k * 3 + 1] - ly, cloud[k * 3 + 2] - lz);
       const float t = fminf(d, temp[k]);
       temp[k] = t;
       if (t > best) { best = t; bk = k; }
     }
     int tbw;
-    const unsigned rk = fps_rank(bk, a.L, a.nper);
+    const unsigned rk = fps_k_to_rank(bk, a.L, a.nper);
     const int wl = warp_argbest(__float_as_int(best), rk, tbw);
     const int buf = j & 1;
     if (lane == wl) {
       FpsEntry en;
       en.tb = __float_as_int(best); en.rank = rk; en.k = bk;
       en.x = cloud[bk * 3 + 0]; en.y = cloud[bk * 3 + 1]; en.z = cloud[bk * 3 + 2];
-      en.tag_a = en.tag_b = 0u;
+      en.pad_a = en.pad_b = 0u;
       ws[buf][warp] = en;
     }
     __syncthreads();
     FpsEntry en;
     en.tb = (int)0x80000000; en.rank = 0xffffffffu; en.x = en.y = en.z = 0.f; en.k = 0;
-    if (lane < FPS_WARPS) en = ws[buf][lane];
+    if (lane < WARPS) en = ws[buf][lane];
     int tbf;
     const int fl = warp_argbest(en.tb, en.rank, tbf);
     lx = __shfl_sync(0xffffffffu, en.x, fl);
@@ -358,20 +358,21 @@ static int ref_block_log2(int n) {
   return L;
 }
 
-template <int P, int MODE>
+template <int PP, int T, int MODE>
 static int launch_fps(const FpsArgs& a, int B, int C, cudaStream_t stream) {
-  const int E = (MODE == 1 || MODE == 3) ? FPS_WARPS * C : (MODE == 0 ? FPS_WARPS : C);
-  const size_t smem = (size_t)3 * P * FPS_T * sizeof(float) + 16 + (size_t)2 * E * sizeof(FpsEntry) +
-                      ((MODE == 2 || MODE == 4) ? (size_t)2 * FPS_WARPS * sizeof(FpsEntry) : 0);
-  auto kern = fps_kernel<P, MODE>;
+  constexpr int P = 2 * PP, WARPS = T / 32;
+  const int E = (MODE == 1) ? WARPS * C : (MODE == 0 ? WARPS : C);
+  const size_t smem = (size_t)4 * P * T * sizeof(float) + 16 + (size_t)2 * E * sizeof(FpsEntry) +
+                      (MODE == 2 ? (size_t)2 * WARPS * sizeof(FpsEntry) : 0);
+  auto kern = fps_kernel<PP, T, MODE>;
   if (smem > 48 * 1024) PS_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   if (MODE == 0) {
-    kern<<<B, FPS_T, smem, stream>>>(a);
+    kern<<<B, T, smem, stream>>>(a);
   } else {
     if (C > 8) PS_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3(B * C);
-    cfg.blockDim = dim3(FPS_T);
+    cfg.blockDim = dim3(T);
     cfg.dynamicSmemBytes = smem;
     cfg.stream = stream;
     cudaLaunchAttribute at[1];
@@ -387,37 +388,44 @@ static int launch_fps(const FpsArgs& a, int B, int C, cudaStream_t stream) {
   return PS_OK;
 }
 
-template <int MODE>
-static int dispatch_p(int P, const FpsArgs& a, int B, int C, cudaStream_t s) {
-  switch (P) {
-    case 1: return launch_fps<1, MODE>(a, B, C, s);
-    case 2: return launch_fps<2, MODE>(a, B, C, s);
-    case 4: return launch_fps<4, MODE>(a, B, C, s);
-    case 8: return launch_fps<8, MODE>(a, B, C, s);
-    case 16: return launch_fps<16, MODE>(a, B, C, s);
+template <int T, int MODE>
+static int dispatch_pp(int PP, const FpsArgs& a, int B, int C, cudaStream_t s) {
+  switch (PP) {
+    case 1: return launch_fps<1, T, MODE>(a, B, C, s);
+    case 2: return launch_fps<2, T, MODE>(a, B, C, s);
+    case 4: return launch_fps<4, T, MODE>(a, B, C, s);
+    case 8: return launch_fps<8, T, MODE>(a, B, C, s);
+    case 16: return launch_fps<16, T, MODE>(a, B, C, s);
   }
-  return set_error(PS_ERR_UNSUPPORTED, "ps_fps: no kernel for P=%d", P);
+  return set_error(PS_ERR_UNSUPPORTED, "ps_fps: no kernel for %d point pairs per thread", PP);
 }
 
-// Per-iteration cost model in SM cycles (measured on B200, profiles/microbench_r1.jsonl):
-// ~32 cycles of issue per resident point-per-thread, ~250 for the single-CTA exchange,
-// ~700 for the cluster exchange (barrier.cluster alone is ~450-480).
-static int choose_cluster(int B, int N, int nsm) {
-  if (const char* e = getenv("PS_FPS_CLUSTER")) {
-    const int c = atoi(e);
-    if (c == 1 || c == 2 || c == 4 || c == 8 || c == 16) return c;
-  }
+struct FpsPlan { int C, T, PP; };
+
+// Per-iteration cost model in SM cycles (fitted to B200 measurements, profiles/fps_r1_notes.md):
+// every warp issues ~6.5 instructions per resident point plus ~90 for the exchange, T/128 warps
+// share a scheduler; the exchange itself costs ~150 cycles inside one CTA and ~600 across a
+// cluster (st.async + mbarrier round trip through distributed shared memory).
+static bool plan_fps(int B, int N, int L, int nper, int nsm, FpsPlan& best) {
+  const long long R = (long long)nper << L;
+  int force_c = 0, force_t = 0;
+  if (const char* e = getenv("PS_FPS_CLUSTER")) force_c = atoi(e);
+  if (const char* e = getenv("PS_FPS_THREADS")) force_t = atoi(e);
   double best_cost = 1e30;
-  int best_c = 1;
+  bool found = false;
   for (int c = 1; c <= 16; c *= 2) {
-    const int p = ceil_div(N, c * FPS_T);
-    if (c > 1 && p < 1) break;
-    if (p > 16) continue;
-    const int waves = ceil_div((long long)B * c, nsm);
-    const double cost = waves * (32.0 * p + (c == 1 ? 250.0 : 700.0));
-    if (cost < best_cost - 1e-9) { best_cost = cost; best_c = c; }
+    if (force_c && c != force_c) continue;
+    for (int t = 128; t <= 256; t *= 2) {
+      if (force_t && t != force_t) continue;
+      int pp = 1;
+      while ((long long)2 * pp * c * t < R) pp *= 2;
+      if (pp > 16) continue;
+      const int waves = ceil_div((long long)B * c, nsm);
+      const double cost = waves * ((t / 128) * (6.5 * 2 * pp + 90.0) + (c == 1 ? 150.0 : 600.0));
+      if (cost < best_cost - 1e-9) { best_cost = cost; best = {c, t, pp}; found = true; }
+    }
   }
-  return best_c;
+  return found;
 }
 
 }  // namespace ps
@@ -438,22 +446,22 @@ extern "C" int ps_fps(const float* xyz, int* idx, int B, int N, int npoint, int 
   a.L = ref_block_log2(N);
   a.nper = ceil_div(N, 1 << a.L);
 
-  if (ceil_div(N, 16 * FPS_T) > 16) {
-    // beyond the register-resident kernels: generic one-CTA-per-cloud path with global scratch
+  FpsPlan pl;
+  if (!plan_fps(B, N, a.L, a.nper, nsm, pl)) {
+    // beyond the register-resident kernels (N > 131072): one CTA per cloud with global scratch
     float* temp = nullptr;
     if (int rc = scratch_alloc((void**)&temp, (size_t)B * N * sizeof(float), dev, stream)) return rc;
-    fps_generic_kernel<<<B, FPS_T, 0, stream>>>(a, temp);
+    fps_generic_kernel<<<B, FPS_GT, 0, stream>>>(a, temp);
     PS_LAUNCH_CHECK();
     PS_CUDA(cudaFreeAsync(temp, stream));
     return PS_OK;
   }
-  const int C = choose_cluster(B, N, nsm);
-  int P = 1;
-  while (P * C * FPS_T < N) P *= 2;
-  // PS_FPS_SYNC=barrier selects the barrier.cluster variants (kept for A/B measurements)
-  const char* sync_env = getenv("PS_FPS_SYNC");
-  const bool poll = !(sync_env && sync_env[0] == 'b');
-  if (C == 1) return dispatch_p<0>(P, a, B, C, stream);
-  if (C <= 4) return poll ? dispatch_p<3>(P, a, B, C, stream) : dispatch_p<1>(P, a, B, C, stream);
-  return poll ? dispatch_p<4>(P, a, B, C, stream) : dispatch_p<2>(P, a, B, C, stream);
+  if (pl.T == 128) {
+    if (pl.C == 1) return dispatch_pp<128, 0>(pl.PP, a, B, pl.C, stream);
+    if (pl.C <= 4) return dispatch_pp<128, 1>(pl.PP, a, B, pl.C, stream);
+    return dispatch_pp<128, 2>(pl.PP, a, B, pl.C, stream);
+  }
+  if (pl.C == 1) return dispatch_pp<256, 0>(pl.PP, a, B, pl.C, stream);
+  if (pl.C <= 4) return dispatch_pp<256, 1>(pl.PP, a, B, pl.C, stream);
+  return dispatch_pp<256, 2>(pl.PP, a, B, pl.C, stream);
 }

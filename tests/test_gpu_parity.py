@@ -134,20 +134,30 @@ def test_fps_vs_oracle(B, N, npoint, dup, no):
     assert np.array_equal(got.cpu().numpy(), O.fps(x.numpy(), npoint))
 
 
-@pytest.mark.parametrize("sync", ["poll", "barrier"])
+@pytest.mark.parametrize("threads", [128, 256])
 @pytest.mark.parametrize("cluster", [1, 2, 4, 8, 16])
-def test_fps_every_cluster_size(cluster, sync, monkeypatch):
-    """Every exchange variant of the kernel (single CTA, DSMEM push + barrier.cluster, DSMEM push +
-    flag polling, two-level) must give the reference's indices, ties included."""
+def test_fps_every_cluster_size(cluster, threads, monkeypatch):
+    """Every exchange variant of the kernel (single CTA; st.async push from every warp; two-level)
+    at both CTA sizes must give the reference's indices, ties included."""
     monkeypatch.setenv("PS_FPS_CLUSTER", str(cluster))
-    monkeypatch.setenv("PS_FPS_SYNC", sync)
+    monkeypatch.setenv("PS_FPS_THREADS", str(threads))
     g = torch.Generator().manual_seed(300 + cluster)
     x = make_cloud(g, 3, 4096, dup=500, near_origin=5)
     got = ps.furthest_point_sample(x.to(DEV), 256)
     assert np.array_equal(got.cpu().numpy(), O.fps(x.numpy(), 256))
-    x = make_cloud(g, 2, min(20000, 8192 * cluster), dup=3000, near_origin=9)  # P > 1 at every cluster size
+    x = make_cloud(g, 2, min(20000, 4000 * cluster), dup=1000, near_origin=9)
     got = ps.furthest_point_sample(x.to(DEV), 300)
     assert np.array_equal(got.cpu().numpy(), O.fps(x.numpy(), 300))
+    x = make_cloud(g, 2, 300, dup=40, near_origin=2)  # bs = 256 < 512, mostly padding ranks
+    got = ps.furthest_point_sample(x.to(DEV), 100)
+    assert np.array_equal(got.cpu().numpy(), O.fps(x.numpy(), 100))
+
+
+def test_fps_generic_fallback_beyond_register_capacity():
+    g = torch.Generator().manual_seed(77)
+    x = make_cloud(g, 1, 140000, near_origin=4)
+    got = ps.furthest_point_sample(x.to(DEV), 40)
+    assert np.array_equal(got.cpu().numpy(), O.fps(x.numpy(), 40))
 
 
 def test_fps_all_points_inside_skip_ball():
