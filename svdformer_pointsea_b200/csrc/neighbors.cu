@@ -37,12 +37,31 @@ __device__ __forceinline__ float knn_dist(float qx, float qy, float qz, float qq
   return __fadd_rn(__fadd_rn(__fmul_rn(-2.0f, dot), qq), pp);
 }
 
+// Warp-wide bitonic sort of one (distance, index) pair per lane, ascending by (d, i).
+__device__ __forceinline__ void warp_bitonic_sort(float& d, int& i, int lane) {
+#pragma unroll
+  for (int k = 2; k <= 32; k <<= 1) {
+#pragma unroll
+    for (int j = k >> 1; j > 0; j >>= 1) {
+      const float od = __shfl_xor_sync(0xffffffffu, d, j);
+      const int oi = __shfl_xor_sync(0xffffffffu, i, j);
+      const bool up = ((lane & k) == 0);          // this k-block sorts ascending
+      const bool lower = ((lane & j) == 0);       // this lane keeps the smaller of the pair
+      const bool other_less = (od < d) || (od == d && oi < i);
+      const bool take = (lower == up) ? other_less : !other_less;
+      if (take) { d = od; i = oi; }
+    }
+  }
+}
+
+// One warp per query; candidates staged as float4 {x, y, z, |p|^2}.  List of the KK = k + skip
+// best lives in lanes 0..KK-1 (R registers per lane when KK > 32), ascending by (dist, index).
 template <int R, int VAR>
 __global__ void __launch_bounds__(NB_THREADS) knn_kernel(const float* __restrict__ xyz,
                                                          const float* __restrict__ new_xyz,
                                                          int* __restrict__ idx, int N, int S, int k,
                                                          int skip, int qpc) {
-  __shared__ float sx[NB_TILE], sy[NB_TILE], sz[NB_TILE], sp[NB_TILE];
+  __shared__ float4 sp[NB_TILE];
   const int b = blockIdx.y, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const float* cloud = xyz + (size_t)b * N * 3;
   const float INF = __int_as_float(0x7f800000);
@@ -56,7 +75,7 @@ __global__ void __launch_bounds__(NB_THREADS) knn_kernel(const float* __restrict
       const float x = __ldg(cloud + (size_t)(ts + i) * 3 + 0);
       const float y = __ldg(cloud + (size_t)(ts + i) * 3 + 1);
       const float z = __ldg(cloud + (size_t)(ts + i) * 3 + 2);
-      sx[i] = x; sy[i] = y; sz[i] = z; sp[i] = sumsq_torch(x, y, z);
+      sp[i] = make_float4(x, y, z, sumsq_torch(x, y, z));
     }
   };
   if (single_tile) { stage(0, N); __syncthreads(); }
@@ -80,40 +99,79 @@ __global__ void __launch_bounds__(NB_THREADS) knn_kernel(const float* __restrict
       const int cnt = min(NB_TILE, N - ts);
       if (!single_tile) { __syncthreads(); stage(ts, cnt); __syncthreads(); }
       if (!valid) continue;
-      for (int j0 = 0; j0 < cnt; j0 += 32) {
-        const int j = j0 + lane;
+      int j0 = 0;
+      if (R == 1 && ts == 0) {
+        // the first 32 candidates seed the list with one bitonic sort instead of 32 insertions
         float d = INF;
-        if (j < cnt) d = knn_dist<VAR>(qx, qy, qz, qq, sx[j], sy[j], sz[j], sp[j]);
-        unsigned mask = __ballot_sync(0xffffffffu, d < thr);
-        while (mask) {
-          const int src = __ffs(mask) - 1;
-          mask &= mask - 1;
-          const float cd = __shfl_sync(0xffffffffu, d, src);
-          if (!(cd < thr)) continue;  // the threshold may have tightened inside this group
-          const int ci = ts + j0 + src;
-          // position = number of entries <= cd (the list is sorted; equal distances keep the
-          // earlier, i.e. lower, index in front)
-          int pos = 0;
+        int ci = lane;
+        if (lane < cnt) { const float4 c = sp[lane]; d = knn_dist<VAR>(qx, qy, qz, qq, c.x, c.y, c.z, c.w); }
+        warp_bitonic_sort(d, ci, lane);
+        ld[0] = d; li[0] = ci;
+        thr = __shfl_sync(0xffffffffu, ld[0], (KK - 1) & 31);
+        j0 = 32;
+      }
+      if (R == 1) {
+        // two candidates per lane per step (indices j0+lane and j0+32+lane); insertion is
+        // branch-free: entries > cd move one lane up, the first of them takes the candidate; equal
+        // distances stay in front (they have lower indices: candidates arrive in index order)
+        for (; j0 < cnt; j0 += 64) {
+          float d0 = INF, d1 = INF;
+          if (j0 + lane < cnt) { const float4 c = sp[j0 + lane]; d0 = knn_dist<VAR>(qx, qy, qz, qq, c.x, c.y, c.z, c.w); }
+          if (j0 + 32 + lane < cnt) { const float4 c = sp[j0 + 32 + lane]; d1 = knn_dist<VAR>(qx, qy, qz, qq, c.x, c.y, c.z, c.w); }
 #pragma unroll
-          for (int r = 0; r < R; r++) pos += __popc(__ballot_sync(0xffffffffu, ld[r] <= cd));
-#pragma unroll
-          for (int r = R - 1; r >= 0; r--) {
-            float ud = __shfl_up_sync(0xffffffffu, ld[r], 1);
-            int ui = __shfl_up_sync(0xffffffffu, li[r], 1);
-            if (r > 0) {
-              const float pd = __shfl_sync(0xffffffffu, ld[r - 1], 31);
-              const int pi = __shfl_sync(0xffffffffu, li[r - 1], 31);
-              if (lane == 0) { ud = pd; ui = pi; }
+          for (int h = 0; h < 2; h++) {
+            const float d = h ? d1 : d0;
+            unsigned mask = __ballot_sync(0xffffffffu, d < thr);
+            while (mask) {
+              const int src = __ffs(mask) - 1;
+              mask &= mask - 1;
+              const float cd = __shfl_sync(0xffffffffu, d, src);
+              const int ci = ts + j0 + 32 * h + src;
+              const bool ok = cd < thr;  // warp-uniform; the threshold may have tightened in this group
+              const float ud = __shfl_up_sync(0xffffffffu, ld[0], 1);
+              const int ui = __shfl_up_sync(0xffffffffu, li[0], 1);
+              const bool shift = ok && (lane > 0) && (ud > cd);
+              const bool ins = ok && (ld[0] > cd);
+              ld[0] = shift ? ud : (ins ? cd : ld[0]);
+              li[0] = shift ? ui : (ins ? ci : li[0]);
+              thr = __shfl_sync(0xffffffffu, ld[0], (KK - 1) & 31);
             }
-            const int e = r * 32 + lane;
-            if (e > pos) { ld[r] = ud; li[r] = ui; }
-            else if (e == pos) { ld[r] = cd; li[r] = ci; }
           }
-          float tv = ld[0];
+        }
+      } else {
+        for (; j0 < cnt; j0 += 32) {
+          const int j = j0 + lane;
+          float d = INF;
+          if (j < cnt) { const float4 c = sp[j]; d = knn_dist<VAR>(qx, qy, qz, qq, c.x, c.y, c.z, c.w); }
+          unsigned mask = __ballot_sync(0xffffffffu, d < thr);
+          while (mask) {
+            const int src = __ffs(mask) - 1;
+            mask &= mask - 1;
+            const float cd = __shfl_sync(0xffffffffu, d, src);
+            if (!(cd < thr)) continue;  // the threshold may have tightened inside this group
+            const int ci = ts + j0 + src;
+            int pos = 0;
 #pragma unroll
-          for (int r = 1; r < R; r++)
-            if (r == ((KK - 1) >> 5)) tv = ld[r];
-          thr = __shfl_sync(0xffffffffu, tv, (KK - 1) & 31);
+            for (int r = 0; r < R; r++) pos += __popc(__ballot_sync(0xffffffffu, ld[r] <= cd));
+#pragma unroll
+            for (int r = R - 1; r >= 0; r--) {
+              float ud = __shfl_up_sync(0xffffffffu, ld[r], 1);
+              int ui = __shfl_up_sync(0xffffffffu, li[r], 1);
+              if (r > 0) {
+                const float pd = __shfl_sync(0xffffffffu, ld[r - 1], 31);
+                const int pi = __shfl_sync(0xffffffffu, li[r - 1], 31);
+                if (lane == 0) { ud = pd; ui = pi; }
+              }
+              const int e = r * 32 + lane;
+              if (e > pos) { ld[r] = ud; li[r] = ui; }
+              else if (e == pos) { ld[r] = cd; li[r] = ci; }
+            }
+            float tv = ld[0];
+#pragma unroll
+            for (int r = 1; r < R; r++)
+              if (r == ((KK - 1) >> 5)) tv = ld[r];
+            thr = __shfl_sync(0xffffffffu, tv, (KK - 1) & 31);
+          }
         }
       }
     }
