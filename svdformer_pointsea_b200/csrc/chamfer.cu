@@ -321,6 +321,10 @@ extern "C" int ps_chamfer_fwd(const float* xyz1, const float* xyz2, float* dist1
   cudaStream_t stream = (cudaStream_t)stream_;
   const int nsm = sm_count(dev);
 
+  {
+    const int rc = chamfer_fwd_symmetric(xyz1, xyz2, dist1, dist2, idx1, idx2, B, N, M, dev, stream);
+    if (rc <= 0) return rc;  // handled (PS_OK) or failed; 1 = shape better served by the two-pass kernel
+  }
   const int maxq = N > M ? N : M;
   const int Q = maxq <= 256 ? 1 : (maxq <= 1024 ? 2 : 4);
   ChamferParams p;

@@ -1,0 +1,305 @@
+// Chamfer forward, symmetric single-pass variant: every pair distance is evaluated ONCE and used
+// for both directions.
+//
+// The reference evaluates d(a_i, b_j) twice, once per direction (chamfer3D.cu:142-143).  Its
+// expression d = fma(dz,dz, fma(dx,dx, dy*dy)) only squares the differences, and
+// (b - a) == -(a - b) exactly in IEEE arithmetic, so both evaluations are bit-identical.  This
+// kernel therefore halves the FP32-pipe work (the bound of the two-pass kernel in chamfer.cu):
+//   * cloud A (the larger one) is held in registers, Q consecutive points per thread
+//     (i = tile*256*Q + tid*Q + q); cloud B streams through shared memory as SoA tiles;
+//   * row side (min over B for each A point): FMNMX3 running minimum + per-step bookkeeping and a
+//     one-step re-evaluation for the argmin, exactly as in chamfer.cu;
+//   * column side (min over A for each B point): per 4-target step every lane folds its Q
+//     distances per target (FMNMX3), the warp folds the 32 lanes with REDUX.MIN on the fp32 bit
+//     pattern (distances are >= 0, so unsigned order == float order), the lowest lane holding the
+//     minimum is found with one ballot; the results of 8 steps are kept in registers (lane l owns
+//     B point 32k+l) and merged as (min_bits << 32 | thread id) into a per-tile shared-memory
+//     key array with one 64-bit atomicMin per lane.  Because a thread's points are
+//     consecutive in i and thread ids order the same way, the key's minimum is the lowest-index
+//     holder of the minimum distance inside the CTA.  After the tile, each B point re-evaluates
+//     the Q points of the recorded thread (A tile kept in shared memory) to get the exact index;
+//   * partial results of both sides (B splits for rows, A tiles for columns) meet in global
+//     64-bit keys (dist_bits << 32 | idx) merged with atomicMin, then an unpack kernel.
+// Index semantics are the reference's on both sides: lowest index among exact minima.
+#include "common.cuh"
+
+#include <cstdlib>
+
+namespace ps {
+
+constexpr int CS_THREADS = 256;
+constexpr int CS_TILE = 2048;  // B points per shared-memory tile
+constexpr int CS_STEP = 4;
+
+struct SymParams {
+  const float* a;   // (B, na, 3)  register side
+  const float* b;   // (B, nb, 3)  streamed side
+  u64* keys_a;      // (B, na) row-side merge keys   (min over b)
+  u64* keys_b;      // (B, nb) column-side merge keys (min over a)
+  int na, nb;
+  int natiles;      // A tiles per cloud
+  int nsplit;       // B splits per cloud
+  int split_len;    // multiple of CS_STEP
+};
+
+static __global__ void sym_unpack_kernel(const u64* __restrict__ keys, float* __restrict__ dist,
+                                         int* __restrict__ idx, size_t n) {
+  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) {
+    const u64 k = keys[i];
+    dist[i] = __uint_as_float((unsigned)(k >> 32));
+    idx[i] = (int)(unsigned)k;
+  }
+}
+
+template <int Q>
+__global__ void __launch_bounds__(CS_THREADS, 2) chamfer_sym_kernel(const SymParams p) {
+  constexpr int TA = CS_THREADS * Q;
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  float* sx = reinterpret_cast<float*>(smem_raw);
+  float* sy = sx + CS_TILE;
+  float* sz = sy + CS_TILE;
+  u64* colkey = reinterpret_cast<u64*>(sz + CS_TILE);
+  float* ax = reinterpret_cast<float*>(colkey + CS_TILE);
+  float* ay = ax + TA;
+  float* az = ay + TA;
+
+  int unit = blockIdx.x;
+  const int split = unit % p.nsplit;
+  unit /= p.nsplit;
+  const int at = unit % p.natiles;
+  const int b = unit / p.natiles;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int na = p.na, nb = p.nb;
+  const float INF = __int_as_float(0x7f800000);
+
+  // ---- A points into registers (and shared memory for the column-side index recovery) -------
+  u64 nqx[Q], nqy[Q], nqz[Q];
+  float best[Q];
+  int cstep[Q];
+  const float* abase = p.a + (size_t)b * na * 3;
+#pragma unroll
+  for (int q = 0; q < Q; q++) {
+    const int i = at * TA + tid * Q + q;
+    const bool valid = i < na;
+    // invalid slots sit at +inf: every distance to them is +inf (or NaN against +inf padding),
+    // which neither FMNMX nor the integer REDUX ever selects over a finite value
+    const float x = valid ? __ldg(abase + (size_t)i * 3 + 0) : INF;
+    const float y = valid ? __ldg(abase + (size_t)i * 3 + 1) : 0.f;
+    const float z = valid ? __ldg(abase + (size_t)i * 3 + 2) : 0.f;
+    ax[tid * Q + q] = x; ay[tid * Q + q] = y; az[tid * Q + q] = z;
+    nqx[q] = pack2(-x, -x); nqy[q] = pack2(-y, -y); nqz[q] = pack2(-z, -z);
+    best[q] = INF;
+    cstep[q] = 0;
+  }
+
+  const int t0 = split * p.split_len;
+  const int t1 = min(nb, t0 + p.split_len);
+  const float* bcloud = p.b + (size_t)b * nb * 3;
+
+  for (int ts = t0; ts < t1; ts += CS_TILE) {
+    const int cnt = min(CS_TILE, t1 - ts);
+    const int cnt_pad = (cnt + CS_STEP - 1) / CS_STEP * CS_STEP;
+    const float* tb = bcloud + (size_t)ts * 3;
+    const bool vec = (reinterpret_cast<uintptr_t>(tb) & 15) == 0;
+    __syncthreads();  // previous tile (and its column pass) fully consumed
+    for (int g = tid; g < cnt_pad / 4; g += CS_THREADS) {
+      float4 X, Y, Z;
+      if (vec && g * 4 + 4 <= cnt) {
+        const float4 a = __ldg(reinterpret_cast<const float4*>(tb + g * 12));
+        const float4 bb = __ldg(reinterpret_cast<const float4*>(tb + g * 12 + 4));
+        const float4 c = __ldg(reinterpret_cast<const float4*>(tb + g * 12 + 8));
+        X = make_float4(a.x, a.w, bb.z, c.y);
+        Y = make_float4(a.y, bb.x, bb.w, c.z);
+        Z = make_float4(a.z, bb.y, c.x, c.w);
+      } else {
+        float xs[4], ys[4], zs[4];
+#pragma unroll
+        for (int e = 0; e < 4; e++) {
+          const int pi = g * 4 + e;
+          const bool in = pi < cnt;
+          xs[e] = in ? __ldg(tb + pi * 3 + 0) : INF;
+          ys[e] = in ? __ldg(tb + pi * 3 + 1) : 0.f;
+          zs[e] = in ? __ldg(tb + pi * 3 + 2) : 0.f;
+        }
+        X = make_float4(xs[0], xs[1], xs[2], xs[3]);
+        Y = make_float4(ys[0], ys[1], ys[2], ys[3]);
+        Z = make_float4(zs[0], zs[1], zs[2], zs[3]);
+      }
+      *reinterpret_cast<float4*>(&sx[g * 4]) = X;
+      *reinterpret_cast<float4*>(&sy[g * 4]) = Y;
+      *reinterpret_cast<float4*>(&sz[g * 4]) = Z;
+    }
+    for (int j = tid; j < cnt_pad; j += CS_THREADS) colkey[j] = ~0ull;
+    __syncthreads();
+
+    // ---- scan: 4 B points x Q A points per lane per step ---------------------------------------
+    // Column results are collected in registers for 8 steps (32 B points: lane l keeps the key of
+    // B point j32 + l) and merged into shared memory with ONE 64-bit atomicMin per lane.
+    int step = (ts - t0) / CS_STEP;
+    for (int j32 = 0; j32 < cnt_pad; j32 += 32) {
+      unsigned key_m = 0xffffffffu, key_t = 0u;
+      const int jend = min(cnt_pad, j32 + 32);
+#pragma unroll 2
+      for (int j = j32; j < jend; j += CS_STEP, step++) {
+        const ulonglong2 X = *reinterpret_cast<const ulonglong2*>(&sx[j]);
+        const ulonglong2 Y = *reinterpret_cast<const ulonglong2*>(&sy[j]);
+        const ulonglong2 Z = *reinterpret_cast<const ulonglong2*>(&sz[j]);
+        float c0 = INF, c1 = INF, c2 = INF, c3 = INF;  // this lane's minimum over its Q points, per B point
+#pragma unroll
+        for (int q = 0; q < Q; q += 2) {
+          const u64 d01 = dist2x2(X.x, Y.x, Z.x, nqx[q], nqy[q], nqz[q]);
+          const u64 d23 = dist2x2(X.y, Y.y, Z.y, nqx[q], nqy[q], nqz[q]);
+          float nb0 = min3(best[q], lo2(d01), hi2(d01));
+          nb0 = min3(nb0, lo2(d23), hi2(d23));
+          if (nb0 < best[q]) cstep[q] = step;
+          best[q] = nb0;
+          const u64 e01 = dist2x2(X.x, Y.x, Z.x, nqx[q + 1], nqy[q + 1], nqz[q + 1]);
+          const u64 e23 = dist2x2(X.y, Y.y, Z.y, nqx[q + 1], nqy[q + 1], nqz[q + 1]);
+          float nb1 = min3(best[q + 1], lo2(e01), hi2(e01));
+          nb1 = min3(nb1, lo2(e23), hi2(e23));
+          if (nb1 < best[q + 1]) cstep[q + 1] = step;
+          best[q + 1] = nb1;
+          c0 = min3(c0, lo2(d01), lo2(e01));
+          c1 = min3(c1, hi2(d01), hi2(e01));
+          c2 = min3(c2, lo2(d23), lo2(e23));
+          c3 = min3(c3, hi2(d23), hi2(e23));
+        }
+        // warp minimum per B point + lowest lane holding it; the owner lane of each B point keeps it
+        const unsigned b0 = __float_as_uint(c0), b1 = __float_as_uint(c1), b2 = __float_as_uint(c2), b3 = __float_as_uint(c3);
+        const unsigned m0 = __reduce_min_sync(0xffffffffu, b0);
+        const unsigned m1 = __reduce_min_sync(0xffffffffu, b1);
+        const unsigned m2 = __reduce_min_sync(0xffffffffu, b2);
+        const unsigned m3 = __reduce_min_sync(0xffffffffu, b3);
+        const unsigned l0 = __ffs(__ballot_sync(0xffffffffu, b0 == m0)) - 1;
+        const unsigned l1 = __ffs(__ballot_sync(0xffffffffu, b1 == m1)) - 1;
+        const unsigned l2 = __ffs(__ballot_sync(0xffffffffu, b2 == m2)) - 1;
+        const unsigned l3 = __ffs(__ballot_sync(0xffffffffu, b3 == m3)) - 1;
+        const int o = lane - (j - j32);  // 0..3 for the four owner lanes of this step
+        if (o == 0) { key_m = m0; key_t = l0; }
+        if (o == 1) { key_m = m1; key_t = l1; }
+        if (o == 2) { key_m = m2; key_t = l2; }
+        if (o == 3) { key_m = m3; key_t = l3; }
+      }
+      if (j32 + lane < cnt_pad)
+        atomicMin(&colkey[j32 + lane], ((u64)key_m << 32) | (unsigned)(warp * 32 + key_t));
+    }
+    __syncthreads();  // all column keys of this tile are final
+
+    // ---- column side: exact index inside the recorded thread's Q points, then global merge ----
+    for (int jj = tid; jj < cnt; jj += CS_THREADS) {
+      const u64 key = colkey[jj];
+      const unsigned mbits = (unsigned)(key >> 32);
+      const int tcand = (int)(unsigned)key;
+      const float bx = sx[jj], by = sy[jj], bz = sz[jj];
+      int found = 0;
+#pragma unroll
+      for (int q = Q - 1; q >= 0; q--) {
+        const float d = dist2_ref(bx - ax[tcand * Q + q], by - ay[tcand * Q + q], bz - az[tcand * Q + q]);
+        if (__float_as_uint(d) == mbits) found = q;
+      }
+      const int ia = at * TA + tcand * Q + found;
+      atomicMin(&p.keys_b[(size_t)b * nb + ts + jj], ((u64)mbits << 32) | (unsigned)ia);
+    }
+  }
+
+  // ---- row side: first B point of the remembered step that reproduces `best` --------------------
+  const int last_ts = t0 + ((t1 - t0 - 1) / CS_TILE) * CS_TILE;
+#pragma unroll
+  for (int q = 0; q < Q; q++) {
+    const int i = at * TA + tid * Q + q;
+    const int base = t0 + cstep[q] * CS_STEP;
+    u64 d01, d23;
+    if (base >= last_ts) {
+      const int off = base - last_ts;
+      const ulonglong2 X = *reinterpret_cast<const ulonglong2*>(&sx[off]);
+      const ulonglong2 Y = *reinterpret_cast<const ulonglong2*>(&sy[off]);
+      const ulonglong2 Z = *reinterpret_cast<const ulonglong2*>(&sz[off]);
+      d01 = dist2x2(X.x, Y.x, Z.x, nqx[q], nqy[q], nqz[q]);
+      d23 = dist2x2(X.y, Y.y, Z.y, nqx[q], nqy[q], nqz[q]);
+    } else {
+      const float* tp = bcloud + (size_t)base * 3;
+      float px[4], py[4], pz[4];
+#pragma unroll
+      for (int e = 0; e < 4; e++) { px[e] = __ldg(tp + e * 3 + 0); py[e] = __ldg(tp + e * 3 + 1); pz[e] = __ldg(tp + e * 3 + 2); }
+      d01 = dist2x2(pack2(px[0], px[1]), pack2(py[0], py[1]), pack2(pz[0], pz[1]), nqx[q], nqy[q], nqz[q]);
+      d23 = dist2x2(pack2(px[2], px[3]), pack2(py[2], py[3]), pack2(pz[2], pz[3]), nqx[q], nqy[q], nqz[q]);
+    }
+    int found = 0;
+    if (hi2(d23) == best[q]) found = 3;
+    if (lo2(d23) == best[q]) found = 2;
+    if (hi2(d01) == best[q]) found = 1;
+    if (lo2(d01) == best[q]) found = 0;
+    if (i >= na) continue;
+    atomicMin(&p.keys_a[(size_t)b * na + i], ((u64)__float_as_uint(best[q]) << 32) | (unsigned)(base + found));
+  }
+}
+
+template <int Q>
+static int launch_sym(const SymParams& p, int grid, cudaStream_t stream) {
+  const size_t smem = (size_t)3 * CS_TILE * 4 + (size_t)CS_TILE * 8 + (size_t)3 * CS_THREADS * Q * 4;
+  auto kern = chamfer_sym_kernel<Q>;
+  PS_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  kern<<<grid, CS_THREADS, smem, stream>>>(p);
+  PS_LAUNCH_CHECK();
+  return PS_OK;
+}
+
+// Returns PS_OK when it handled the call, 1 when the shape is better served by the two-pass kernel.
+int chamfer_fwd_symmetric(const float* xyz1, const float* xyz2, float* dist1, float* dist2, int* idx1,
+                          int* idx2, int B, int N, int M, int dev, cudaStream_t stream) {
+  if (const char* e = getenv("PS_CHAMFER_SYM"))
+    if (atoi(e) == 0) return 1;
+  const int big = N > M ? N : M, small = N > M ? M : N;
+  if (small < 256 || big < 1024) return 1;  // tiny clouds: launch-bound either way
+  const int nsm = sm_count(dev);
+  const bool a_is_1 = N >= M;  // the larger cloud sits in registers
+  SymParams p;
+  p.a = a_is_1 ? xyz1 : xyz2;
+  p.b = a_is_1 ? xyz2 : xyz1;
+  p.na = big;
+  p.nb = small;
+  int Q = 8;
+  if (const char* e = getenv("PS_CHAMFER_SYM_Q")) { const int v = atoi(e); if (v == 2 || v == 4 || v == 8) Q = v; }
+  while (Q > 2 && CS_THREADS * Q / 2 >= big) Q /= 2;
+  p.natiles = ceil_div(big, CS_THREADS * Q);
+  // B-side split: enough units for >= 3 waves of the 2 resident CTAs per SM (measured on C1:
+  // L=256 0.339 ms, L=512 0.330, L=1024 0.367, L=2048 0.375), but never below 256 targets per
+  // unit so the per-unit fixed cost (A load, column pass, merge atomics) stays small.
+  const int slots = nsm * 2;
+  const long long base_units = (long long)B * p.natiles;
+  int nsplit = (int)((3ll * slots + base_units - 1) / base_units);
+  const int max_split = small / 256 > 0 ? small / 256 : 1;
+  if (nsplit > max_split) nsplit = max_split;
+  if (nsplit < 1) nsplit = 1;
+  int bestL = ceil_div(small, nsplit);
+  bestL = (bestL + CS_STEP - 1) / CS_STEP * CS_STEP;
+  if (const char* e = getenv("PS_CHAMFER_SPLIT")) { const int v = atoi(e); if (v >= CS_STEP) bestL = (v + 3) / 4 * 4; }
+  p.split_len = bestL;
+  p.nsplit = ceil_div(small, bestL);
+
+  const size_t nka = (size_t)B * big, nkb = (size_t)B * small;
+  u64* scratch = nullptr;
+  if (int rc = scratch_alloc((void**)&scratch, (nka + nkb) * sizeof(u64), dev, stream)) return rc;
+  PS_CUDA(cudaMemsetAsync(scratch, 0xFF, (nka + nkb) * sizeof(u64), stream));
+  p.keys_a = scratch;
+  p.keys_b = scratch + nka;
+  const int grid = B * p.natiles * p.nsplit;
+  int rc;
+  if (Q == 8) rc = launch_sym<8>(p, grid, stream);
+  else if (Q == 4) rc = launch_sym<4>(p, grid, stream);
+  else rc = launch_sym<2>(p, grid, stream);
+  if (rc) return rc;
+  float* da = a_is_1 ? dist1 : dist2;
+  int* ia = a_is_1 ? idx1 : idx2;
+  float* db = a_is_1 ? dist2 : dist1;
+  int* ib = a_is_1 ? idx2 : idx1;
+  sym_unpack_kernel<<<ceil_div(nka, 256), 256, 0, stream>>>(p.keys_a, da, ia, nka);
+  PS_LAUNCH_CHECK();
+  sym_unpack_kernel<<<ceil_div(nkb, 256), 256, 0, stream>>>(p.keys_b, db, ib, nkb);
+  PS_LAUNCH_CHECK();
+  PS_CUDA(cudaFreeAsync(scratch, stream));
+  return PS_OK;
+}
+
+}  // namespace ps

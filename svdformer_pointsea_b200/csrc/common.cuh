@@ -62,6 +62,10 @@ int sm_count(int dev);
 // stream-ordered scratch allocation (pool keeps freed blocks cached); free with cudaFreeAsync
 int scratch_alloc(void** ptr, size_t bytes, int dev, cudaStream_t stream);
 
+// chamfer_sym.cu: PS_OK when handled, 1 when the two-pass kernel should run instead
+int chamfer_fwd_symmetric(const float* xyz1, const float* xyz2, float* dist1, float* dist2, int* idx1,
+                          int* idx2, int B, int N, int M, int dev, cudaStream_t stream);
+
 static inline int ceil_div(long long a, long long b) { return (int)((a + b - 1) / b); }
 
 // ---- device arithmetic ----------------------------------------------------------------------

@@ -52,6 +52,24 @@ def test_chamfer_fwd_bwd_vs_oracle(B, N, M, dup):
     assert_close_rel(g2.cpu().numpy(), og2, what="gradxyz2")
 
 
+@pytest.mark.parametrize("sym,q", [("1", "8"), ("1", "4"), ("1", "2"), ("0", "8")])
+@pytest.mark.parametrize("B,N,M,dup", [(2, 2048, 4096, 700), (3, 5000, 1300, 300), (1, 16384, 2048, 548),
+                                       (2, 1024, 1024, 1000), (1, 2050, 257, 0), (1, 300, 9000, 100)])
+def test_chamfer_symmetric_and_two_pass_kernels_agree_with_oracle(B, N, M, dup, sym, q, monkeypatch):
+    """Both forward kernels (single-pass symmetric, two-pass) at every register blocking, with
+    heavy duplication inside and across the clouds (exact ties on both sides)."""
+    monkeypatch.setenv("PS_CHAMFER_SYM", sym)
+    monkeypatch.setenv("PS_CHAMFER_SYM_Q", q)
+    g = torch.Generator().manual_seed(900 + N + M)
+    a, b = make_cloud(g, B, N, dup=min(dup, N - 1)), make_cloud(g, B, M, dup=min(dup, M - 1))
+    n_shared = min(N, M) // 3
+    b[:, :n_shared] = a[:, N - n_shared:]  # cross-cloud exact matches at different indices
+    d1, d2, i1, i2 = ps.chamfer_forward(a.to(DEV), b.to(DEV))
+    od1, od2, oi1, oi2 = O.chamfer_fwd(a.numpy(), b.numpy())
+    assert np.array_equal(i1.cpu().numpy(), oi1) and np.array_equal(i2.cpu().numpy(), oi2)
+    assert np.array_equal(d1.cpu().numpy(), od1) and np.array_equal(d2.cpu().numpy(), od2)
+
+
 def test_chamfer_golden():
     z = load_golden("chamfer")
     for name in ("small", "tiles", "dups", "tiny"):
