@@ -60,6 +60,13 @@ int ps_chamfer_bwd(const float* xyz1, const float* xyz2, const float* graddist1,
                    const float* graddist2, const int* idx1, const int* idx2, float* gradxyz1,
                    float* gradxyz2, int B, int N, int M, int dev, void* stream);
 
+/* Fused reduction of Chamfer's outputs as the callers reduce them (utils/loss_utils.py:10-31 `mean`,
+ * `mean(sqrt)`; :98-103 per-cloud means): out6 (6 doubles, device) = { sum sqrt(dist1),
+ * sum sqrt(dist2), sum dist1, sum dist2, n1, n2 }.  One launch; these partial sums and counts are
+ * what the multi-GPU path all-reduces. */
+int ps_chamfer_sums(const float* dist1, const float* dist2, double* out6, long long n1, long long n2,
+                    int dev, void* stream);
+
 /* ---- Furthest point sampling ------------------------------------------------------------
  * Replaces furthest_point_sampling_kernel_wrapper (pointnet2_ops/_ext-src/src/sampling_gpu.cu:175-229,
  * kernel :69-173; pybind `_ext.furthest_point_sampling`, sampling.cpp:66-87).

@@ -48,6 +48,20 @@ def chamfer_backward(xyz1, xyz2, graddist1, graddist2, idx1, idx2):
     return gradxyz1, gradxyz2
 
 
+def chamfer_sums(dist1, dist2):
+    """One-launch reduction of Chamfer outputs: float64 tensor [sum sqrt(d1), sum sqrt(d2), sum d1,
+    sum d2, numel(d1), numel(d2)] on the device (no host sync, no autograd) — the partial sums behind
+    utils/loss_utils.py:10-31 and the only data the multi-GPU path all-reduces."""
+    L.require(dist1, "dist1", torch.float32, dist1.dim())
+    L.require(dist2, "dist2", torch.float32, dist2.dim())
+    dev = L.same_device(dist1, dist2)
+    out = torch.empty(6, device=dist1.device, dtype=torch.float64)
+    rc = L.load().ps_chamfer_sums(L.ptr(dist1), L.ptr(dist2), L.ptr(out), dist1.numel(), dist2.numel(), dev,
+                                  L.stream_ptr(dev))
+    L.check(rc, "ps_chamfer_sums")
+    return out
+
+
 class chamfer_3DFunction(Function):
     """Drop-in for dist_chamfer_3D.chamfer_3DFunction (dist_chamfer_3D.py:26-64)."""
 

@@ -380,3 +380,60 @@ extern "C" int ps_chamfer_bwd(const float* xyz1, const float* xyz2, const float*
   PS_LAUNCH_CHECK();
   return PS_OK;
 }
+
+// ---- fused loss/metric partial sums ---------------------------------------------------------------
+// The reductions the callers apply to Chamfer's outputs (utils/loss_utils.py:10-31,98-103:
+// mean(d), mean(sqrt(d)) per side) as ONE launch instead of ~10 small torch kernels:
+// out[0] = sum sqrt(dist1), out[1] = sum sqrt(dist2), out[2] = sum dist1, out[3] = sum dist2,
+// accumulated in double; out[4], out[5] = the element counts.  These four numbers (plus the element counts) are exactly what the
+// multi-GPU path all-reduces.
+namespace ps {
+__global__ void __launch_bounds__(256) chamfer_sums_kernel(const float* __restrict__ d1, const float* __restrict__ d2,
+                                                           double* __restrict__ out, long long n1, long long n2) {
+  double s[4] = {0.0, 0.0, 0.0, 0.0};
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n1; i += stride) {
+    const float v = __ldg(d1 + i);
+    s[0] += (double)sqrtf(v);
+    s[2] += (double)v;
+  }
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n2; i += stride) {
+    const float v = __ldg(d2 + i);
+    s[1] += (double)sqrtf(v);
+    s[3] += (double)v;
+  }
+  __shared__ double sh[8][4];
+#pragma unroll
+  for (int k = 0; k < 4; k++) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) s[k] += __shfl_xor_sync(0xffffffffu, s[k], o);
+  }
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  if (lane == 0) { sh[warp][0] = s[0]; sh[warp][1] = s[1]; sh[warp][2] = s[2]; sh[warp][3] = s[3]; }
+  __syncthreads();
+  if (threadIdx.x < 4) {
+    double t = 0.0;
+#pragma unroll
+    for (int w = 0; w < 8; w++) t += sh[w][threadIdx.x];
+    atomicAdd(out + threadIdx.x, t);
+  }
+  if (blockIdx.x == 0 && threadIdx.x == 4) { out[4] = (double)n1; out[5] = (double)n2; }  // element counts
+}
+}  // namespace ps
+
+extern "C" int ps_chamfer_sums(const float* dist1, const float* dist2, double* out4, long long n1,
+                               long long n2, int dev, void* stream_) {
+  PS_REQUIRE(n1 >= 0 && n2 >= 0 && out4 && (n1 == 0 || dist1) && (n2 == 0 || dist2), "ps_chamfer_sums: bad arguments");
+  DeviceGuard guard(dev);
+  if (!guard.ok) return set_error(PS_ERR_CUDA, "ps_chamfer_sums: cannot select device %d", dev);
+  cudaStream_t stream = (cudaStream_t)stream_;
+  PS_CUDA(cudaMemsetAsync(out4, 0, 6 * sizeof(double), stream));
+  const long long n = n1 > n2 ? n1 : n2;
+  if (n == 0) return PS_OK;
+  int grid = ceil_div(n, 256 * 8);
+  const int cap = sm_count(dev) * 4;
+  if (grid > cap) grid = cap;
+  chamfer_sums_kernel<<<grid, 256, 0, stream>>>(dist1, dist2, out4, n1, n2);
+  PS_LAUNCH_CHECK();
+  return PS_OK;
+}

@@ -68,6 +68,16 @@ class LossSums:
         return out
 
 
+def chamfer_metric_means(d1, d2, group=None):
+    """Global means {sqrt_d1, sqrt_d2, d1, d2} of Chamfer outputs over all ranks' shards: one fused
+    reduction kernel (ps_chamfer_sums) + ONE all-reduce of 6 doubles.  Metric path (no autograd)."""
+    from .chamfer import chamfer_sums
+    vec = chamfer_sums(d1, d2)  # [sum sqrt d1, sum sqrt d2, sum d1, sum d2, n1, n2]
+    if dist.is_initialized() and dist.get_world_size(group) > 1:
+        dist.all_reduce(vec, op=dist.ReduceOp.SUM, group=group)
+    return {"sqrt_d1": vec[0] / vec[4], "sqrt_d2": vec[1] / vec[5], "d1": vec[2] / vec[4], "d2": vec[3] / vec[5]}
+
+
 def chamfer_loss_terms(sums, name, d1, d2, sqrt=True):
     """Registers the two directional means of one Chamfer term (chamfer / chamfer_sqrt,
     utils/loss_utils.py:10-19)."""

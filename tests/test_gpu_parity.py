@@ -70,6 +70,18 @@ def test_chamfer_symmetric_and_two_pass_kernels_agree_with_oracle(B, N, M, dup, 
     assert np.array_equal(d1.cpu().numpy(), od1) and np.array_equal(d2.cpu().numpy(), od2)
 
 
+def test_chamfer_sums_match_torch_reductions():
+    g = torch.Generator().manual_seed(12)
+    a, b = make_cloud(g, 3, 777).to(DEV), make_cloud(g, 3, 1500).to(DEV)
+    d1, d2, _, _ = ps.chamfer_forward(a, b)
+    s = ps.chamfer_sums(d1, d2).cpu().numpy()
+    want = [torch.sqrt(d1).double().sum().item(), torch.sqrt(d2).double().sum().item(), d1.double().sum().item(), d2.double().sum().item()]
+    assert np.allclose(s[:4], want, rtol=1e-9) and s[4] == d1.numel() and s[5] == d2.numel()
+    from svdformer_pointsea_b200.dist import chamfer_metric_means
+    m = chamfer_metric_means(d1, d2)
+    assert abs(m["sqrt_d1"].item() - torch.sqrt(d1).double().mean().item()) < 1e-12
+
+
 def test_chamfer_golden():
     z = load_golden("chamfer")
     for name in ("small", "tiles", "dups", "tiny"):
