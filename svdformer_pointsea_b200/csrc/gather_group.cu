@@ -23,6 +23,8 @@
 //     buffer); rows too long for shared memory fall back to memset + global RED.
 #include "common.cuh"
 
+#include <cstdlib>
+
 namespace ps {
 
 constexpr int GG_THREADS = 256;
@@ -219,6 +221,154 @@ __global__ void __launch_bounds__(GG_THREADS) scatter_direct_kernel(
   atomicAdd(gfeat + ((size_t)b * C + c) * N + i, __ldg(gout + ((size_t)b * C + c) * Mp + p));
 }
 
+// ---- backward through an inverse index (dense grouping: every source point appears many times) ---
+// grad_features[b,c,n] = sum over the positions p with idx[b,p] == n of grad_out[b,c,p].
+// The index tensor is shared by all C channels, so its inverse (CSR: for each source n the sorted
+// list of positions that reference it) is built ONCE per call; the reduction then becomes a
+// gather: no atomics in the channel loop, deterministic summation order (ascending p).
+//   csr_build_kernel   one CTA per cloud: histogram in shared memory, exclusive scan, fill, per-list
+//                      insertion sort, and per-source chunk boundaries (positions are processed in
+//                      chunks of CSR_CHUNK so a chunk of a grad_out row fits a shared-memory stage)
+//   scatter_csr_kernel persistent CTA per (cloud, CPB channels): a 2-stage ring of CSR_CHUNK-float
+//                      buffers filled by 1-D bulk async copies (TMA engine, mbarrier completion)
+//                      while the other stage is being gathered from; accumulators in registers.
+constexpr int CSR_CHUNK = 16384;   // positions per stage (64 KB)
+constexpr int CSR_THREADS = 512;
+constexpr int CSR_BUILD_THREADS = 1024;
+
+__global__ void __launch_bounds__(CSR_BUILD_THREADS) csr_build_kernel(const int* __restrict__ idx, int* __restrict__ off_all,
+                                                                     int* __restrict__ bnd_all, int* __restrict__ inv_all,
+                                                                     int N, int Mp, int nchunks) {
+  extern __shared__ int sm_i[];
+  int* cnt = sm_i;             // N + 1
+  int* cur = sm_i + (N + 1);   // N
+  __shared__ int warp_tot[CSR_BUILD_THREADS / 32];
+  const int b = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int* ib = idx + (size_t)b * Mp;
+  int* off = off_all + (size_t)b * (N + 1);
+  int* bnd = bnd_all + (size_t)b * N * (nchunks + 1);
+  int* inv = inv_all + (size_t)b * Mp;
+  for (int n = tid; n <= N; n += CSR_BUILD_THREADS) cnt[n] = 0;
+  __syncthreads();
+  for (int p = tid; p < Mp; p += CSR_BUILD_THREADS) atomicAdd(&cnt[__ldg(ib + p)], 1);
+  __syncthreads();
+  // exclusive scan of cnt[0..N): each thread owns a contiguous run
+  const int per = (N + CSR_BUILD_THREADS - 1) / CSR_BUILD_THREADS;
+  const int lo = min(N, tid * per), hi = min(N, lo + per);
+  int run = 0;
+  for (int n = lo; n < hi; n++) run += cnt[n];
+  int incl = run;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) { const int v = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += v; }
+  if (lane == 31) warp_tot[warp] = incl;
+  __syncthreads();
+  if (warp == 0) {
+    int w = warp_tot[lane];
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) { const int v = __shfl_up_sync(0xffffffffu, w, o); if (lane >= o) w += v; }
+    warp_tot[lane] = w;  // inclusive over warps
+  }
+  __syncthreads();
+  int base = incl - run + (warp ? warp_tot[warp - 1] : 0);
+  for (int n = lo; n < hi; n++) { const int c = cnt[n]; cur[n] = base; off[n] = base; base += c; }
+  if (tid == 0) off[N] = Mp;
+  __syncthreads();
+  for (int p = tid; p < Mp; p += CSR_BUILD_THREADS) inv[atomicAdd(&cur[__ldg(ib + p)], 1)] = p;
+  __syncthreads();  // global writes of this CTA are visible to its own threads after the barrier
+  // sort each list ascending (deterministic summation order) and emit chunk boundaries
+  for (int n = tid; n < N; n += CSR_BUILD_THREADS) {
+    const int s = off[n], e = (n + 1 < N) ? off[n + 1] : Mp;
+    for (int i = s + 1; i < e; i++) {
+      const int v = inv[i];
+      int j = i - 1;
+      while (j >= s && inv[j] > v) { inv[j + 1] = inv[j]; j--; }
+      inv[j + 1] = v;
+    }
+    int q = s;
+    for (int k = 0; k <= nchunks; k++) {
+      const int limit = k * CSR_CHUNK;
+      while (q < e && inv[q] < limit) q++;
+      bnd[(size_t)n * (nchunks + 1) + k] = (k == nchunks) ? e : q;
+    }
+  }
+}
+
+template <int NPT>  // sources per thread = ceil(N / CSR_THREADS)
+__global__ void __launch_bounds__(CSR_THREADS, 1) scatter_csr_kernel(const float* __restrict__ gout, const int* __restrict__ bnd_all,
+                                                                     const int* __restrict__ inv_all, float* __restrict__ gfeat,
+                                                                     int C, int N, int Mp, int nchunks, int cpb) {
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  u64* bars = reinterpret_cast<u64*>(smem_raw);          // full[2]
+  float* stage0 = reinterpret_cast<float*>(smem_raw + 128);
+  float* stage1 = stage0 + CSR_CHUNK;
+  const int b = blockIdx.y, c0 = blockIdx.x * cpb, tid = threadIdx.x;
+  const int nch = min(cpb, C - c0);
+  const int* bnd = bnd_all + (size_t)b * N * (nchunks + 1);
+  const int* inv = inv_all + (size_t)b * Mp;
+  const int items = nch * nchunks;
+  if (tid == 0) {
+    mbar_init(smem_u32(&bars[0]), 1);
+    mbar_init(smem_u32(&bars[1]), 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
+  auto issue = [&](int item) {  // thread 0 only
+    const int c = c0 + item / nchunks, k = item % nchunks;
+    const int p0 = k * CSR_CHUNK, len = min(CSR_CHUNK, Mp - p0);
+    const unsigned bar = smem_u32(&bars[item & 1]);
+    mbar_arrive_expect_tx(bar, (unsigned)len * 4u);
+    bulk_g2s(smem_u32((item & 1) ? stage1 : stage0), gout + ((size_t)b * C + c) * Mp + p0, (unsigned)len * 4u, bar);
+  };
+  if (tid == 0) { issue(0); if (items > 1) issue(1); }
+  float acc[NPT];
+#pragma unroll
+  for (int i = 0; i < NPT; i++) acc[i] = 0.f;
+  for (int item = 0; item < items; item++) {
+    const int k = item % nchunks;
+    const float* st = (item & 1) ? stage1 : stage0;
+    while (!mbar_try_wait(smem_u32(&bars[item & 1]), (unsigned)(item >> 1) & 1u)) {}
+    const int p0 = k * CSR_CHUNK;
+    // list bounds of all NPT sources first, then up to 8 entries per source with all index loads
+    // in flight at once (the dependent chain inv[q] -> shared-memory read is what limits this loop)
+    int lo[NPT], hi[NPT];
+#pragma unroll
+    for (int i = 0; i < NPT; i++) {
+      const int n = tid + i * CSR_THREADS;
+      lo[i] = hi[i] = 0;
+      if (n < N) {
+        lo[i] = __ldg(bnd + (size_t)n * (nchunks + 1) + k);
+        hi[i] = __ldg(bnd + (size_t)n * (nchunks + 1) + k + 1);
+      }
+    }
+    int pp[NPT][8];
+#pragma unroll
+    for (int i = 0; i < NPT; i++)
+#pragma unroll
+      for (int u = 0; u < 8; u++) pp[i][u] = (lo[i] + u < hi[i]) ? __ldg(inv + lo[i] + u) : -1;
+#pragma unroll
+    for (int i = 0; i < NPT; i++) {
+      float a = acc[i];
+#pragma unroll
+      for (int u = 0; u < 8; u++)
+        if (pp[i][u] >= 0) a += st[pp[i][u] - p0];
+      for (int q = lo[i] + 8; q < hi[i]; q++) a += st[__ldg(inv + q) - p0];  // long lists: remainder
+      acc[i] = a;
+    }
+    if (k == nchunks - 1) {  // channel finished: write its row, reset
+      const int c = c0 + item / nchunks;
+      float* dst = gfeat + ((size_t)b * C + c) * N;
+#pragma unroll
+      for (int i = 0; i < NPT; i++) {
+        const int n = tid + i * CSR_THREADS;
+        if (n < N) dst[n] = acc[i];
+        acc[i] = 0.f;
+      }
+    }
+    __syncthreads();  // every thread is done with this stage before it is refilled
+    if (tid == 0 && item + 2 < items) issue(item + 2);
+  }
+}
+
 static const size_t GG_SMEM_MAX = 200 * 1024;
 
 static int gather_fwd_impl(const float* feat, const int* idx, float* out, int B, int C, int N,
@@ -233,24 +383,36 @@ static int gather_fwd_impl(const float* feat, const int* idx, float* out, int B,
   const int vec_ok = ((Mp & 3) == 0) && ((reinterpret_cast<uintptr_t>(idx) & 15) == 0) && ((reinterpret_cast<uintptr_t>(out) & 15) == 0);
   // Stage through shared memory when each feature element is reused (output >= 2x the input)
   // and 8 rows fit; otherwise gather straight from L1/L2.
-  constexpr int CT = 8;
+  int CT = 8;
+  int per_sm = 16;  // measured on C3 (B200): 4 -> 73 %, 8 -> 81 %, 16 -> 83 % of HBM peak (CT=8)
+  if (const char* e = getenv("PS_GATHER_CT")) { const int v = atoi(e); if (v == 4 || v == 8) CT = v; }
+  if (const char* e = getenv("PS_GATHER_PER_SM")) { const int v = atoi(e); if (v > 0) per_sm = v; }
   const size_t row_bytes = (size_t)N * 4;
   const bool staged = (long long)Mp >= 2ll * N && row_bytes * CT + 128 <= GG_SMEM_MAX / 2 && C >= 2;
   if (staged) {
     const size_t smem = 128 + row_bytes * CT;
     const int ctiles = ceil_div(C, CT);
-    // slices so that the grid covers ~4 CTAs per SM; each slice a multiple of 1024 positions
-    int nslice = ceil_div((long long)nsm * 4, (long long)B * ctiles);
-    const int max_slice = ceil_div(Mp, GG_THREADS * 4 * 2);
+    // slices so that the grid covers ~per_sm CTAs per SM; each slice a multiple of 1024 positions
+    int nslice = ceil_div((long long)nsm * per_sm, (long long)B * ctiles);
+    // a slice re-stages the CT rows (N floats each): keep it >= 2N positions so staging stays a
+    // fraction of the output traffic, and >= 2048 positions
+    const int min_len = 2 * N > 2048 ? 2 * N : 2048;
+    const int max_slice = Mp / min_len > 0 ? Mp / min_len : 1;
     if (nslice > max_slice) nslice = max_slice;
     if (nslice < 1) nslice = 1;
     int slice_len = ceil_div(Mp, nslice);
     slice_len = (slice_len + 1023) / 1024 * 1024;
     nslice = ceil_div(Mp, slice_len);
     const int use_bulk = ((N & 3) == 0) && ((reinterpret_cast<uintptr_t>(feat) & 15) == 0) && row_bytes <= 65536 * 4;
-    auto kern = gather_staged_kernel<CT>;
-    PS_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    kern<<<dim3(nslice, ctiles, B), GG_THREADS, smem, stream>>>(feat, idx, out, C, N, Mp, slice_len, use_bulk, vec_ok);
+    if (CT == 8) {
+      auto kern = gather_staged_kernel<8>;
+      PS_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      kern<<<dim3(nslice, ctiles, B), GG_THREADS, smem, stream>>>(feat, idx, out, C, N, Mp, slice_len, use_bulk, vec_ok);
+    } else {
+      auto kern = gather_staged_kernel<4>;
+      PS_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      kern<<<dim3(nslice, ctiles, B), GG_THREADS, smem, stream>>>(feat, idx, out, C, N, Mp, slice_len, use_bulk, vec_ok);
+    }
     PS_LAUNCH_CHECK();
   } else {
     constexpr int CTD = 4;
@@ -274,6 +436,39 @@ static int gather_bwd_impl(const float* gout, const int* idx, float* gfeat, int 
     return PS_OK;
   }
   const int vec_ok = ((Mp & 3) == 0) && ((reinterpret_cast<uintptr_t>(idx) & 15) == 0) && ((reinterpret_cast<uintptr_t>(gout) & 15) == 0);
+  // Dense grouping (each source referenced >= 4 times on average, several channels): inverse-index
+  // path.  Needs 16-byte aligned rows for the bulk copies and N small enough for the build kernel.
+  bool use_csr = (long long)Mp >= 4ll * N && C >= 4 && N <= 8 * CSR_THREADS && (size_t)(2 * N + 1) * 4 <= 160 * 1024 &&
+                 (Mp & 3) == 0 && (reinterpret_cast<uintptr_t>(gout) & 15) == 0;
+  if (const char* e = getenv("PS_SCATTER_CSR")) use_csr = use_csr && atoi(e) != 0;
+  if (use_csr) {
+    const int nchunks = ceil_div(Mp, CSR_CHUNK);
+    const size_t n_off = (size_t)B * (N + 1), n_bnd = (size_t)B * N * (nchunks + 1), n_inv = (size_t)B * Mp;
+    int* scratch = nullptr;
+    if (int rc = scratch_alloc((void**)&scratch, (n_off + n_bnd + n_inv) * sizeof(int), dev, stream)) return rc;
+    int *off = scratch, *bnd = scratch + n_off, *inv = bnd + n_bnd;
+    const size_t smem_b = (size_t)(2 * N + 1) * sizeof(int);
+    PS_CUDA(cudaFuncSetAttribute(csr_build_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_b));
+    csr_build_kernel<<<B, CSR_BUILD_THREADS, smem_b, stream>>>(idx, off, bnd, inv, N, Mp, nchunks);
+    PS_LAUNCH_CHECK();
+    const size_t smem = 128 + (size_t)2 * CSR_CHUNK * sizeof(float);
+    const int nsm = sm_count(dev);
+    int cpb = 8;  // channels per persistent CTA: enough CTAs for a few waves of 1 CTA per SM
+    while (cpb > 1 && (long long)B * ceil_div(C, cpb) < 4ll * nsm) cpb /= 2;
+    const dim3 grid(ceil_div(C, cpb), B);
+    const int npt = ceil_div(N, CSR_THREADS);
+#define PS_CSR(NPTV)                                                                               \
+  {                                                                                                \
+    auto kern = scatter_csr_kernel<NPTV>;                                                          \
+    PS_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));   \
+    kern<<<grid, CSR_THREADS, smem, stream>>>(gout, bnd, inv, gfeat, C, N, Mp, nchunks, cpb);      \
+  }
+    if (npt <= 1) PS_CSR(1) else if (npt <= 2) PS_CSR(2) else if (npt <= 4) PS_CSR(4) else PS_CSR(8)
+#undef PS_CSR
+    PS_LAUNCH_CHECK();
+    PS_CUDA(cudaFreeAsync(scratch, stream));
+    return PS_OK;
+  }
   int ct = 0;
   if (row_bytes * 8 <= GG_SMEM_MAX / 2) ct = 8;
   else if (row_bytes * 4 <= GG_SMEM_MAX) ct = 4;
