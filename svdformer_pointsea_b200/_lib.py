@@ -11,7 +11,8 @@ import os.path as osp
 import torch
 
 _HERE = osp.dirname(osp.abspath(__file__))
-LIB_PATH = osp.join(_HERE, "lib", "libpointsea_b200.so")
+# POINTSEA_B200_LIB points at an alternative build of the same C ABI (A/B measurements)
+LIB_PATH = os.environ.get("POINTSEA_B200_LIB", osp.join(_HERE, "lib", "libpointsea_b200.so"))
 
 _c_int = ctypes.c_int
 _c_void_p = ctypes.c_void_p

@@ -223,34 +223,38 @@ __global__ void __launch_bounds__(GG_THREADS) scatter_direct_kernel(
 
 // ---- backward through an inverse index (dense grouping: every source point appears many times) ---
 // grad_features[b,c,n] = sum over the positions p with idx[b,p] == n of grad_out[b,c,p].
-// The index tensor is shared by all C channels, so its inverse (CSR: for each source n the sorted
-// list of positions that reference it) is built ONCE per call; the reduction then becomes a
-// gather: no atomics in the channel loop, deterministic summation order (ascending p).
-//   csr_build_kernel   one CTA per cloud: histogram in shared memory, exclusive scan, fill, per-list
-//                      insertion sort, and per-source chunk boundaries (positions are processed in
-//                      chunks of CSR_CHUNK so a chunk of a grad_out row fits a shared-memory stage)
-//   scatter_csr_kernel persistent CTA per (cloud, CPB channels): a 2-stage ring of CSR_CHUNK-float
-//                      buffers filled by 1-D bulk async copies (TMA engine, mbarrier completion)
-//                      while the other stage is being gathered from; accumulators in registers.
-constexpr int CSR_CHUNK = 16384;   // positions per stage (64 KB)
-constexpr int CSR_THREADS = 512;
+// The index tensor is shared by all C channels, so its inverse is built ONCE per call and the
+// reduction becomes a gather: no atomics in the channel loop, deterministic summation order
+// (ascending p).  Positions are handled in chunks of CSR_CHUNK (one 64 KB shared-memory stage of a
+// grad_out row); per (cloud, chunk) the inverse is a counting sort of the chunk's positions by
+// source: `list` (u16 position-in-chunk, sorted by (source, position)) + `bnd` (N+1 offsets).
+//   csr_build_kernel   one CTA per (chunk, cloud): histogram / scan / fill / per-list sort, all in
+//                      shared memory, coalesced write-out
+//   scatter_csr_kernel persistent CTA per (cloud, CPB channels): per chunk the list + offsets are
+//                      staged in shared memory and each thread caches the entries of its NPT
+//                      sources in registers; the CPB grad_out row chunks then stream through a
+//                      2-stage ring filled by 1-D bulk async copies (TMA engine, mbarrier
+//                      completion) and are gathered from shared memory into register accumulators.
+constexpr int CSR_CHUNK = 16384;   // positions per stage (64 KB of fp32)
+constexpr int CSR_THREADS = 1024;  // measured on C3: 512 thr 0.195 ms, 1024 thr 0.172 ms
 constexpr int CSR_BUILD_THREADS = 1024;
 
-__global__ void __launch_bounds__(CSR_BUILD_THREADS) csr_build_kernel(const int* __restrict__ idx, int* __restrict__ off_all,
-                                                                     int* __restrict__ bnd_all, int* __restrict__ inv_all,
-                                                                     int N, int Mp, int nchunks) {
+__global__ void __launch_bounds__(CSR_BUILD_THREADS) csr_build_kernel(const int* __restrict__ idx, int* __restrict__ bnd_all,
+                                                                     unsigned short* __restrict__ list_all, int N, int Mp,
+                                                                     int nchunks) {
   extern __shared__ int sm_i[];
   int* cnt = sm_i;             // N + 1
   int* cur = sm_i + (N + 1);   // N
+  unsigned short* list = reinterpret_cast<unsigned short*>(cur + N);  // CSR_CHUNK
   __shared__ int warp_tot[CSR_BUILD_THREADS / 32];
-  const int b = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const int* ib = idx + (size_t)b * Mp;
-  int* off = off_all + (size_t)b * (N + 1);
-  int* bnd = bnd_all + (size_t)b * N * (nchunks + 1);
-  int* inv = inv_all + (size_t)b * Mp;
+  const int k = blockIdx.x, b = blockIdx.y, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int p0 = k * CSR_CHUNK, len = min(CSR_CHUNK, Mp - p0);
+  const int* ib = idx + (size_t)b * Mp + p0;
+  int* bnd = bnd_all + ((size_t)b * nchunks + k) * (N + 1);
+  unsigned short* out = list_all + (size_t)b * Mp + p0;
   for (int n = tid; n <= N; n += CSR_BUILD_THREADS) cnt[n] = 0;
   __syncthreads();
-  for (int p = tid; p < Mp; p += CSR_BUILD_THREADS) atomicAdd(&cnt[__ldg(ib + p)], 1);
+  for (int p = tid; p < len; p += CSR_BUILD_THREADS) atomicAdd(&cnt[__ldg(ib + p)], 1);
   __syncthreads();
   // exclusive scan of cnt[0..N): each thread owns a contiguous run
   const int per = (N + CSR_BUILD_THREADS - 1) / CSR_BUILD_THREADS;
@@ -270,41 +274,38 @@ __global__ void __launch_bounds__(CSR_BUILD_THREADS) csr_build_kernel(const int*
   }
   __syncthreads();
   int base = incl - run + (warp ? warp_tot[warp - 1] : 0);
-  for (int n = lo; n < hi; n++) { const int c = cnt[n]; cur[n] = base; off[n] = base; base += c; }
-  if (tid == 0) off[N] = Mp;
+  for (int n = lo; n < hi; n++) { const int c = cnt[n]; cur[n] = base; cnt[n] = base; base += c; }  // cnt now holds the offsets
   __syncthreads();
-  for (int p = tid; p < Mp; p += CSR_BUILD_THREADS) inv[atomicAdd(&cur[__ldg(ib + p)], 1)] = p;
-  __syncthreads();  // global writes of this CTA are visible to its own threads after the barrier
-  // sort each list ascending (deterministic summation order) and emit chunk boundaries
-  for (int n = tid; n < N; n += CSR_BUILD_THREADS) {
-    const int s = off[n], e = (n + 1 < N) ? off[n + 1] : Mp;
+  if (tid == 0) cnt[N] = len;
+  for (int p = tid; p < len; p += CSR_BUILD_THREADS) list[atomicAdd(&cur[__ldg(ib + p)], 1)] = (unsigned short)p;
+  __syncthreads();
+  for (int n = tid; n < N; n += CSR_BUILD_THREADS) {  // ascending positions inside each list
+    const int s = cnt[n], e = cnt[n + 1];
     for (int i = s + 1; i < e; i++) {
-      const int v = inv[i];
+      const unsigned short v = list[i];
       int j = i - 1;
-      while (j >= s && inv[j] > v) { inv[j + 1] = inv[j]; j--; }
-      inv[j + 1] = v;
-    }
-    int q = s;
-    for (int k = 0; k <= nchunks; k++) {
-      const int limit = k * CSR_CHUNK;
-      while (q < e && inv[q] < limit) q++;
-      bnd[(size_t)n * (nchunks + 1) + k] = (k == nchunks) ? e : q;
+      while (j >= s && list[j] > v) { list[j + 1] = list[j]; j--; }
+      list[j + 1] = v;
     }
   }
+  __syncthreads();
+  for (int n = tid; n <= N; n += CSR_BUILD_THREADS) bnd[n] = cnt[n];
+  for (int i = tid; i < len; i += CSR_BUILD_THREADS) out[i] = list[i];
 }
 
-template <int NPT>  // sources per thread = ceil(N / CSR_THREADS)
+// NPT sources per thread, PF list entries per source cached in registers, CPB channels per CTA
+template <int NPT, int PF, int CSR_CPB>
 __global__ void __launch_bounds__(CSR_THREADS, 1) scatter_csr_kernel(const float* __restrict__ gout, const int* __restrict__ bnd_all,
-                                                                     const int* __restrict__ inv_all, float* __restrict__ gfeat,
-                                                                     int C, int N, int Mp, int nchunks, int cpb) {
+                                                                     const unsigned short* __restrict__ list_all,
+                                                                     float* __restrict__ gfeat, int C, int N, int Mp, int nchunks) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
   u64* bars = reinterpret_cast<u64*>(smem_raw);          // full[2]
   float* stage0 = reinterpret_cast<float*>(smem_raw + 128);
   float* stage1 = stage0 + CSR_CHUNK;
-  const int b = blockIdx.y, c0 = blockIdx.x * cpb, tid = threadIdx.x;
-  const int nch = min(cpb, C - c0);
-  const int* bnd = bnd_all + (size_t)b * N * (nchunks + 1);
-  const int* inv = inv_all + (size_t)b * Mp;
+  unsigned short* list = reinterpret_cast<unsigned short*>(stage1 + CSR_CHUNK);  // CSR_CHUNK
+  int* bnd = reinterpret_cast<int*>(list + CSR_CHUNK);                           // N + 1
+  const int b = blockIdx.y, c0 = blockIdx.x * CSR_CPB, tid = threadIdx.x;
+  const int nch = min(CSR_CPB, C - c0);
   const int items = nch * nchunks;
   if (tid == 0) {
     mbar_init(smem_u32(&bars[0]), 1);
@@ -312,60 +313,72 @@ __global__ void __launch_bounds__(CSR_THREADS, 1) scatter_csr_kernel(const float
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   __syncthreads();
-  auto issue = [&](int item) {  // thread 0 only
-    const int c = c0 + item / nchunks, k = item % nchunks;
+  auto issue = [&](int item) {  // thread 0 only; items are chunk-major: item = k * nch + c
+    const int k = item / nch, c = c0 + item % nch;
     const int p0 = k * CSR_CHUNK, len = min(CSR_CHUNK, Mp - p0);
     const unsigned bar = smem_u32(&bars[item & 1]);
     mbar_arrive_expect_tx(bar, (unsigned)len * 4u);
     bulk_g2s(smem_u32((item & 1) ? stage1 : stage0), gout + ((size_t)b * C + c) * Mp + p0, (unsigned)len * 4u, bar);
   };
   if (tid == 0) { issue(0); if (items > 1) issue(1); }
-  float acc[NPT];
+  float acc[NPT][CSR_CPB];
 #pragma unroll
-  for (int i = 0; i < NPT; i++) acc[i] = 0.f;
-  for (int item = 0; item < items; item++) {
-    const int k = item % nchunks;
-    const float* st = (item & 1) ? stage1 : stage0;
-    while (!mbar_try_wait(smem_u32(&bars[item & 1]), (unsigned)(item >> 1) & 1u)) {}
-    const int p0 = k * CSR_CHUNK;
-    // list bounds of all NPT sources first, then up to 8 entries per source with all index loads
-    // in flight at once (the dependent chain inv[q] -> shared-memory read is what limits this loop)
-    int lo[NPT], hi[NPT];
+  for (int i = 0; i < NPT; i++)
+#pragma unroll
+    for (int c = 0; c < CSR_CPB; c++) acc[i][c] = 0.f;
+
+  int item = 0;
+  for (int k = 0; k < nchunks; k++) {
+    const int p0 = k * CSR_CHUNK, len = min(CSR_CHUNK, Mp - p0);
+    // stage this chunk's inverse (shared by all channels)
+    const int* gb = bnd_all + ((size_t)b * nchunks + k) * (N + 1);
+    const unsigned short* gl = list_all + (size_t)b * Mp + p0;
+    for (int n = tid; n <= N; n += CSR_THREADS) bnd[n] = __ldg(gb + n);
+    for (int i = tid; i < len / 2; i += CSR_THREADS)
+      reinterpret_cast<unsigned*>(list)[i] = __ldg(reinterpret_cast<const unsigned*>(gl) + i);
+    if ((len & 1) && tid == 0) list[len - 1] = __ldg(gl + len - 1);
+    __syncthreads();
+    int lo[NPT], cntv[NPT];
+    int pp[NPT][PF];
 #pragma unroll
     for (int i = 0; i < NPT; i++) {
       const int n = tid + i * CSR_THREADS;
-      lo[i] = hi[i] = 0;
-      if (n < N) {
-        lo[i] = __ldg(bnd + (size_t)n * (nchunks + 1) + k);
-        hi[i] = __ldg(bnd + (size_t)n * (nchunks + 1) + k + 1);
+      lo[i] = 0; cntv[i] = 0;
+      if (n < N) { lo[i] = bnd[n]; cntv[i] = bnd[n + 1] - lo[i]; }
+#pragma unroll
+      for (int u = 0; u < PF; u++) pp[i][u] = (u < cntv[i]) ? (int)list[lo[i] + u] : -1;
+    }
+#pragma unroll
+    for (int c = 0; c < CSR_CPB; c++) {
+      if (c < nch) {
+        const float* st = (item & 1) ? stage1 : stage0;
+        while (!mbar_try_wait(smem_u32(&bars[item & 1]), (unsigned)(item >> 1) & 1u)) {}
+#pragma unroll
+        for (int i = 0; i < NPT; i++) {
+          float a = acc[i][c];
+#pragma unroll
+          for (int u = 0; u < PF; u++)
+            if (pp[i][u] >= 0) a += st[pp[i][u]];
+          for (int q = PF; q < cntv[i]; q++) a += st[list[lo[i] + q]];  // long lists: remainder from shared memory
+          acc[i][c] = a;
+        }
+        __syncthreads();  // every thread is done with this stage before it is refilled
+        if (tid == 0 && item + 2 < items) issue(item + 2);
+        item++;
       }
     }
-    int pp[NPT][8];
+    // the barrier above also protects `list` / `bnd` before the next chunk overwrites them
+  }
 #pragma unroll
-    for (int i = 0; i < NPT; i++)
-#pragma unroll
-      for (int u = 0; u < 8; u++) pp[i][u] = (lo[i] + u < hi[i]) ? __ldg(inv + lo[i] + u) : -1;
-#pragma unroll
-    for (int i = 0; i < NPT; i++) {
-      float a = acc[i];
-#pragma unroll
-      for (int u = 0; u < 8; u++)
-        if (pp[i][u] >= 0) a += st[pp[i][u] - p0];
-      for (int q = lo[i] + 8; q < hi[i]; q++) a += st[__ldg(inv + q) - p0];  // long lists: remainder
-      acc[i] = a;
-    }
-    if (k == nchunks - 1) {  // channel finished: write its row, reset
-      const int c = c0 + item / nchunks;
-      float* dst = gfeat + ((size_t)b * C + c) * N;
+  for (int c = 0; c < CSR_CPB; c++) {
+    if (c < nch) {
+      float* dst = gfeat + ((size_t)b * C + c0 + c) * N;
 #pragma unroll
       for (int i = 0; i < NPT; i++) {
         const int n = tid + i * CSR_THREADS;
-        if (n < N) dst[n] = acc[i];
-        acc[i] = 0.f;
+        if (n < N) dst[n] = acc[i][c];
       }
     }
-    __syncthreads();  // every thread is done with this stage before it is refilled
-    if (tid == 0 && item + 2 < items) issue(item + 2);
   }
 }
 
@@ -438,32 +451,32 @@ static int gather_bwd_impl(const float* gout, const int* idx, float* gfeat, int 
   const int vec_ok = ((Mp & 3) == 0) && ((reinterpret_cast<uintptr_t>(idx) & 15) == 0) && ((reinterpret_cast<uintptr_t>(gout) & 15) == 0);
   // Dense grouping (each source referenced >= 4 times on average, several channels): inverse-index
   // path.  Needs 16-byte aligned rows for the bulk copies and N small enough for the build kernel.
-  bool use_csr = (long long)Mp >= 4ll * N && C >= 4 && N <= 8 * CSR_THREADS && (size_t)(2 * N + 1) * 4 <= 160 * 1024 &&
-                 (Mp & 3) == 0 && (reinterpret_cast<uintptr_t>(gout) & 15) == 0;
+  bool use_csr = (long long)Mp >= 4ll * N && C >= 4 && N <= 8 * CSR_THREADS && (Mp & 3) == 0 &&
+                 (reinterpret_cast<uintptr_t>(gout) & 15) == 0;
   if (const char* e = getenv("PS_SCATTER_CSR")) use_csr = use_csr && atoi(e) != 0;
   if (use_csr) {
     const int nchunks = ceil_div(Mp, CSR_CHUNK);
-    const size_t n_off = (size_t)B * (N + 1), n_bnd = (size_t)B * N * (nchunks + 1), n_inv = (size_t)B * Mp;
-    int* scratch = nullptr;
-    if (int rc = scratch_alloc((void**)&scratch, (n_off + n_bnd + n_inv) * sizeof(int), dev, stream)) return rc;
-    int *off = scratch, *bnd = scratch + n_off, *inv = bnd + n_bnd;
-    const size_t smem_b = (size_t)(2 * N + 1) * sizeof(int);
+    const size_t bnd_bytes = ((size_t)B * nchunks * (N + 1) * sizeof(int) + 15) / 16 * 16;
+    const size_t list_bytes = (size_t)B * Mp * sizeof(unsigned short);
+    unsigned char* scratch = nullptr;
+    if (int rc = scratch_alloc((void**)&scratch, bnd_bytes + list_bytes, dev, stream)) return rc;
+    int* bnd = reinterpret_cast<int*>(scratch);
+    unsigned short* list = reinterpret_cast<unsigned short*>(scratch + bnd_bytes);
+    const size_t smem_b = (size_t)(2 * N + 1) * sizeof(int) + (size_t)CSR_CHUNK * sizeof(unsigned short);
     PS_CUDA(cudaFuncSetAttribute(csr_build_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_b));
-    csr_build_kernel<<<B, CSR_BUILD_THREADS, smem_b, stream>>>(idx, off, bnd, inv, N, Mp, nchunks);
+    csr_build_kernel<<<dim3(nchunks, B), CSR_BUILD_THREADS, smem_b, stream>>>(idx, bnd, list, N, Mp, nchunks);
     PS_LAUNCH_CHECK();
-    const size_t smem = 128 + (size_t)2 * CSR_CHUNK * sizeof(float);
-    const int nsm = sm_count(dev);
-    int cpb = 8;  // channels per persistent CTA: enough CTAs for a few waves of 1 CTA per SM
-    while (cpb > 1 && (long long)B * ceil_div(C, cpb) < 4ll * nsm) cpb /= 2;
-    const dim3 grid(ceil_div(C, cpb), B);
+    const size_t smem = 128 + (size_t)2 * CSR_CHUNK * sizeof(float) + (size_t)CSR_CHUNK * sizeof(unsigned short) +
+                        (size_t)(N + 1) * sizeof(int);
     const int npt = ceil_div(N, CSR_THREADS);
-#define PS_CSR(NPTV)                                                                               \
+    // register budget at 1024 threads is 64: accumulators NPT*CPB + cached entries NPT*PF
+#define PS_CSR(NPTV, PFV, CPBV)                                                                    \
   {                                                                                                \
-    auto kern = scatter_csr_kernel<NPTV>;                                                          \
+    auto kern = scatter_csr_kernel<NPTV, PFV, CPBV>;                                               \
     PS_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));   \
-    kern<<<grid, CSR_THREADS, smem, stream>>>(gout, bnd, inv, gfeat, C, N, Mp, nchunks, cpb);      \
+    kern<<<dim3(ceil_div(C, CPBV), B), CSR_THREADS, smem, stream>>>(gout, bnd, list, gfeat, C, N, Mp, nchunks); \
   }
-    if (npt <= 1) PS_CSR(1) else if (npt <= 2) PS_CSR(2) else if (npt <= 4) PS_CSR(4) else PS_CSR(8)
+    if (npt <= 1) PS_CSR(1, 12, 8) else if (npt <= 2) PS_CSR(2, 12, 8) else if (npt <= 4) PS_CSR(4, 8, 4) else PS_CSR(8, 4, 2)
 #undef PS_CSR
     PS_LAUNCH_CHECK();
     PS_CUDA(cudaFreeAsync(scratch, stream));

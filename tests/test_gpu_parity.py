@@ -233,7 +233,9 @@ def test_gather_fwd_bwd(B, C, N, M):
 
 
 @pytest.mark.parametrize("B,C,N,S,K", [(2, 6, 256, 64, 16), (2, 128, 2048, 256, 16), (2, 3, 2048, 512, 16),
-                                       (1, 2, 50, 7, 3), (2, 9, 300, 33, 5), (1, 4, 70000, 64, 8)])
+                                       (1, 2, 50, 7, 3), (2, 9, 300, 33, 5), (1, 4, 70000, 64, 8),
+                                       (2, 8, 3000, 1024, 16), (1, 5, 7000, 2048, 16), (1, 4, 512, 1100, 32),
+                                       (2, 12, 1024, 40000, 1)])
 def test_group_fwd_bwd(B, C, N, S, K):
     g = torch.Generator().manual_seed(500 + N + S)
     feat = torch.randn(B, C, N, generator=g)
