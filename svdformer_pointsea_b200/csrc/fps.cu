@@ -179,6 +179,7 @@ __global__ void __launch_bounds__(T, 1) fps_kernel(const FpsArgs a) {
   for (int j = 1; j < a.npoint; j++) {
     // ---- per-thread update + best: d = |p - last|^2 two points at a time (FADD2/FMUL2/FFMA2) --
     const u64 nlx = pack2(-lx, -lx), nly = pack2(-ly, -ly), nlz = pack2(-lz, -lz);
+    float run[PP];  // running maximum after each pair (non-decreasing)
     float best = -1.0f;
 #pragma unroll
     for (int i = 0; i < PP; i++) {
@@ -186,12 +187,16 @@ __global__ void __launch_bounds__(T, 1) fps_kernel(const FpsArgs a) {
       t[2 * i] = fminf(lo2(d), t[2 * i]);
       t[2 * i + 1] = fminf(hi2(d), t[2 * i + 1]);  // padding / skipped points stay at -1
       best = max3(best, t[2 * i], t[2 * i + 1]);    // one FMNMX3 per two points
+      run[i] = best;
     }
-    // lowest i holding the maximum == lowest rank among this thread's ties
-    int bi = 0;
+    // lowest i holding the maximum == lowest rank among this thread's ties: the first pair whose
+    // running maximum already equals the final one contains it (one compare per PAIR, not per point)
+    int bp = 0;
+    float e0 = t[0];
 #pragma unroll
-    for (int i = P - 1; i >= 0; i--)
-      if (t[i] == best) bi = i;
+    for (int i = PP - 1; i >= 0; i--)
+      if (run[i] == best) { bp = i; e0 = t[2 * i]; }
+    const int bi = 2 * bp + (e0 == best ? 0 : 1);
     const int tb = __float_as_int(best);
     const unsigned rk = rank0 + (unsigned)bi;
     int tbw;

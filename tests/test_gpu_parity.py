@@ -405,3 +405,61 @@ def test_streams_and_reentrancy():
     [t_.join() for t_ in th]
     assert all(torch.equal(r[1], want) for r in results)
     assert len({r[0] for r in results}) == 1
+
+
+# ---------------------------------------------------------------- robustness
+def _misaligned(t):
+    """Same values in a contiguous tensor whose data pointer is only 4-byte aligned."""
+    flat = torch.empty(t.numel() + 1, dtype=t.dtype, device=t.device)
+    view = flat[1:].view(t.shape)
+    view.copy_(t)
+    assert view.is_contiguous() and view.data_ptr() % 16 != 0
+    return view
+
+
+def test_misaligned_and_odd_sized_inputs_take_the_scalar_paths():
+    g = torch.Generator().manual_seed(21)
+    a, b = make_cloud(g, 3, 1031), make_cloud(g, 3, 2050)  # B*N*3 floats not a multiple of 4 either
+    A, Bc = _misaligned(a.to(DEV)), _misaligned(b.to(DEV))
+    d1, d2, i1, i2 = ps.chamfer_forward(A, Bc)
+    od1, od2, oi1, oi2 = O.chamfer_fwd(a.numpy(), b.numpy())
+    assert np.array_equal(i1.cpu().numpy(), oi1) and np.array_equal(i2.cpu().numpy(), oi2)
+    assert np.array_equal(d1.cpu().numpy(), od1) and np.array_equal(d2.cpu().numpy(), od2)
+    assert np.array_equal(ps.furthest_point_sample(Bc, 77).cpu().numpy(), O.fps(b.numpy(), 77))
+    assert np.array_equal(ps.query_knn(9, Bc, A).cpu().numpy(), O.knn(b.numpy(), a.numpy(), 9))
+    feat = torch.randn(3, 5, 2050, generator=g)
+    idx = torch.randint(0, 2050, (3, 1031, 7), generator=g, dtype=torch.int32)
+    F, I = _misaligned(feat.to(DEV)), _misaligned(idx.to(DEV))
+    out = pu.group_raw(F, I)
+    assert np.array_equal(out.cpu().numpy(), O.group(feat.numpy(), idx.numpy()))
+    go = torch.randn(3, 5, 1031, 7, generator=g)
+    gr = pu.group_grad_raw(_misaligned(go.to(DEV)), I, 2050)
+    assert_close_rel(gr.cpu().numpy(), O.group_grad(go.numpy(), idx.numpy(), 2050), what="misaligned group grad")
+
+
+def test_cuda_graph_capture_and_replay():
+    """The whole path is stream-ordered (no host syncs, stream-ordered scratch), so a step can be
+    captured once and replayed: launch-bound inner loops belong in CUDA graphs."""
+    g = torch.Generator().manual_seed(31)
+    a, b = make_cloud(g, 4, 2048).to(DEV), make_cloud(g, 4, 4096).to(DEV)
+    feat = torch.randn(4, 16, 4096, generator=g).to(DEV)
+    for _ in range(2):  # warm-up outside capture (function attributes, pools)
+        ps.chamfer_forward(a, b); ps.furthest_point_sample(b, 256)
+        pu.group_raw(feat, ps.query_knn(8, b, a))
+    torch.cuda.synchronize()
+    graph = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(graph):
+        d1, d2, i1, i2 = ps.chamfer_forward(a, b)
+        fidx = ps.furthest_point_sample(b, 256)
+        knn = ps.query_knn(8, b, a)
+        grp = pu.group_raw(feat, knn)
+    a2, b2 = make_cloud(g, 4, 2048), make_cloud(g, 4, 4096)
+    a.copy_(a2.to(DEV)); b.copy_(b2.to(DEV))
+    graph.replay()
+    torch.cuda.synchronize()
+    od1, od2, oi1, oi2 = O.chamfer_fwd(a2.numpy(), b2.numpy())
+    assert np.array_equal(i1.cpu().numpy(), oi1) and np.array_equal(d2.cpu().numpy(), od2)
+    assert np.array_equal(fidx.cpu().numpy(), O.fps(b2.numpy(), 256))
+    want_knn = O.knn(b2.numpy(), a2.numpy(), 8)
+    assert np.array_equal(knn.cpu().numpy(), want_knn)
+    assert np.array_equal(grp.cpu().numpy(), O.group(feat.cpu().numpy(), want_knn))
