@@ -463,3 +463,27 @@ def test_cuda_graph_capture_and_replay():
     want_knn = O.knn(b2.numpy(), a2.numpy(), 8)
     assert np.array_equal(knn.cpu().numpy(), want_knn)
     assert np.array_equal(grp.cpu().numpy(), O.group(feat.cpu().numpy(), want_knn))
+
+
+def test_repeatability_as_a_race_guard():
+    """compute-sanitizer is closed on this GPU pool, so races in the cluster exchange (FPS), the
+    shared-memory key merges (Chamfer) and the mbarrier rings (group) are guarded by repetition:
+    25 back-to-back runs on two streams must be bit-identical (all three are deterministic by design)."""
+    g = torch.Generator().manual_seed(41)
+    x = make_cloud(g, 6, 16384, dup=2000, near_origin=6).to(DEV)
+    y = make_cloud(g, 6, 3000, dup=500).to(DEV)
+    feat = torch.randn(6, 16, 3000, generator=g).to(DEV)
+    idx = torch.randint(0, 3000, (6, 2048, 16), generator=g, dtype=torch.int32).to(DEV)
+    go = torch.randn(6, 16, 2048, 16, generator=g).to(DEV)
+    ref = None
+    streams = [torch.cuda.Stream(), torch.cuda.Stream()]
+    for it in range(25):
+        with torch.cuda.stream(streams[it & 1]):
+            out = (ps.furthest_point_sample(x, 512), *ps.chamfer_forward(x, y), pu.group_raw(feat, idx),
+                   pu.group_grad_raw(go, idx, 3000))
+        streams[it & 1].synchronize()
+        if ref is None:
+            ref = [o.clone() for o in out]
+        else:
+            for k, (o, r) in enumerate(zip(out, ref)):
+                assert torch.equal(o, r), f"output {k} changed on repetition {it}"
