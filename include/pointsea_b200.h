@@ -74,6 +74,12 @@ int ps_chamfer_sums(const float* dist1, const float* dist2, double* out6, long l
  *   min-distance array lives in registers).  Tie-break and origin-skip rule are the reference's.
  */
 int ps_fps(const float* xyz, int* idx, int B, int N, int npoint, int dev, void* stream);
+/* Same sampling, additionally writing the sampled coordinates new_xyz (B,npoint,3) = xyz[b, idx[b,j]]
+ * from inside the FPS kernel (the winner's coordinates are already in registers): the fused form of
+ * the call site fps_subsample = FPS + gather + two transposes (models/model_utils.py:489-499).
+ * new_xyz may be NULL (then identical to ps_fps). */
+int ps_fps_sample(const float* xyz, int* idx, float* new_xyz, int B, int N, int npoint, int dev,
+                  void* stream);
 
 /* ---- gather / group ---------------------------------------------------------------------
  * Replaces gather_points_kernel_wrapper (sampling_gpu.cu:22-30) / _grad_ (:49-57):

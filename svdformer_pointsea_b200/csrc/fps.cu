@@ -57,6 +57,7 @@ struct __align__(16) FpsEntry {  // two 16-byte vectors, each written by ONE st.
 struct FpsArgs {
   const float* xyz;
   int* idx;
+  float* new_xyz;  // optional (B, npoint, 3): coordinates of the sampled points (fused fps_subsample)
   int N, npoint;
   int L;     // log2(bs) of the reference launch
   int nper;  // ceil(N / bs)
@@ -172,7 +173,8 @@ __global__ void __launch_bounds__(T, 1) fps_kernel(const FpsArgs a) {
   }
   const float p0x = __ldg(cloud + 0), p0y = __ldg(cloud + 1), p0z = __ldg(cloud + 2);
   float lx = p0x, ly = p0y, lz = p0z;
-  if (g == 0 && a.npoint > 0) out[0] = 0;
+  float* oxyz = a.new_xyz ? a.new_xyz + (size_t)b * a.npoint * 3 : nullptr;
+  if (g == 0 && a.npoint > 0) { out[0] = 0; if (oxyz) { oxyz[0] = p0x; oxyz[1] = p0y; oxyz[2] = p0z; } }
   if (CLUSTER) { cluster_arrive_release(); cluster_wait_acquire(); }  // peers resident, mbarriers armed
   else __syncthreads();
 
@@ -286,7 +288,7 @@ __global__ void __launch_bounds__(T, 1) fps_kernel(const FpsArgs a) {
     if (tbf < 0) {  // no eligible point anywhere: the reference's tree returns thread 0's besti = 0
       kf = 0; lx = p0x; ly = p0y; lz = p0z;
     }
-    if (g == 0) out[j] = kf;
+    if (g == 0) { out[j] = kf; if (oxyz) { oxyz[j * 3 + 0] = lx; oxyz[j * 3 + 1] = ly; oxyz[j * 3 + 2] = lz; } }
   }
   if (CLUSTER) { cluster_arrive_release(); cluster_wait_acquire(); }  // no CTA exits while peers may still write to it
 }
@@ -312,7 +314,8 @@ __global__ void __launch_bounds__(FPS_GT, 1) fps_generic_kernel(const FpsArgs a,
     temp[k] = ((double)mag <= 1e-3) ? -1.0f : 1e10f;
   }
   float lx = cloud[0], ly = cloud[1], lz = cloud[2];
-  if (tid == 0 && a.npoint > 0) out[0] = 0;
+  float* oxyz = a.new_xyz ? a.new_xyz + (size_t)b * a.npoint * 3 : nullptr;
+  if (tid == 0 && a.npoint > 0) { out[0] = 0; if (oxyz) { oxyz[0] = lx; oxyz[1] = ly; oxyz[2] = lz; } }
   __syncthreads();
   for (int j = 1; j < a.npoint; j++) {
     // stride FPS_GT is a multiple of bs, so k mod bs is constant per thread and the first maximum
@@ -347,7 +350,7 @@ __global__ void __launch_bounds__(FPS_GT, 1) fps_generic_kernel(const FpsArgs a,
     lz = __shfl_sync(0xffffffffu, en.z, fl);
     int kf = __shfl_sync(0xffffffffu, en.k, fl);
     if (tbf < 0) { kf = 0; lx = cloud[0]; ly = cloud[1]; lz = cloud[2]; }
-    if (tid == 0) out[j] = kf;
+    if (tid == 0) { out[j] = kf; if (oxyz) { oxyz[j * 3 + 0] = lx; oxyz[j * 3 + 1] = ly; oxyz[j * 3 + 2] = lz; } }
   }
 }
 
@@ -438,6 +441,10 @@ static bool plan_fps(int B, int N, int L, int nper, int nsm, FpsPlan& best) {
 using namespace ps;
 
 extern "C" int ps_fps(const float* xyz, int* idx, int B, int N, int npoint, int dev, void* stream_) {
+  return ps_fps_sample(xyz, idx, nullptr, B, N, npoint, dev, stream_);
+}
+
+extern "C" int ps_fps_sample(const float* xyz, int* idx, float* new_xyz, int B, int N, int npoint, int dev, void* stream_) {
   PS_REQUIRE(B >= 0 && N > 0 && npoint >= 0, "ps_fps: bad sizes B=%d N=%d npoint=%d", B, N, npoint);
   if (B == 0 || npoint == 0) return PS_OK;
   PS_REQUIRE(xyz && idx, "ps_fps: null pointer");
@@ -447,7 +454,7 @@ extern "C" int ps_fps(const float* xyz, int* idx, int B, int N, int npoint, int 
   const int nsm = sm_count(dev);
 
   FpsArgs a;
-  a.xyz = xyz; a.idx = idx; a.N = N; a.npoint = npoint;
+  a.xyz = xyz; a.idx = idx; a.new_xyz = new_xyz; a.N = N; a.npoint = npoint;
   a.L = ref_block_log2(N);
   a.nper = ceil_div(N, 1 << a.L);
 

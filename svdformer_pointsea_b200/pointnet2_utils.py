@@ -283,7 +283,39 @@ def query_knn(nsample, xyz, new_xyz, include_self=True):
     return knn_raw(xyz.contiguous(), new_xyz.contiguous(), nsample, pad)
 
 
+def fps_sample_raw(xyz, npoint):
+    """(idx (B,npoint) int32, new_xyz (B,npoint,3)) from ONE kernel: the FPS kernel writes the
+    coordinates of every selected point as it goes (ps_fps_sample)."""
+    L.require(xyz, "xyz", torch.float32, 3)
+    if xyz.size(2) != 3:
+        raise L.PointSeaError(f"xyz must be (B,N,3), got {tuple(xyz.shape)}")
+    npoint = int(npoint)
+    dev = L.same_device(xyz)
+    B, N, _ = xyz.shape
+    idx = torch.empty(B, npoint, device=xyz.device, dtype=torch.int32)
+    new_xyz = torch.empty(B, npoint, 3, device=xyz.device, dtype=torch.float32)
+    L.check(L.load().ps_fps_sample(L.ptr(xyz), L.ptr(idx), L.ptr(new_xyz), B, N, npoint, dev, L.stream_ptr(dev)),
+            "ps_fps_sample")
+    return idx, new_xyz
+
+
+class _FpsSubsample(Function):
+    """Fused fps_subsample with the reference's gradient (gather backward = scatter-add by idx)."""
+
+    @staticmethod
+    def forward(ctx, pcd, n_points):
+        idx, new_pcd = fps_sample_raw(pcd.contiguous(), n_points)
+        ctx.save_for_backward(idx)
+        ctx.N = pcd.size(1)
+        return new_pcd
+
+    @staticmethod
+    def backward(ctx, grad_out):
+        (idx,) = ctx.saved_tensors
+        g = gather_grad_raw(grad_out.permute(0, 2, 1).contiguous(), idx, ctx.N)  # (B,3,N)
+        return g.permute(0, 2, 1).contiguous(), None
+
+
 def fps_subsample(pcd, n_points=2048):
-    """models/model_utils.py:489-499 (FPS + gather + transposes)."""
-    new_pcd = gather_operation(pcd.permute(0, 2, 1).contiguous(), furthest_point_sample(pcd, n_points))
-    return new_pcd.permute(0, 2, 1).contiguous()
+    """models/model_utils.py:489-499 (FPS + gather + two transposes) as one kernel launch."""
+    return _FpsSubsample.apply(pcd, n_points)

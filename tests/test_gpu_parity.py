@@ -487,3 +487,22 @@ def test_repeatability_as_a_race_guard():
         else:
             for k, (o, r) in enumerate(zip(out, ref)):
                 assert torch.equal(o, r), f"output {k} changed on repetition {it}"
+
+
+def test_fused_fps_subsample_matches_unfused_call_site():
+    """fps_subsample (models/model_utils.py:489-499): one kernel vs FPS + gather + transposes,
+    forward values and the gather gradient."""
+    g = torch.Generator().manual_seed(51)
+    x = make_cloud(g, 3, 5000, dup=700, near_origin=4)
+    xc = x.to(DEV).requires_grad_(True)
+    sub = ps.fps_subsample(xc, 333)
+    want_idx = O.fps(x.numpy(), 333)
+    want = np.take_along_axis(x.numpy(), want_idx[..., None].astype(np.int64), axis=1)
+    assert np.array_equal(sub.detach().cpu().numpy(), want)
+    go = torch.randn(3, 333, 3, generator=g)
+    sub.backward(go.to(DEV))
+    want_g = O.gather_grad(go.numpy().transpose(0, 2, 1).copy(), want_idx, 5000).transpose(0, 2, 1)
+    assert_close_rel(xc.grad.cpu().numpy(), want_g, what="fps_subsample grad")
+    # the unfused composition gives the same tensor
+    unf = ps.gather_operation(xc.detach().permute(0, 2, 1).contiguous(), ps.furthest_point_sample(xc.detach(), 333))
+    assert torch.equal(unf.permute(0, 2, 1).contiguous(), sub.detach())
