@@ -372,6 +372,13 @@ extern "C" int ps_knn(const float* xyz, const float* new_xyz, int* idx, int B, i
   const dim3 grid(ceil_div(S, qpc), B);
   const int KK = k + skip;
   const int var = knn_variant();
+  {
+    const char* e = getenv("PS_KNN_SELECT");  // PS_KNN_SELECT=0 forces the streaming kernel (A/B, tests)
+    if (!(e && atoi(e) == 0)) {
+      const int rc = knn_select_launch(xyz, new_xyz, idx, B, N, S, k, skip, var, nsm, stream);
+      if (rc <= 0) return rc;
+    }
+  }
   if (KK <= 32) launch_knn<1>(var, grid, stream, xyz, new_xyz, idx, N, S, k, skip, qpc);
   else if (KK <= 64) launch_knn<2>(var, grid, stream, xyz, new_xyz, idx, N, S, k, skip, qpc);
   else launch_knn<4>(var, grid, stream, xyz, new_xyz, idx, N, S, k, skip, qpc);

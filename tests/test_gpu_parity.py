@@ -506,3 +506,23 @@ def test_fused_fps_subsample_matches_unfused_call_site():
     # the unfused composition gives the same tensor
     unf = ps.gather_operation(xc.detach().permute(0, 2, 1).contiguous(), ps.furthest_point_sample(xc.detach(), 333))
     assert torch.equal(unf.permute(0, 2, 1).contiguous(), sub.detach())
+
+
+@pytest.mark.parametrize("select", ["1", "0"])
+def test_knn_heavy_duplication_and_both_kernels(select, monkeypatch):
+    """The threshold-selection kernel (N <= 2048, k+skip <= 16) must fall back correctly when far
+    more than 32 candidates tie at the threshold; PS_KNN_SELECT=0 exercises the streaming kernel."""
+    monkeypatch.setenv("PS_KNN_SELECT", select)
+    g = torch.Generator().manual_seed(61)
+    xyz = make_cloud(g, 2, 1500)
+    xyz[:, 100:400] = xyz[:, 7:8]          # 300 copies of one point
+    xyz[:, 900:960] = xyz[:, 800:801]      # 60 copies of another
+    q = torch.cat([xyz[:, 5:9], xyz[:, 798:803], make_cloud(g, 2, 40)], 1).contiguous()
+    for k, inc in ((16, True), (15, False), (3, True)):
+        got = ps.query_knn(k, xyz.to(DEV), q.to(DEV), include_self=inc)
+        want = O.knn(xyz.numpy(), q.numpy(), k, 0 if inc else 1)
+        assert np.array_equal(got.cpu().numpy(), want), (k, inc)
+    for N in (16, 33, 500, 2048):          # short clouds: padding steps, N < 32 lanes
+        x = make_cloud(g, 2, N, dup=N // 5)
+        got = ps.query_knn(min(16, N), x.to(DEV), x.to(DEV))
+        assert np.array_equal(got.cpu().numpy(), O.knn(x.numpy(), x.numpy(), min(16, N))), N
