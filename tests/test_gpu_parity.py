@@ -526,3 +526,22 @@ def test_knn_heavy_duplication_and_both_kernels(select, monkeypatch):
         x = make_cloud(g, 2, N, dup=N // 5)
         got = ps.query_knn(min(16, N), x.to(DEV), x.to(DEV))
         assert np.array_equal(got.cpu().numpy(), O.knn(x.numpy(), x.numpy(), min(16, N))), N
+
+
+def test_empty_batches_and_zero_sized_requests_are_no_ops():
+    """B = 0, npoint = 0, M = 0: the reference's kernels simply do not iterate; ours return
+    correctly shaped empty tensors without touching the (null) pointers."""
+    e3 = torch.empty(0, 16, 3, device=DEV)
+    d1, d2, i1, i2 = ps.chamfer_forward(e3, torch.empty(0, 8, 3, device=DEV))
+    assert tuple(d1.shape) == (0, 16) and tuple(i2.shape) == (0, 8) and i1.dtype == torch.int32
+    assert tuple(ps.furthest_point_sample(e3, 4).shape) == (0, 4)
+    x = make_cloud(torch.Generator().manual_seed(1), 2, 64).to(DEV)
+    assert tuple(ps.furthest_point_sample(x, 0).shape) == (2, 0)
+    feat = torch.randn(2, 5, 64, device=DEV)
+    assert tuple(ps.gather_operation(feat, torch.empty(2, 0, device=DEV, dtype=torch.int32)).shape) == (2, 5, 0)
+    assert tuple(ps.grouping_operation(feat, torch.empty(2, 0, 4, device=DEV, dtype=torch.int32)).shape) == (2, 5, 0, 4)
+    g = pu.gather_grad_raw(torch.empty(2, 5, 0, device=DEV), torch.empty(2, 0, device=DEV, dtype=torch.int32), 64)
+    assert tuple(g.shape) == (2, 5, 64) and torch.count_nonzero(g) == 0
+    assert tuple(ps.query_knn(4, x, torch.empty(2, 0, 3, device=DEV)).shape) == (2, 0, 4)
+    assert tuple(ps.ball_query(0.1, 4, x, torch.empty(2, 0, 3, device=DEV)).shape) == (2, 0, 4)
+    torch.cuda.synchronize()
