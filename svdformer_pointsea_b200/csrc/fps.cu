@@ -410,11 +410,47 @@ static int dispatch_pp(int PP, const FpsArgs& a, int B, int C, cudaStream_t s) {
 
 struct FpsPlan { int C, T, PP; };
 
+// How many clusters of `c` CTAs (one CTA per SM, as every fps_kernel configuration runs) the device
+// keeps resident at once: clusters must sit inside one GPC, so this is less than SMs / c for the
+// large sizes.  Probed once per (device, size) with cudaOccupancyMaxActiveClusters on a stand-in
+// kernel of the same footprint.
+__global__ void __launch_bounds__(256, 1) fps_capacity_probe_kernel(int* p) {
+  extern __shared__ int probe_smem[];
+  if (p) p[0] = probe_smem[0];
+}
+static int cluster_capacity(int dev, int c, int nsm) {
+  static int cache[64][5] = {{0}};
+  int slot = 0;
+  while ((1 << slot) < c) slot++;
+  if (dev >= 0 && dev < 64 && cache[dev][slot]) return cache[dev][slot];
+  int cap = nsm / c;
+  if (c > 1) {
+    const int smem = 120 * 1024;  // forces one CTA per SM
+    cudaFuncSetAttribute(fps_capacity_probe_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    if (c > 8) cudaFuncSetAttribute(fps_capacity_probe_kernel, cudaFuncAttributeNonPortableClusterSizeAllowed, 1);
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(c * nsm);
+    cfg.blockDim = dim3(256);
+    cfg.dynamicSmemBytes = smem;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeClusterDimension;
+    at[0].val.clusterDim.x = c; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+    cfg.attrs = at;
+    cfg.numAttrs = 1;
+    int n = 0;
+    if (cudaOccupancyMaxActiveClusters(&n, fps_capacity_probe_kernel, &cfg) == cudaSuccess && n > 0) cap = n;
+    else cudaGetLastError();
+  }
+  if (cap < 1) cap = 1;
+  if (dev >= 0 && dev < 64) cache[dev][slot] = cap;
+  return cap;
+}
+
 // Per-iteration cost model in SM cycles (fitted to B200 measurements, profiles/fps_r1_notes.md):
 // every warp issues ~6.5 instructions per resident point plus ~90 for the exchange, T/128 warps
 // share a scheduler; the exchange itself costs ~150 cycles inside one CTA and ~600 across a
 // cluster (st.async + mbarrier round trip through distributed shared memory).
-static bool plan_fps(int B, int N, int L, int nper, int nsm, FpsPlan& best) {
+static bool plan_fps(int B, int N, int L, int nper, int nsm, int dev, FpsPlan& best) {
   const long long R = (long long)nper << L;
   int force_c = 0, force_t = 0;
   if (const char* e = getenv("PS_FPS_CLUSTER")) force_c = atoi(e);
@@ -428,7 +464,7 @@ static bool plan_fps(int B, int N, int L, int nper, int nsm, FpsPlan& best) {
       int pp = 1;
       while ((long long)2 * pp * c * t < R) pp *= 2;
       if (pp > 16) continue;
-      const int waves = ceil_div((long long)B * c, nsm);
+      const int waves = ceil_div(B, cluster_capacity(dev, c, nsm));  // clusters that do not fit wait for a free GPC slot
       const double cost = waves * ((t / 128) * (6.5 * 2 * pp + 90.0) + (c == 1 ? 150.0 : 600.0));
       if (cost < best_cost - 1e-9) { best_cost = cost; best = {c, t, pp}; found = true; }
     }
@@ -459,7 +495,7 @@ extern "C" int ps_fps_sample(const float* xyz, int* idx, float* new_xyz, int B, 
   a.nper = ceil_div(N, 1 << a.L);
 
   FpsPlan pl;
-  if (!plan_fps(B, N, a.L, a.nper, nsm, pl)) {
+  if (!plan_fps(B, N, a.L, a.nper, nsm, dev, pl)) {
     // beyond the register-resident kernels (N > 131072): one CTA per cloud with global scratch
     float* temp = nullptr;
     if (int rc = scratch_alloc((void**)&temp, (size_t)B * N * sizeof(float), dev, stream)) return rc;
