@@ -235,6 +235,218 @@ __global__ void __launch_bounds__(CS_THREADS, 2) chamfer_sym_kernel(const SymPar
   }
 }
 
+// ------------------------------------------------------------------------------------------------
+// A-packed variant.  Same algorithm, other register layout: the two halves of every packed
+// operand are two DIFFERENT A points of the thread (a_2p, a_2p+1) and the streamed B point is
+// duplicated in shared memory ((x_j, x_j) pairs, read as broadcast LDS.128).  An A point then
+// costs 3 registers instead of 6, so a thread holds Q = 16 points at the same 128 registers and
+// every per-B-point cost of the warp (column REDUX + ballot + owner selects, B loads, loop
+// overhead) is amortised over twice as many pair evaluations; FLO/BREV (XU pipe, 1/8 rate) leave
+// the loop because the owner lane keeps the ballot mask and takes ffs once per 32 B points.
+constexpr int CP_TILE = 1024;  // B points per shared-memory tile (2 floats per coordinate)
+
+// if (a < b) shared[addr] = v;  one FSETP + one predicated STS, the address stays in its register
+__device__ __forceinline__ void st_shared_if_less(float a, float b, unsigned addr, int v) {
+  // no "memory" clobber on purpose: it would pin the B-tile loads of the next step behind these stores.
+  // The slots are only read back through ld_shared_volatile (volatile asm statements keep their order).
+  asm volatile("{\n\t.reg .pred p;\n\tsetp.lt.f32 p, %0, %1;\n\t@p st.shared.u32 [%2], %3;\n\t}" ::"f"(a), "f"(b), "r"(addr), "r"(v));
+}
+__device__ __forceinline__ void st_shared_volatile(unsigned addr, int v) { asm volatile("st.shared.u32 [%0], %1;" ::"r"(addr), "r"(v)); }
+__device__ __forceinline__ int ld_shared_volatile(unsigned addr) { int v; asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(addr)); return v; }
+
+template <int QP>
+__global__ void __launch_bounds__(CS_THREADS, QP >= 8 ? 2 : (QP == 4 ? 3 : 4)) chamfer_symp_kernel(const SymParams p) {
+  constexpr int Q = 2 * QP;
+  constexpr int TA = CS_THREADS * Q;
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  float* sxd = reinterpret_cast<float*>(smem_raw);
+  float* syd = sxd + 2 * CP_TILE;
+  float* szd = syd + 2 * CP_TILE;
+  u64* colkey = reinterpret_cast<u64*>(szd + 2 * CP_TILE);
+  float* ax = reinterpret_cast<float*>(colkey + CP_TILE);
+  float* ay = ax + TA;
+  float* az = ay + TA;
+  // [q][thread]: step of the last strict improvement of best[q]
+  const unsigned cstep_addr = smem_u32(reinterpret_cast<int*>(az + TA) + threadIdx.x);
+
+  int unit = blockIdx.x;
+  const int split = unit % p.nsplit;
+  unit /= p.nsplit;
+  const int at = unit % p.natiles;
+  const int b = unit / p.natiles;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int na = p.na, nb = p.nb;
+  const float INF = __int_as_float(0x7f800000);
+
+  // ---- A points: negated and packed two per register pair; plain copy in shared memory --------
+  u64 nax[QP], nay[QP], naz[QP];
+  float best[Q];
+  const float* abase = p.a + (size_t)b * na * 3;
+#pragma unroll
+  for (int pp = 0; pp < QP; pp++) {
+    float x[2], y[2], z[2];
+#pragma unroll
+    for (int h = 0; h < 2; h++) {
+      const int i = at * TA + tid * Q + 2 * pp + h;
+      const bool valid = i < na;
+      x[h] = valid ? __ldg(abase + (size_t)i * 3 + 0) : INF;  // see chamfer_sym_kernel: +inf slots never win
+      y[h] = valid ? __ldg(abase + (size_t)i * 3 + 1) : 0.f;
+      z[h] = valid ? __ldg(abase + (size_t)i * 3 + 2) : 0.f;
+      ax[tid * Q + 2 * pp + h] = x[h]; ay[tid * Q + 2 * pp + h] = y[h]; az[tid * Q + 2 * pp + h] = z[h];
+      best[2 * pp + h] = INF;
+      st_shared_volatile(cstep_addr + (2 * pp + h) * CS_THREADS * 4, 0);
+    }
+    nax[pp] = pack2(-x[0], -x[1]); nay[pp] = pack2(-y[0], -y[1]); naz[pp] = pack2(-z[0], -z[1]);
+  }
+
+  const int t0 = split * p.split_len;
+  const int t1 = min(nb, t0 + p.split_len);
+  const float* bcloud = p.b + (size_t)b * nb * 3;
+
+  for (int ts = t0; ts < t1; ts += CP_TILE) {
+    const int cnt = min(CP_TILE, t1 - ts);
+    const int cnt_pad = (cnt + CS_STEP - 1) / CS_STEP * CS_STEP;
+    const float* tb = bcloud + (size_t)ts * 3;
+    const bool vec = (reinterpret_cast<uintptr_t>(tb) & 15) == 0;
+    __syncthreads();  // previous tile (and its column pass) fully consumed
+    for (int g = tid; g < cnt_pad / 4; g += CS_THREADS) {
+      float xs[4], ys[4], zs[4];
+      if (vec && g * 4 + 4 <= cnt) {
+        const float4 a = __ldg(reinterpret_cast<const float4*>(tb + g * 12));
+        const float4 bb = __ldg(reinterpret_cast<const float4*>(tb + g * 12 + 4));
+        const float4 c = __ldg(reinterpret_cast<const float4*>(tb + g * 12 + 8));
+        xs[0] = a.x; xs[1] = a.w; xs[2] = bb.z; xs[3] = c.y;
+        ys[0] = a.y; ys[1] = bb.x; ys[2] = bb.w; ys[3] = c.z;
+        zs[0] = a.z; zs[1] = bb.y; zs[2] = c.x; zs[3] = c.w;
+      } else {
+#pragma unroll
+        for (int e = 0; e < 4; e++) {
+          const int pi = g * 4 + e;
+          const bool in = pi < cnt;
+          xs[e] = in ? __ldg(tb + pi * 3 + 0) : INF;
+          ys[e] = in ? __ldg(tb + pi * 3 + 1) : 0.f;
+          zs[e] = in ? __ldg(tb + pi * 3 + 2) : 0.f;
+        }
+      }
+      *reinterpret_cast<float4*>(&sxd[g * 8]) = make_float4(xs[0], xs[0], xs[1], xs[1]);
+      *reinterpret_cast<float4*>(&sxd[g * 8 + 4]) = make_float4(xs[2], xs[2], xs[3], xs[3]);
+      *reinterpret_cast<float4*>(&syd[g * 8]) = make_float4(ys[0], ys[0], ys[1], ys[1]);
+      *reinterpret_cast<float4*>(&syd[g * 8 + 4]) = make_float4(ys[2], ys[2], ys[3], ys[3]);
+      *reinterpret_cast<float4*>(&szd[g * 8]) = make_float4(zs[0], zs[0], zs[1], zs[1]);
+      *reinterpret_cast<float4*>(&szd[g * 8 + 4]) = make_float4(zs[2], zs[2], zs[3], zs[3]);
+    }
+    for (int j = tid; j < cnt_pad; j += CS_THREADS) colkey[j] = ~0ull;
+    __syncthreads();
+
+    int step = (ts - t0) / CS_STEP;
+    for (int j32 = 0; j32 < cnt_pad; j32 += 32) {
+      unsigned key_m = 0xffffffffu, key_b = 1u;
+      const int jend = min(cnt_pad, j32 + 32);
+#pragma unroll 2
+      for (int j = j32; j < jend; j += CS_STEP, step++) {
+        const ulonglong2 X01 = *reinterpret_cast<const ulonglong2*>(&sxd[2 * j]);
+        const ulonglong2 X23 = *reinterpret_cast<const ulonglong2*>(&sxd[2 * j + 4]);
+        const ulonglong2 Y01 = *reinterpret_cast<const ulonglong2*>(&syd[2 * j]);
+        const ulonglong2 Y23 = *reinterpret_cast<const ulonglong2*>(&syd[2 * j + 4]);
+        const ulonglong2 Z01 = *reinterpret_cast<const ulonglong2*>(&szd[2 * j]);
+        const ulonglong2 Z23 = *reinterpret_cast<const ulonglong2*>(&szd[2 * j + 4]);
+        float c0 = INF, c1 = INF, c2 = INF, c3 = INF;  // this lane's minimum over its Q points, per B point
+#pragma unroll
+        for (int pp = 0; pp < QP; pp++) {
+          const u64 d0 = dist2x2(X01.x, Y01.x, Z01.x, nax[pp], nay[pp], naz[pp]);  // {d(a_2p, b_j), d(a_2p+1, b_j)}
+          const u64 d1 = dist2x2(X01.y, Y01.y, Z01.y, nax[pp], nay[pp], naz[pp]);
+          const u64 d2 = dist2x2(X23.x, Y23.x, Z23.x, nax[pp], nay[pp], naz[pp]);
+          const u64 d3 = dist2x2(X23.y, Y23.y, Z23.y, nax[pp], nay[pp], naz[pp]);
+          float nl = min3(best[2 * pp], lo2(d0), lo2(d1));
+          nl = min3(nl, lo2(d2), lo2(d3));
+          st_shared_if_less(nl, best[2 * pp], cstep_addr + (2 * pp) * CS_THREADS * 4, step);
+          best[2 * pp] = nl;
+          float nh = min3(best[2 * pp + 1], hi2(d0), hi2(d1));
+          nh = min3(nh, hi2(d2), hi2(d3));
+          st_shared_if_less(nh, best[2 * pp + 1], cstep_addr + (2 * pp + 1) * CS_THREADS * 4, step);
+          best[2 * pp + 1] = nh;
+          c0 = min3(c0, lo2(d0), hi2(d0));
+          c1 = min3(c1, lo2(d1), hi2(d1));
+          c2 = min3(c2, lo2(d2), hi2(d2));
+          c3 = min3(c3, lo2(d3), hi2(d3));
+        }
+        // warp minimum per B point + the lanes holding it; the owner lane of each B point keeps both
+        const unsigned b0 = __float_as_uint(c0), b1 = __float_as_uint(c1), b2 = __float_as_uint(c2), b3 = __float_as_uint(c3);
+        const unsigned m0 = __reduce_min_sync(0xffffffffu, b0);
+        const unsigned m1 = __reduce_min_sync(0xffffffffu, b1);
+        const unsigned m2 = __reduce_min_sync(0xffffffffu, b2);
+        const unsigned m3 = __reduce_min_sync(0xffffffffu, b3);
+        const unsigned l0 = __ballot_sync(0xffffffffu, b0 == m0);
+        const unsigned l1 = __ballot_sync(0xffffffffu, b1 == m1);
+        const unsigned l2 = __ballot_sync(0xffffffffu, b2 == m2);
+        const unsigned l3 = __ballot_sync(0xffffffffu, b3 == m3);
+        const int o = lane - (j - j32);  // 0..3 for the four owner lanes of this step
+        if (o == 0) { key_m = m0; key_b = l0; }
+        if (o == 1) { key_m = m1; key_b = l1; }
+        if (o == 2) { key_m = m2; key_b = l2; }
+        if (o == 3) { key_m = m3; key_b = l3; }
+      }
+      if (j32 + lane < cnt_pad)
+        atomicMin(&colkey[j32 + lane], ((u64)key_m << 32) | (unsigned)(warp * 32 + __ffs(key_b) - 1));
+    }
+    __syncthreads();  // all column keys of this tile are final
+
+    // ---- column side: exact index inside the recorded thread's Q points, then global merge ----
+    for (int jj = tid; jj < cnt; jj += CS_THREADS) {
+      const u64 key = colkey[jj];
+      const unsigned mbits = (unsigned)(key >> 32);
+      const int tcand = (int)(unsigned)key;
+      const float bx = sxd[2 * jj], by = syd[2 * jj], bz = szd[2 * jj];
+      int found = 0;
+#pragma unroll
+      for (int q = Q - 1; q >= 0; q--) {
+        const float d = dist2_ref(bx - ax[tcand * Q + q], by - ay[tcand * Q + q], bz - az[tcand * Q + q]);
+        if (__float_as_uint(d) == mbits) found = q;
+      }
+      const int ia = at * TA + tcand * Q + found;
+      atomicMin(&p.keys_b[(size_t)b * nb + ts + jj], ((u64)mbits << 32) | (unsigned)ia);
+    }
+  }
+
+  // ---- row side: first B point of the remembered step that reproduces `best` --------------------
+  const int last_ts = t0 + ((t1 - t0 - 1) / CP_TILE) * CP_TILE;
+#pragma unroll
+  for (int q = 0; q < Q; q++) {
+    const int i = at * TA + tid * Q + q;
+    const int base = t0 + ld_shared_volatile(cstep_addr + q * CS_THREADS * 4) * CS_STEP;
+    const float qx = (q & 1) ? hi2(nax[q >> 1]) : lo2(nax[q >> 1]);  // negated coordinates
+    const float qy = (q & 1) ? hi2(nay[q >> 1]) : lo2(nay[q >> 1]);
+    const float qz = (q & 1) ? hi2(naz[q >> 1]) : lo2(naz[q >> 1]);
+    float d[4];
+    if (base >= last_ts) {
+      const int off = base - last_ts;
+#pragma unroll
+      for (int e = 0; e < 4; e++) d[e] = dist2_ref(sxd[2 * (off + e)] + qx, syd[2 * (off + e)] + qy, szd[2 * (off + e)] + qz);
+    } else {
+      const float* tp = bcloud + (size_t)base * 3;
+#pragma unroll
+      for (int e = 0; e < 4; e++) d[e] = dist2_ref(__ldg(tp + e * 3 + 0) + qx, __ldg(tp + e * 3 + 1) + qy, __ldg(tp + e * 3 + 2) + qz);
+    }
+    int found = 0;
+    if (d[3] == best[q]) found = 3;
+    if (d[2] == best[q]) found = 2;
+    if (d[1] == best[q]) found = 1;
+    if (d[0] == best[q]) found = 0;
+    if (i >= na) continue;
+    atomicMin(&p.keys_a[(size_t)b * na + i], ((u64)__float_as_uint(best[q]) << 32) | (unsigned)(base + found));
+  }
+}
+
+template <int QP>
+static int launch_symp(const SymParams& p, int grid, cudaStream_t stream) {
+  const size_t smem = (size_t)6 * CP_TILE * 4 + (size_t)CP_TILE * 8 + (size_t)4 * CS_THREADS * 2 * QP * 4;
+  auto kern = chamfer_symp_kernel<QP>;
+  PS_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  kern<<<grid, CS_THREADS, smem, stream>>>(p);
+  PS_LAUNCH_CHECK();
+  return PS_OK;
+}
+
 template <int Q>
 static int launch_sym(const SymParams& p, int grid, cudaStream_t stream) {
   const size_t smem = (size_t)3 * CS_TILE * 4 + (size_t)CS_TILE * 8 + (size_t)3 * CS_THREADS * Q * 4;
@@ -248,8 +460,9 @@ static int launch_sym(const SymParams& p, int grid, cudaStream_t stream) {
 // Returns PS_OK when it handled the call, 1 when the shape is better served by the two-pass kernel.
 int chamfer_fwd_symmetric(const float* xyz1, const float* xyz2, float* dist1, float* dist2, int* idx1,
                           int* idx2, int B, int N, int M, int dev, cudaStream_t stream) {
-  if (const char* e = getenv("PS_CHAMFER_SYM"))
-    if (atoi(e) == 0) return 1;
+  int variant = 1;  // 1: B-packed (chamfer_sym_kernel), 2: A-packed kernel (chamfer_symp_kernel), 0: two-pass
+  if (const char* e = getenv("PS_CHAMFER_SYM")) variant = atoi(e);
+  if (variant == 0) return 1;
   const int big = N > M ? N : M, small = N > M ? M : N;
   if (small < 256 || big < 1024) return 1;  // tiny clouds: launch-bound either way
   const int nsm = sm_count(dev);
@@ -259,9 +472,10 @@ int chamfer_fwd_symmetric(const float* xyz1, const float* xyz2, float* dist1, fl
   p.b = a_is_1 ? xyz2 : xyz1;
   p.na = big;
   p.nb = small;
-  int Q = 8;
-  if (const char* e = getenv("PS_CHAMFER_SYM_Q")) { const int v = atoi(e); if (v == 2 || v == 4 || v == 8) Q = v; }
-  while (Q > 2 && CS_THREADS * Q / 2 >= big) Q /= 2;
+  const int qmin = variant == 2 ? 4 : 2;
+  int Q = variant == 2 ? 16 : 8;
+  if (const char* e = getenv("PS_CHAMFER_SYM_Q")) { const int v = atoi(e); if (v >= qmin && v <= Q && (v & (v - 1)) == 0) Q = v; }
+  while (Q > qmin && CS_THREADS * Q / 2 >= big) Q /= 2;
   p.natiles = ceil_div(big, CS_THREADS * Q);
   // B-side split: enough units for >= 3 waves of the 2 resident CTAs per SM (measured on C1:
   // L=256 0.339 ms, L=512 0.330, L=1024 0.367, L=2048 0.375), but never below 256 targets per
@@ -286,9 +500,15 @@ int chamfer_fwd_symmetric(const float* xyz1, const float* xyz2, float* dist1, fl
   p.keys_b = scratch + nka;
   const int grid = B * p.natiles * p.nsplit;
   int rc;
-  if (Q == 8) rc = launch_sym<8>(p, grid, stream);
-  else if (Q == 4) rc = launch_sym<4>(p, grid, stream);
-  else rc = launch_sym<2>(p, grid, stream);
+  if (variant == 2) {
+    if (Q == 16) rc = launch_symp<8>(p, grid, stream);
+    else if (Q == 8) rc = launch_symp<4>(p, grid, stream);
+    else rc = launch_symp<2>(p, grid, stream);
+  } else {
+    if (Q == 8) rc = launch_sym<8>(p, grid, stream);
+    else if (Q == 4) rc = launch_sym<4>(p, grid, stream);
+    else rc = launch_sym<2>(p, grid, stream);
+  }
   if (rc) return rc;
   float* da = a_is_1 ? dist1 : dist2;
   int* ia = a_is_1 ? idx1 : idx2;

@@ -52,7 +52,7 @@ def test_chamfer_fwd_bwd_vs_oracle(B, N, M, dup):
     assert_close_rel(g2.cpu().numpy(), og2, what="gradxyz2")
 
 
-@pytest.mark.parametrize("sym,q", [("1", "8"), ("1", "4"), ("1", "2"), ("0", "8")])
+@pytest.mark.parametrize("sym,q", [("2", "16"), ("2", "8"), ("2", "4"), ("1", "8"), ("1", "4"), ("1", "2"), ("0", "8")])
 @pytest.mark.parametrize("B,N,M,dup", [(2, 2048, 4096, 700), (3, 5000, 1300, 300), (1, 16384, 2048, 548),
                                        (2, 1024, 1024, 1000), (1, 2050, 257, 0), (1, 300, 9000, 100)])
 def test_chamfer_symmetric_and_two_pass_kernels_agree_with_oracle(B, N, M, dup, sym, q, monkeypatch):
