@@ -67,6 +67,20 @@ int ps_chamfer_bwd(const float* xyz1, const float* xyz2, const float* graddist1,
 int ps_chamfer_sums(const float* dist1, const float* dist2, double* out6, long long n1, long long n2,
                     int dev, void* stream);
 
+/* Host-buffer form of one Chamfer step (forward, and backward when graddist1/2 are given): every
+ * pointer here is a HOST pointer with the shapes of ps_chamfer_fwd / ps_chamfer_bwd.  This is the
+ * call for the reference's CPU-allocating wrapper (dist_chamfer_3D.py:33-42 allocates dist/idx on
+ * the CPU and copies) and for metric loops whose clouds arrive from the data loader in host memory.
+ * The batch is processed in chunks of `chunk` clouds (<= 0: library default) on three internal
+ * streams so that upload, kernels and download of consecutive chunks overlap; results are
+ * bit-identical to the device entry points for any chunk size (all kernels are per-cloud).
+ * The call enqueues and returns: the output buffers are complete once `stream` has passed this
+ * point (synchronise it, or an event recorded on it).  Pinned host memory is needed for overlap.
+ * graddist1 == graddist2 == NULL => forward only (gradxyz1/2 ignored). */
+int ps_chamfer_host(const float* xyz1, const float* xyz2, float* dist1, float* dist2, int* idx1,
+                    int* idx2, const float* graddist1, const float* graddist2, float* gradxyz1,
+                    float* gradxyz2, int B, int N, int M, int chunk, int dev, void* stream);
+
 /* ---- Furthest point sampling ------------------------------------------------------------
  * Replaces furthest_point_sampling_kernel_wrapper (pointnet2_ops/_ext-src/src/sampling_gpu.cu:175-229,
  * kernel :69-173; pybind `_ext.furthest_point_sampling`, sampling.cpp:66-87).

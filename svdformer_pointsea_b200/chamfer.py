@@ -62,6 +62,60 @@ def chamfer_sums(dist1, dist2):
     return out
 
 
+def _require_host(t, name, dtype, shape):
+    if not isinstance(t, torch.Tensor) or t.is_cuda:
+        raise L.PointSeaError(f"{name} must be a CPU torch.Tensor (this is the host-buffer entry point)")
+    if t.dtype != dtype or tuple(t.shape) != tuple(shape) or not t.is_contiguous():
+        raise L.PointSeaError(f"{name} must be a contiguous {dtype} tensor of shape {tuple(shape)}, got {t.dtype} {tuple(t.shape)}")
+    return t
+
+
+def chamfer_host(xyz1, xyz2, graddist1=None, graddist2=None, out=None, chunk=0, device=None, blocking=True):
+    """Chamfer forward (+ backward when graddist1/2 are given) on HOST tensors, pipelined through the GPU.
+
+    The batch is cut into chunks of `chunk` clouds (0: library default); upload, kernels and download
+    of consecutive chunks overlap on three streams (csrc/host_pipeline.cu).  Inputs and outputs are
+    CPU tensors — pinned (`.pin_memory()`) for the overlap to happen; `out` may carry preallocated
+    pinned outputs `(dist1, dist2, idx1, idx2[, gradxyz1, gradxyz2])`, otherwise they are allocated
+    pinned here.  With `blocking=False` the outputs are valid once the current CUDA stream of
+    `device` has been synchronised.  Results are bit-identical to chamfer_forward / chamfer_backward.
+    """
+    if xyz1.dim() != 3 or xyz2.dim() != 3 or xyz1.size(2) != 3 or xyz2.size(2) != 3 or xyz1.size(0) != xyz2.size(0):
+        raise L.PointSeaError(f"chamfer expects (B,N,3) and (B,M,3), got {tuple(xyz1.shape)} {tuple(xyz2.shape)}")
+    B, N, _ = xyz1.shape
+    M = xyz2.size(1)
+    _require_host(xyz1, "xyz1", torch.float32, (B, N, 3))
+    _require_host(xyz2, "xyz2", torch.float32, (B, M, 3))
+    with_bwd = graddist1 is not None or graddist2 is not None
+    if with_bwd:
+        if graddist1 is None or graddist2 is None:
+            raise L.PointSeaError("chamfer_host: backward needs both graddist1 and graddist2")
+        _require_host(graddist1, "graddist1", torch.float32, (B, N))
+        _require_host(graddist2, "graddist2", torch.float32, (B, M))
+    if not torch.cuda.is_available():
+        raise L.PointSeaError("chamfer_host needs a CUDA device (there is no CPU implementation)")
+    index = torch.cuda.current_device() if device is None else torch.device(device).index
+    L._check_device(index)
+    if out is None:
+        out = [torch.empty(B, N, dtype=torch.float32).pin_memory(), torch.empty(B, M, dtype=torch.float32).pin_memory(),
+               torch.empty(B, N, dtype=torch.int32).pin_memory(), torch.empty(B, M, dtype=torch.int32).pin_memory()]
+        if with_bwd:
+            out += [torch.empty(B, N, 3, dtype=torch.float32).pin_memory(), torch.empty(B, M, 3, dtype=torch.float32).pin_memory()]
+    shapes = [((B, N), torch.float32), ((B, M), torch.float32), ((B, N), torch.int32), ((B, M), torch.int32),
+              ((B, N, 3), torch.float32), ((B, M, 3), torch.float32)]
+    if len(out) != (6 if with_bwd else 4):
+        raise L.PointSeaError(f"chamfer_host: `out` must hold {6 if with_bwd else 4} tensors")
+    for t, (shape, dt), nm in zip(out, shapes, ("dist1", "dist2", "idx1", "idx2", "gradxyz1", "gradxyz2")):
+        _require_host(t, nm, dt, shape)
+    gp = [L.ptr(graddist1), L.ptr(graddist2), L.ptr(out[4]), L.ptr(out[5])] if with_bwd else [None] * 4
+    rc = L.load().ps_chamfer_host(L.ptr(xyz1), L.ptr(xyz2), L.ptr(out[0]), L.ptr(out[1]), L.ptr(out[2]), L.ptr(out[3]),
+                                  gp[0], gp[1], gp[2], gp[3], B, N, M, int(chunk), index, L.stream_ptr(index))
+    L.check(rc, "ps_chamfer_host")
+    if blocking:
+        torch.cuda.current_stream(index).synchronize()
+    return tuple(out)
+
+
 class chamfer_3DFunction(Function):
     """Drop-in for dist_chamfer_3D.chamfer_3DFunction (dist_chamfer_3D.py:26-64)."""
 

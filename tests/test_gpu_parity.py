@@ -70,6 +70,40 @@ def test_chamfer_symmetric_and_two_pass_kernels_agree_with_oracle(B, N, M, dup, 
     assert np.array_equal(d1.cpu().numpy(), od1) and np.array_equal(d2.cpu().numpy(), od2)
 
 
+@pytest.mark.parametrize("B,N,M,chunk,bwd", [(5, 300, 700, 2, True), (4, 1024, 2048, 0, True), (3, 64, 4096, 1, False),
+                                              (7, 2048, 512, 3, True), (1, 10, 20, 8, True)])
+def test_chamfer_host_pipeline_matches_device_entry_points_bitwise(B, N, M, chunk, bwd):
+    """ps_chamfer_host (host buffers, chunked 3-stream pipeline) == device entry points, bit for bit,
+    for every chunking including ragged last chunks; and it matches the oracle."""
+    g = torch.Generator().manual_seed(4000 + N + M)
+    a, b = make_cloud(g, B, N).pin_memory(), make_cloud(g, B, M).pin_memory()
+    gd1, gd2 = torch.randn(B, N, generator=g).pin_memory(), torch.randn(B, M, generator=g).pin_memory()
+    out = ps.chamfer_host(a, b, gd1 if bwd else None, gd2 if bwd else None, chunk=chunk)
+    d1, d2, i1, i2 = ps.chamfer_forward(a.to(DEV), b.to(DEV))
+    for h, d in zip(out[:4], (d1, d2, i1, i2)):
+        assert torch.equal(h, d.cpu())
+    od1, od2, oi1, oi2 = O.chamfer_fwd(a.numpy(), b.numpy())
+    assert np.array_equal(out[2].numpy(), oi1) and np.array_equal(out[3].numpy(), oi2)
+    assert np.array_equal(out[0].numpy(), od1) and np.array_equal(out[1].numpy(), od2)
+    if bwd:
+        og1, og2 = O.chamfer_bwd(a.numpy(), b.numpy(), gd1.numpy(), gd2.numpy(), oi1, oi2)
+        assert_close_rel(out[4].numpy(), og1, what="gradxyz1 (host)")
+        assert_close_rel(out[5].numpy(), og2, what="gradxyz2 (host)")
+    # second call reuses the staging slots; pageable (non-pinned) buffers also work
+    out2 = ps.chamfer_host(a.clone(), b.clone(), chunk=chunk)
+    assert torch.equal(out2[0], out[0]) and torch.equal(out2[3], out[3])
+
+
+def test_chamfer_host_rejects_device_tensors_and_bad_shapes():
+    a = torch.zeros(2, 8, 3, device=DEV)
+    with pytest.raises(ps.PointSeaError):
+        ps.chamfer_host(a, a)
+    with pytest.raises(ps.PointSeaError):
+        ps.chamfer_host(torch.zeros(2, 8, 3), torch.zeros(3, 8, 3))
+    with pytest.raises(ps.PointSeaError):
+        ps.chamfer_host(torch.zeros(2, 8, 3), torch.zeros(2, 8, 3), graddist1=torch.zeros(2, 8))
+
+
 def test_chamfer_sums_match_torch_reductions():
     g = torch.Generator().manual_seed(12)
     a, b = make_cloud(g, 3, 777).to(DEV), make_cloud(g, 3, 1500).to(DEV)
