@@ -143,6 +143,57 @@ int ps_three_interpolate_fwd(const float* points, const int* idx, const float* w
 int ps_three_interpolate_bwd(const float* grad_out, const int* idx, const float* weight,
                              float* grad_points, int B, int C, int n, int m, int dev, void* stream);
 
+/* ---- fused call sites and the next ops on the path ----------------------
+ * Result order of the kNN entry points below. */
+#define PS_ORDER_SORT 0 /* ascending (dist, index): torch.argsort, as ps_knn */
+#define PS_ORDER_TOPK 1 /* torch.topk(k, largest=False, sorted=True) on CUDA, including its order among
+                            equal distances (gather order + 32-slot bitonic network, k <= 32) */
+
+/* query_knn_point (models/model_utils.py:807-810): square_distance + topk(k, largest=False).
+ * Same arithmetic as ps_knn, result in torch.topk's order.  idx (B,S,k) i32. */
+int ps_knn_point(const float* xyz, const float* new_xyz, int* idx, int B, int N, int S, int k, int dev,
+                 void* stream);
+
+/* The kNN + coordinate grouping + centre subtraction of sample_and_group_knn
+ * (models/model_utils.py:342-345: query_knn, grouping_operation(xyz, idx), grouped_xyz -= new_xyz) in ONE
+ * kernel: idx (B,S,k) i32 as ps_knn, grouped_xyz (B,3,S,k) f32 = xyz[b,idx[b,s,j],c] - new_xyz[b,s,c]. */
+int ps_knn_group_xyz(const float* xyz, const float* new_xyz, int* idx, float* grouped_xyz, int B, int N,
+                     int S, int k, int dev, void* stream);
+
+/* Feature-space kNN (group_local / EdgeConv neighbourhoods, models/model_utils.py:258-279, 807-826):
+ *   xr references, xq queries; channel_major != 0: (B,C,N) / (B,C,S) tensors (EdgeConv's layout), else
+ *   (B,N,C) / (B,S,C) (the layout query_knn_point receives).  idx (B,S,k) i32, k <= 32, N <= 6144.
+ *   dist = ((-2 * dot) + |q|^2) + |r|^2 with dot an ascending-channel FMA chain (cuBLAS fp32 order) and
+ *   |.|^2 in the order of torch.sum(x ** 2, -1) on CUDA; order = PS_ORDER_SORT / PS_ORDER_TOPK.
+ *   No (B,S,N) matrix is materialised. */
+int ps_knn_feat(const float* xr, const float* xq, int* idx, int B, int C, int N, int S, int k,
+                int channel_major, int order, int dev, void* stream);
+
+/* EdgeConv front (models/model_utils.py:869-877 after group_local): x (B,C,N), idx (B,N,K) i32 ->
+ *   out (B,2C,N,K): out[b,c,n,k] = x[b,c,n] - x[b,c,idx[b,n,k]], out[b,C+c,n,k] = x[b,c,n].
+ * bwd: grad_x (B,C,N) is OVERWRITTEN with the gradient of grad_out (B,2C,N,K). */
+int ps_edge_features_fwd(const float* x, const int* idx, float* out, int B, int C, int N, int K, int dev,
+                         void* stream);
+int ps_edge_features_bwd(const float* grad_out, const int* idx, float* grad_x, int B, int C, int N, int K,
+                         int dev, void* stream);
+
+/* index_points (models/model_utils.py:828-845): points (B,N,C), idx (B,M) i32 (trailing index dims
+ * flattened) -> out (B,M,C) = points[b, idx[b,m], :].  bwd OVERWRITES grad_points (B,N,C). */
+int ps_index_points_fwd(const float* points, const int* idx, float* out, int B, int N, int M, int C,
+                        int dev, void* stream);
+int ps_index_points_bwd(const float* grad_out, const int* idx, float* grad_points, int B, int N, int M,
+                        int C, int dev, void* stream);
+
+/* Evaluation epilogue of one Chamfer call (calc_cd utils/loss_utils.py:98-115, fscore metrics/CD/fscore.py:3-16,
+ * calc_dcd utils/loss_utils.py:117-155) in one launch:
+ *   out8 (B,8) f32 = { mean sqrt dist1, mean sqrt dist2, mean dist1, mean dist2, precision_1, precision_2,
+ *                      fscore, dcd } per cloud; dist1 (B,n1), dist2 (B,n2), idx1 (B,n1) in [0,n2), idx2 (B,n2)
+ *   in [0,n1).  idx1 == idx2 == NULL skips the density-aware term (out[7] = 0).  dcd_frac1 / dcd_frac2 are
+ *   calc_dcd's frac_21 / frac_12 (the factors applied to the dist1 / dist2 side). */
+int ps_chamfer_metrics(const float* dist1, const float* dist2, const int* idx1, const int* idx2, float* out8,
+                       int B, int n1, int n2, float fscore_threshold, float dcd_alpha, float dcd_n_lambda,
+                       float dcd_frac1, float dcd_frac2, int dev, void* stream);
+
 /* ---- measurement helpers (bench.py) ------------------------------------------------------
  * Runs an FFMA2-only kernel on `dev` and returns the best-of-`reps` fp32 TFLOP/s: the live
  * roofline denominator for the Chamfer kernel (MEASURED_PEAKS.json has no fp32 figure).

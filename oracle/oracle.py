@@ -250,3 +250,181 @@ def torch_gather(features, idx):
     import torch
     B, C, N = features.shape
     return torch.gather(features, 2, idx.long()[:, None, :].expand(B, C, idx.shape[1]))
+
+
+# ---- "next" rows: torch re-expressions of the reference call sites -----------------
+def torch_square_distance(src, dst):
+    """models/model_utils.py:258-279 verbatim (expanded form through matmul)."""
+    import torch
+    B, N, _ = src.shape
+    M = dst.shape[1]
+    dist = -2 * torch.matmul(src, dst.permute(0, 2, 1))
+    dist += torch.sum(src ** 2, -1).view(B, N, 1)
+    dist += torch.sum(dst ** 2, -1).view(B, 1, M)
+    return dist
+
+
+def torch_query_knn_point(k, xyz, new_xyz):
+    """models/model_utils.py:807-810: topk(k, largest=False) of square_distance; (B,S,k) int64."""
+    dist = torch_square_distance(new_xyz, xyz)
+    _, group_idx = dist.topk(k, largest=False)
+    return group_idx
+
+
+def torch_index_points(points, idx):
+    """models/model_utils.py:828-845: points (B,N,C), idx (B,S[,K]) -> (B,S[,K],C)."""
+    import torch
+    B = points.shape[0]
+    view_shape = list(idx.shape)
+    view_shape[1:] = [1] * (len(view_shape) - 1)
+    repeat_shape = list(idx.shape)
+    repeat_shape[0] = 1
+    batch_indices = torch.arange(B, dtype=torch.long, device=points.device).view(view_shape).repeat(repeat_shape)
+    return points[batch_indices, idx, :]
+
+
+def torch_edge_features(x, k, idx=None):
+    """EdgeConv up to the convolution (models/model_utils.py:812-826, 869-877): x (B,C,N) ->
+    (feature (B,2C,N,k) = cat(central - neighbour, central), idx (B,N,k) int64)."""
+    import torch
+    xt = x.transpose(2, 1).contiguous()
+    if idx is None:
+        idx = torch_query_knn_point(k, xt, xt)
+    neigh = torch_index_points(xt, idx).permute(0, 3, 1, 2).contiguous()
+    central = x.unsqueeze(dim=3).repeat(1, 1, 1, k)
+    edge = central - neigh
+    return torch.cat((edge, central), dim=1), idx
+
+
+def torch_fscore(dist1, dist2, threshold=0.0001):
+    """metrics/CD/fscore.py:3-16 verbatim."""
+    import torch
+    precision_1 = torch.mean((dist1 < threshold).float(), dim=1)
+    precision_2 = torch.mean((dist2 < threshold).float(), dim=1)
+    fscore = 2 * precision_1 * precision_2 / (precision_1 + precision_2)
+    fscore[torch.isnan(fscore)] = 0
+    return fscore, precision_1, precision_2
+
+
+def torch_cd_terms(dist1, dist2):
+    """calc_cd's reductions (utils/loss_utils.py:102-103): per-cloud cd_p, cd_t."""
+    import torch
+    cd_p = (torch.sqrt(dist1).mean(1) + torch.sqrt(dist2).mean(1)) / 2
+    cd_t = dist1.mean(1) + dist2.mean(1)
+    return cd_p, cd_t
+
+
+def torch_dcd_from_raw(dist1, dist2, idx1, idx2, n_x, n_gt, alpha=1000, n_lambda=1, non_reg=False):
+    """calc_dcd after its Chamfer call (utils/loss_utils.py:117-155): dist1/idx1 are per gt point
+    (nearest x), dist2/idx2 per x point (nearest gt).  Returns the per-cloud loss (B,)."""
+    import torch
+    if non_reg:
+        frac_12 = max(1, n_x / n_gt)
+        frac_21 = max(1, n_gt / n_x)
+    else:
+        frac_12 = n_x / n_gt
+        frac_21 = n_gt / n_x
+    exp_dist1, exp_dist2 = torch.exp(-dist1 * alpha), torch.exp(-dist2 * alpha)
+    count1 = torch.zeros_like(idx2)
+    count1.scatter_add_(1, idx1.long(), torch.ones_like(idx1))
+    weight1 = count1.gather(1, idx1.long()).float().detach() ** n_lambda
+    weight1 = (weight1 + 1e-6) ** (-1) * frac_21
+    loss1 = (1 - exp_dist1 * weight1).mean(dim=1)
+    count2 = torch.zeros_like(idx1)
+    count2.scatter_add_(1, idx2.long(), torch.ones_like(idx2))
+    weight2 = count2.gather(1, idx2.long()).float().detach() ** n_lambda
+    weight2 = (weight2 + 1e-6) ** (-1) * frac_12
+    loss2 = (1 - exp_dist2 * weight2).mean(dim=1)
+    return (loss1 + loss2) / 2
+
+
+# ---- bit-exact checker for the "next" rows (C restatement) ------------------------------------------
+def _next_lib():
+    L = lib()
+    if not getattr(L, "_next_ready", False):
+        _fo = ctypes.c_float
+        L.or_knn_feat.argtypes = [_F, _F, _I, _i, _i, _i, _i, _i, _i]
+        L.or_edge_features.argtypes = [_F, _I, _F, _i, _i, _i, _i]
+        L.or_edge_features_grad.argtypes = [_F, _I, _F, _i, _i, _i, _i]
+        L.or_index_points.argtypes = [_F, _I, _F, _i, _i, _i, _i]
+        L.or_index_points_grad.argtypes = [_F, _I, _F, _i, _i, _i, _i]
+        L.or_chamfer_metrics.argtypes = [_F, _F, ctypes.c_void_p, ctypes.c_void_p, _F, _i, _i, _i, _fo, _fo, _fo, _fo, _fo]
+        for n in ("or_knn_feat", "or_edge_features", "or_edge_features_grad", "or_index_points", "or_index_points_grad",
+                  "or_chamfer_metrics"):
+            getattr(L, n).restype = None
+        L._next_ready = True
+    return L
+
+
+def knn_feat(xr, xq, k, order=0):
+    """xr (B,N,C), xq (B,S,C) point-major -> (B,S,k) int32; order 0 = (dist, index), 1 = torch.topk order."""
+    xr, xq = _f(xr), _f(xq)
+    B, N, C = xr.shape
+    S = xq.shape[1]
+    out = np.empty((B, S, k), np.int32)
+    _next_lib().or_knn_feat(xr, xq, out, B, C, N, S, k, order)
+    return out
+
+
+def knn_point(xyz, new_xyz, k):
+    """query_knn_point on coordinates: torch.topk order."""
+    return knn_feat(xyz, new_xyz, k, order=1)
+
+
+def knn_group_xyz(xyz, new_xyz, k):
+    """sample_and_group_knn's kNN + grouping + centre subtraction (models/model_utils.py:342-345)."""
+    xyz, new_xyz = _f(xyz), _f(new_xyz)
+    idx = knn(xyz, new_xyz, k)
+    g = group(np.ascontiguousarray(xyz.transpose(0, 2, 1)), idx)  # (B,3,S,k)
+    g = g - np.ascontiguousarray(new_xyz.transpose(0, 2, 1))[:, :, :, None]
+    return idx, g.astype(np.float32)
+
+
+def edge_features(x, idx):
+    x, idx = _f(x), _n(idx)
+    B, C, N = x.shape
+    K = idx.shape[2]
+    out = np.empty((B, 2 * C, N, K), np.float32)
+    _next_lib().or_edge_features(x, idx, out, B, C, N, K)
+    return out
+
+
+def edge_features_grad(gout, idx):
+    gout, idx = _f(gout), _n(idx)
+    B, C2, N, K = gout.shape
+    out = np.empty((B, C2 // 2, N), np.float32)
+    _next_lib().or_edge_features_grad(gout, idx, out, B, C2 // 2, N, K)
+    return out
+
+
+def index_points(points, idx):
+    points, idx = _f(points), _n(idx)
+    B, N, C = points.shape
+    flat = np.ascontiguousarray(idx.reshape(B, -1))
+    out = np.empty((B, flat.shape[1], C), np.float32)
+    _next_lib().or_index_points(points, flat, out, B, N, flat.shape[1], C)
+    return out.reshape(*idx.shape, C)
+
+
+def index_points_grad(gout, idx, N):
+    gout, idx = _f(gout), _n(idx)
+    B = gout.shape[0]
+    C = gout.shape[-1]
+    flat = np.ascontiguousarray(idx.reshape(B, -1))
+    g = np.ascontiguousarray(gout.reshape(B, -1, C))
+    out = np.empty((B, N, C), np.float32)
+    _next_lib().or_index_points_grad(g, flat, out, B, N, flat.shape[1], C)
+    return out
+
+
+def chamfer_metrics(dist1, dist2, idx1=None, idx2=None, threshold=0.0001, alpha=1000.0, n_lambda=1.0, frac1=1.0, frac2=1.0):
+    dist1, dist2 = _f(dist1), _f(dist2)
+    B, n1 = dist1.shape
+    n2 = dist2.shape[1]
+    out = np.empty((B, 8), np.float32)
+    p1 = p2 = None
+    if idx1 is not None:
+        idx1, idx2 = _n(idx1), _n(idx2)
+        p1, p2 = idx1.ctypes.data, idx2.ctypes.data
+    _next_lib().or_chamfer_metrics(dist1, dist2, p1, p2, out, B, n1, n2, threshold, alpha, n_lambda, frac1, frac2)
+    return out

@@ -337,3 +337,224 @@ void or_knn(const float* xyz, const float* new_xyz, int* idx, int B, int N, int 
     }
   free(row);
 }
+
+/* ================================================================================================
+ * "Next" rows: feature-space kNN in torch.topk order, EdgeConv front, index_points,
+ * evaluation metrics.  Their reference is torch code, so the restatement follows the torch CUDA
+ * kernels that code dispatches to; pinned by tests/golden/next.npz (torch 2.11 + cuBLAS on B200).
+ * ================================================================================================ */
+
+/* torch.sum(x ** 2, -1) of one row of C elements (stride sc), in the order of ATen's reduce kernel
+ * (ATen/native/cuda/Reduce.cuh): `bw` cooperating threads; thread t owns elements t, t+bw, ... in
+ * vt0 = 4 interleaved accumulators (thread_reduce_impl :562-630), or — "vectorize along input",
+ * chosen when C >= 128 (:1099) — float4 chunks t, t+bw, ... with one accumulator per vector lane
+ * (input_vectorized_thread_reduce_impl :500-560); accumulators are combined ((a0+a1)+a2)+a3 and the
+ * threads by a shuffle-down tree with decreasing offset (block_x_reduce :632-667). */
+static int pow2floor_i(long long v) { int p = 1; while ((long long)p * 2 <= v) p *= 2; return p; }
+static int torch_reduce_bw(long long d0, long long rows) { /* ReduceConfig::set_block_dimension, :100-108 */
+  const int maxt = 512;
+  int d0p = d0 < maxt ? pow2floor_i(d0) : maxt;
+  int d1p = rows < maxt ? pow2floor_i(rows) : maxt;
+  int bw = d0p < 32 ? d0p : 32;
+  int bh = d1p < maxt / bw ? d1p : maxt / bw;
+  bw = d0p < maxt / bh ? d0p : maxt / bh;
+  return bw;
+}
+static float torch_rowsumsq(const float* p, int C, long long sc, long long rows) {
+  const int vec = C >= 128 && (C % 4) == 0;
+  const int bw = torch_reduce_bw(vec ? C / 4 : C, rows);
+  float tv[512];
+  for (int t = 0; t < bw; t++) {
+    float a[4] = {0.f, 0.f, 0.f, 0.f};
+    if (vec) {
+      for (int c = t; c < C / 4; c += bw)
+        for (int i = 0; i < 4; i++) { const float v = p[(size_t)(4 * c + i) * sc]; const float s = v * v; a[i] = a[i] + s; }
+    } else {
+      int j = 0;
+      for (int e = t; e < C; e += bw, j++) { const float v = p[(size_t)e * sc]; const float s = v * v; a[j & 3] = a[j & 3] + s; }
+    }
+    float v = a[0] + a[1];
+    v = v + a[2];
+    v = v + a[3];
+    tv[t] = v;
+  }
+  for (int off = bw / 2; off > 0; off /= 2)
+    for (int t = 0; t < off; t++) tv[t] = tv[t] + tv[t + off];
+  return tv[0];
+}
+
+/* torch.topk(k, largest=False, sorted=True) order of k results given in ascending (d, i) order:
+ * gather [d < kth in index order] ++ [d == kth in index order] (TensorTopK.cu gatherTopK), then the
+ * 32-slot bitonic network of sortKeyValueInplace (SortUtils.cuh:33-98), comparator LTOp, slots >= k invalid. */
+static int cmp_int(const void* a, const void* b) { const int x = *(const int*)a, y = *(const int*)b; return (x > y) - (x < y); }
+static void torch_topk_order(knn_pair* r, int k) {
+  float keys[32]; int vals[32]; int valid[32];
+  const float kth = r[k - 1].d;
+  int less[32], eq[32], nl = 0, ne = 0;
+  for (int e = 0; e < k; e++) { if (r[e].d < kth) less[nl++] = e; else eq[ne++] = e; }
+  /* index order inside each group */
+  int order[32], n = 0;
+  { int tmp[32]; for (int e = 0; e < nl; e++) tmp[e] = r[less[e]].i; qsort(tmp, (size_t)nl, sizeof(int), cmp_int);
+    for (int e = 0; e < nl; e++) for (int f = 0; f < nl; f++) if (r[less[f]].i == tmp[e]) { order[n++] = less[f]; break; } }
+  { int tmp[32]; for (int e = 0; e < ne; e++) tmp[e] = r[eq[e]].i; qsort(tmp, (size_t)ne, sizeof(int), cmp_int);
+    for (int e = 0; e < ne; e++) for (int f = 0; f < ne; f++) if (r[eq[f]].i == tmp[e]) { order[n++] = eq[f]; break; } }
+  for (int e = 0; e < 32; e++) { valid[e] = e < k; keys[e] = e < k ? r[order[e]].d : 0.f; vals[e] = e < k ? r[order[e]].i : -1; }
+#define OR_SWAP(POS, STRIDE, DIR)                                                        \
+  do {                                                                                   \
+    const int a_ = (POS), b_ = (POS) + (STRIDE);                                         \
+    const int sw_ = ((keys[a_] < keys[b_]) && valid[a_]) || !valid[b_];                  \
+    if (sw_ == (DIR)) {                                                                  \
+      float tk = keys[a_]; keys[a_] = keys[b_]; keys[b_] = tk;                           \
+      int tv_ = vals[a_]; vals[a_] = vals[b_]; vals[b_] = tv_;                           \
+      int tb = valid[a_]; valid[a_] = valid[b_]; valid[b_] = tb;                         \
+    }                                                                                    \
+  } while (0)
+  for (unsigned size = 2; size < 32; size *= 2)
+    for (unsigned stride = size / 2; stride > 0; stride /= 2)
+      for (unsigned t = 0; t < 16; t++) {
+        const int flag = (t & (size / 2)) != 0;
+        const unsigned pos = 2 * t - (t & (stride - 1));
+        OR_SWAP(pos, stride, flag);
+      }
+  for (unsigned stride = 16; stride > 0; stride /= 2)
+    for (unsigned t = 0; t < 16; t++) {
+      const unsigned pos = 2 * t - (t & (stride - 1));
+      OR_SWAP(pos, stride, 0);
+    }
+#undef OR_SWAP
+  for (int e = 0; e < k; e++) { r[e].d = keys[e]; r[e].i = vals[e]; }
+}
+
+/* query_knn_point / square_distance on C-dimensional points (models/model_utils.py:258-279, 807-810):
+ * xr (B,N,C) references, xq (B,S,C) queries, point-major.  dot = ascending-channel fmaf chain (cuBLAS fp32),
+ * norms = torch_rowsumsq, dist = ((-2*dot) + |q|^2) + |r|^2.  order 0: ascending (dist, index);
+ * order 1: torch.topk order (k <= 32). */
+void or_knn_feat(const float* xr, const float* xq, int* idx, int B, int C, int N, int S, int k, int order) {
+  knn_pair* row = (knn_pair*)malloc(sizeof(knn_pair) * (size_t)N);
+  float* pp = (float*)malloc(sizeof(float) * (size_t)N);
+  for (int b = 0; b < B; b++) {
+    for (int n = 0; n < N; n++) pp[n] = torch_rowsumsq(xr + ((size_t)b * N + n) * C, C, 1, (long long)B * N);
+    for (int s = 0; s < S; s++) {
+      const float* q = xq + ((size_t)b * S + s) * C;
+      const float qq = torch_rowsumsq(q, C, 1, (long long)B * S);
+      for (int n = 0; n < N; n++) {
+        const float* r = xr + ((size_t)b * N + n) * C;
+        float dot = 0.f;
+        for (int c = 0; c < C; c++) dot = fmaf(q[c], r[c], dot);
+        float d = -2.0f * dot;
+        d = d + qq;
+        d = d + pp[n];
+        row[n].d = d;
+        row[n].i = n;
+      }
+      qsort(row, (size_t)N, sizeof(knn_pair), knn_cmp);
+      if (order == 1) torch_topk_order(row, k);
+      for (int e = 0; e < k; e++) idx[((size_t)b * S + s) * k + e] = row[e].i;
+    }
+  }
+  free(row);
+  free(pp);
+}
+
+/* Top of EdgeConv.forward (models/model_utils.py:869-877): out (B,2C,N,K) = cat(central - neighbour, central). */
+void or_edge_features(const float* x, const int* idx, float* out, int B, int C, int N, int K) {
+  for (int b = 0; b < B; b++)
+    for (int c = 0; c < C; c++)
+      for (int n = 0; n < N; n++)
+        for (int k = 0; k < K; k++) {
+          const float cen = x[((size_t)b * C + c) * N + n];
+          const float nb = x[((size_t)b * C + c) * N + idx[((size_t)b * N + n) * K + k]];
+          out[(((size_t)b * 2 * C + c) * N + n) * K + k] = cen - nb;
+          out[(((size_t)b * 2 * C + C + c) * N + n) * K + k] = cen;
+        }
+}
+/* its gradient (what autograd derives from the reference expression), accumulated in double */
+void or_edge_features_grad(const float* gout, const int* idx, float* gx, int B, int C, int N, int K) {
+  double* acc = (double*)malloc(sizeof(double) * (size_t)N);
+  for (int b = 0; b < B; b++)
+    for (int c = 0; c < C; c++) {
+      for (int n = 0; n < N; n++) acc[n] = 0.0;
+      for (int n = 0; n < N; n++)
+        for (int k = 0; k < K; k++) {
+          const double ge = gout[(((size_t)b * 2 * C + c) * N + n) * K + k];
+          const double gc = gout[(((size_t)b * 2 * C + C + c) * N + n) * K + k];
+          acc[n] += ge + gc;
+          acc[idx[((size_t)b * N + n) * K + k]] -= ge;
+        }
+      for (int n = 0; n < N; n++) gx[((size_t)b * C + c) * N + n] = (float)acc[n];
+    }
+  free(acc);
+}
+
+/* index_points (models/model_utils.py:828-845): out (B,M,C) = points[b, idx[b,m], :] */
+void or_index_points(const float* pts, const int* idx, float* out, int B, int N, int M, int C) {
+  for (int b = 0; b < B; b++)
+    for (int m = 0; m < M; m++)
+      memcpy(out + ((size_t)b * M + m) * C, pts + ((size_t)b * N + idx[(size_t)b * M + m]) * C, sizeof(float) * (size_t)C);
+}
+void or_index_points_grad(const float* gout, const int* idx, float* gpts, int B, int N, int M, int C) {
+  double* acc = (double*)calloc((size_t)N * C, sizeof(double));
+  for (int b = 0; b < B; b++) {
+    memset(acc, 0, sizeof(double) * (size_t)N * C);
+    for (int m = 0; m < M; m++)
+      for (int c = 0; c < C; c++) acc[(size_t)idx[(size_t)b * M + m] * C + c] += gout[((size_t)b * M + m) * C + c];
+    for (size_t i = 0; i < (size_t)N * C; i++) gpts[(size_t)b * N * C + i] = (float)acc[i];
+  }
+  free(acc);
+}
+
+/* calc_cd / fscore / calc_dcd per cloud (utils/loss_utils.py:98-155, metrics/CD/fscore.py:3-16):
+ * out (B,8) = { mean sqrt d1, mean sqrt d2, mean d1, mean d2, precision_1, precision_2, fscore, dcd }.
+ * Element-wise steps in fp32 in the reference's order, means accumulated in double. */
+void or_chamfer_metrics(const float* dist1, const float* dist2, const int* idx1, const int* idx2, float* out, int B,
+                        int n1, int n2, float thr, float alpha, float n_lambda, float frac1, float frac2) {
+  int* count1 = (int*)malloc(sizeof(int) * (size_t)n2);
+  int* count2 = (int*)malloc(sizeof(int) * (size_t)n1);
+  for (int b = 0; b < B; b++) {
+    const float* d1 = dist1 + (size_t)b * n1;
+    const float* d2 = dist2 + (size_t)b * n2;
+    double v[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    if (idx1 && idx2) {
+      memset(count1, 0, sizeof(int) * (size_t)n2);
+      memset(count2, 0, sizeof(int) * (size_t)n1);
+      for (int j = 0; j < n1; j++) count1[idx1[(size_t)b * n1 + j]]++;
+      for (int j = 0; j < n2; j++) count2[idx2[(size_t)b * n2 + j]]++;
+    }
+    for (int side = 0; side < 2; side++) {
+      const float* d = side ? d2 : d1;
+      const int n = side ? n2 : n1;
+      const int* ix = side ? idx2 : idx1;
+      const int* cnt = side ? count2 : count1;
+      const float frac = side ? frac2 : frac1;
+      for (int j = 0; j < n; j++) {
+        v[0 + side] += (double)sqrtf(d[j]);
+        v[2 + side] += (double)d[j];
+        v[4 + side] += d[j] < thr ? 1.0 : 0.0;
+        if (idx1 && idx2) {
+          const float e = expf(-d[j] * alpha);
+          float w = (float)cnt[ix[(size_t)b * n + j]];
+          if (n_lambda == 0.5f) w = sqrtf(w); /* torch's pow special-cases 0.5 / 2 (PowKernel.cu) */
+          else if (n_lambda == 2.0f) w = w * w;
+          else if (n_lambda != 1.0f) w = powf(w, n_lambda);
+          w = w + 1e-6f;
+          w = 1.0f / w;
+          w = w * frac;
+          const float t = e * w;
+          v[6 + side] += (double)(1.0f - t);
+        }
+      }
+    }
+    float* o = out + (size_t)b * 8;
+    o[0] = (float)(v[0] / n1); o[1] = (float)(v[1] / n2);
+    o[2] = (float)(v[2] / n1); o[3] = (float)(v[3] / n2);
+    const float p1 = (float)(v[4] / n1), p2 = (float)(v[5] / n2);
+    o[4] = p1; o[5] = p2;
+    float f = 2.0f * p1;
+    f = f * p2;
+    f = f / (p1 + p2);
+    o[6] = (f != f) ? 0.f : f;
+    o[7] = (idx1 && idx2) ? ((float)(v[6] / n1) + (float)(v[7] / n2)) / 2.0f : 0.f;
+  }
+  free(count1);
+  free(count2);
+}

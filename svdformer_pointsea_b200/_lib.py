@@ -33,6 +33,15 @@ _SIGNATURES = {
     "ps_group_bwd": [_P, _P, _P, _c_int, _c_int, _c_int, _c_int, _c_int, _c_int, _P],
     "ps_ball_query": [_P, _P, _P, _c_int, _c_int, _c_int, _c_float, _c_int, _c_int, _P],
     "ps_knn": [_P, _P, _P, _c_int, _c_int, _c_int, _c_int, _c_int, _c_int, _P],
+    "ps_knn_point": [_P, _P, _P, _c_int, _c_int, _c_int, _c_int, _c_int, _P],
+    "ps_knn_group_xyz": [_P, _P, _P, _P, _c_int, _c_int, _c_int, _c_int, _c_int, _P],
+    "ps_knn_feat": [_P, _P, _P, _c_int, _c_int, _c_int, _c_int, _c_int, _c_int, _c_int, _c_int, _P],
+    "ps_edge_features_fwd": [_P, _P, _P, _c_int, _c_int, _c_int, _c_int, _c_int, _P],
+    "ps_edge_features_bwd": [_P, _P, _P, _c_int, _c_int, _c_int, _c_int, _c_int, _P],
+    "ps_index_points_fwd": [_P, _P, _P, _c_int, _c_int, _c_int, _c_int, _c_int, _P],
+    "ps_index_points_bwd": [_P, _P, _P, _c_int, _c_int, _c_int, _c_int, _c_int, _P],
+    "ps_chamfer_metrics": [_P, _P, _P, _P, _P, _c_int, _c_int, _c_int, _c_float, _c_float, _c_float, _c_float,
+                           _c_float, _c_int, _P],
     "ps_three_nn": [_P, _P, _P, _P, _c_int, _c_int, _c_int, _c_int, _P],
     "ps_three_interpolate_fwd": [_P, _P, _P, _P, _c_int, _c_int, _c_int, _c_int, _c_int, _P],
     "ps_three_interpolate_bwd": [_P, _P, _P, _P, _c_int, _c_int, _c_int, _c_int, _c_int, _P],

@@ -67,8 +67,8 @@ int chamfer_fwd_symmetric(const float* xyz1, const float* xyz2, float* dist1, fl
                           int* idx2, int B, int N, int M, int dev, cudaStream_t stream);
 
 // knn_select.cu: PS_OK when handled, 1 when the streaming kernel in neighbors.cu should run instead
-int knn_select_launch(const float* xyz, const float* new_xyz, int* idx, int B, int N, int S, int k, int skip,
-                      int var, int nsm, cudaStream_t stream);
+int knn_select_launch(const float* xyz, const float* new_xyz, int* idx, float* gxyz, int B, int N, int S, int k,
+                      int skip, int order, int var, int nsm, cudaStream_t stream);
 
 static inline int ceil_div(long long a, long long b) { return (int)((a + b - 1) / b); }
 

@@ -1,0 +1,328 @@
+// Feature-space kNN for sm_100a: query_knn_point / group_local / EdgeConv neighbourhoods on C-dimensional
+// features (models/model_utils.py:258-279 square_distance, :807-826; EdgeConv(64,256,8), EdgeConv(256,512,4)
+// in models/SVDFormer.py:171-172 and models_PointSea/PointSea.py:234-236).
+//
+// The reference materialises dist = -2 * (Q @ R^T) + |q|^2 + |r|^2 as a (B,S,N) fp32 matrix through cuBLAS and
+// two torch reductions, then runs torch.topk on every row.  Here one CTA owns a tile of TQ queries of one
+// cloud: the TQ x N distance block is produced in shared memory by an fp32 FMA tile loop and each row is
+// reduced to its k smallest by one warp (threshold selection as in knn_select.cu) — nothing of size S*N
+// ever reaches HBM.
+//
+// Arithmetic (measured bit-exactly on B200 against torch 2.11 / cuBLAS, tools + tests/golden/next.npz):
+//   dot   = ascending-channel FMA chain: acc = fma(q_c, r_c, acc), c = 0..C-1  (cuBLAS fp32 SIMT GEMM order)
+//   |x|^2 = torch.sum(x ** 2, -1) in the order of ATen's reduce kernel (Reduce.cuh): squares rounded
+//           separately; "thread" t of a row owns elements t, t+bw, ... (or float4 chunks t, t+bw, ... when
+//           C >= 128) in 4 interleaved accumulators, combined ((a0+a1)+a2)+a3, then a shuffle-down tree
+//           over bw = min(pow2floor(C or C/4), 32) threads.  C = 3 gives (x^2 + z^2) + y^2, the order
+//           found earlier for the coordinate kNN.
+//   dist  = ((-2 * dot) + |q|^2) + |r|^2
+// Result order: PS_ORDER_SORT or PS_ORDER_TOPK (select.cuh).
+#include "common.cuh"
+#include "select.cuh"
+
+#include <cstdlib>
+
+namespace ps {
+namespace {
+
+constexpr int FK_THREADS = 256;
+constexpr int FK_WARPS = FK_THREADS / 32;
+constexpr int FK_KC = 16;   // channels per shared-memory stage
+constexpr int FK_TR = 128;  // reference points per accumulator pass
+
+// One warp per row; lane t plays torch's reduce thread t (block width bw <= 32).
+__global__ void __launch_bounds__(FK_THREADS) rowsumsq_torch_kernel(const float* __restrict__ x, float* __restrict__ out,
+                                                                    int C, int N, long long sb, long long sn, long long sc,
+                                                                    int vec, int bw, long long rows) {
+  const long long row = (long long)blockIdx.x * FK_WARPS + (threadIdx.x >> 5);
+  if (row >= rows) return;
+  const int lane = threadIdx.x & 31;
+  const int b = (int)(row / N), n = (int)(row % N);
+  const float* p = x + (size_t)b * sb + (size_t)n * sn;
+  float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+  if (lane < bw) {
+    if (vec) {
+      for (int c = lane; c < C / 4; c += bw) {
+        const float v0 = __ldg(p + (size_t)(4 * c + 0) * sc), v1 = __ldg(p + (size_t)(4 * c + 1) * sc);
+        const float v2 = __ldg(p + (size_t)(4 * c + 2) * sc), v3 = __ldg(p + (size_t)(4 * c + 3) * sc);
+        a0 = __fadd_rn(a0, __fmul_rn(v0, v0));
+        a1 = __fadd_rn(a1, __fmul_rn(v1, v1));
+        a2 = __fadd_rn(a2, __fmul_rn(v2, v2));
+        a3 = __fadd_rn(a3, __fmul_rn(v3, v3));
+      }
+    } else {
+      int j = 0;
+      for (int e = lane; e < C; e += bw, j++) {
+        const float v = __ldg(p + (size_t)e * sc);
+        const float s = __fmul_rn(v, v);
+        const int a = j & 3;
+        if (a == 0) a0 = __fadd_rn(a0, s);
+        else if (a == 1) a1 = __fadd_rn(a1, s);
+        else if (a == 2) a2 = __fadd_rn(a2, s);
+        else a3 = __fadd_rn(a3, s);
+      }
+    }
+  }
+  float v = __fadd_rn(__fadd_rn(__fadd_rn(a0, a1), a2), a3);
+  for (int off = bw >> 1; off > 0; off >>= 1) v = __fadd_rn(v, __shfl_down_sync(0xffffffffu, v, off));
+  if (lane == 0) out[row] = v;
+}
+
+struct FkArgs {
+  const float* xq; const float* xr;    // queries / references
+  const float* qq; const float* pp;    // their torch-order squared norms, (B,S) and (B,N)
+  int* idx;                            // (B,S,k)
+  int C, N, S, k, order, npad;
+  long long sbq, snq, scq, sbr, snr, scr;
+};
+
+// values only, ascending
+__device__ __forceinline__ float fk_sort_values(float v, int lane) {
+#pragma unroll
+  for (int k = 2; k <= 32; k <<= 1) {
+#pragma unroll
+    for (int j = k >> 1; j > 0; j >>= 1) {
+      const float o = __shfl_xor_sync(0xffffffffu, v, j);
+      const bool keep_min = (((lane & k) == 0) == ((lane & j) == 0));
+      v = keep_min ? fminf(v, o) : fmaxf(v, o);
+    }
+  }
+  return v;
+}
+
+template <int TQ>
+__global__ void __launch_bounds__(FK_THREADS) knn_feat_kernel(const FkArgs a) {
+  constexpr int QPT = TQ / FK_WARPS;  // queries per thread in the tile loop = rows per warp in the selection
+  extern __shared__ __align__(16) float smem[];
+  float* dist = smem;                          // TQ x npad
+  float* qs = dist + (size_t)TQ * a.npad;      // FK_KC x TQ
+  float* rs = qs + FK_KC * TQ;                 // FK_KC x FK_TR
+  __shared__ float bufd[FK_WARPS][32];
+  __shared__ int bufi[FK_WARPS][32];
+  const int b = blockIdx.y, q0 = blockIdx.x * TQ, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const float INF = __int_as_float(0x7f800000);
+  const float* xq = a.xq + (size_t)b * a.sbq;
+  const float* xr = a.xr + (size_t)b * a.sbr;
+  const int C = a.C, N = a.N, S = a.S, npad = a.npad;
+
+  float qn[QPT];
+#pragma unroll
+  for (int i = 0; i < QPT; i++) {
+    const int q = q0 + warp * QPT + i;
+    qn[i] = q < S ? __ldg(a.qq + (size_t)b * S + q) : 0.f;
+  }
+
+  for (int r0 = 0; r0 < npad; r0 += FK_TR) {
+    float acc[QPT][4];
+#pragma unroll
+    for (int i = 0; i < QPT; i++)
+#pragma unroll
+      for (int j = 0; j < 4; j++) acc[i][j] = 0.f;
+    for (int c0 = 0; c0 < C; c0 += FK_KC) {
+      const int kcn = min(FK_KC, C - c0);
+      __syncthreads();
+      for (int i = tid; i < FK_KC * TQ; i += FK_THREADS) {
+        const int kc = i / TQ, q = i % TQ;
+        float v = 0.f;
+        if (kc < kcn && q0 + q < S) v = __ldg(xq + (size_t)(q0 + q) * a.snq + (size_t)(c0 + kc) * a.scq);
+        qs[kc * TQ + q] = v;
+      }
+      for (int i = tid; i < FK_KC * FK_TR; i += FK_THREADS) {
+        const int kc = i / FK_TR, r = i % FK_TR;
+        float v = 0.f;
+        if (kc < kcn && r0 + r < N) v = __ldg(xr + (size_t)(r0 + r) * a.snr + (size_t)(c0 + kc) * a.scr);
+        rs[kc * FK_TR + r] = v;
+      }
+      __syncthreads();
+      // ascending-channel FMA chain per (query, reference) pair; a partial last stage stops at kcn so that
+      // no padded product enters the chain
+      if (kcn == FK_KC) {
+#pragma unroll
+        for (int kc = 0; kc < FK_KC; kc++) {
+          const float4 rv = *reinterpret_cast<const float4*>(&rs[kc * FK_TR + lane * 4]);
+#pragma unroll
+          for (int i = 0; i < QPT; i++) {
+            const float qv = qs[kc * TQ + warp * QPT + i];
+            acc[i][0] = __fmaf_rn(qv, rv.x, acc[i][0]);
+            acc[i][1] = __fmaf_rn(qv, rv.y, acc[i][1]);
+            acc[i][2] = __fmaf_rn(qv, rv.z, acc[i][2]);
+            acc[i][3] = __fmaf_rn(qv, rv.w, acc[i][3]);
+          }
+        }
+      } else {
+        for (int kc = 0; kc < kcn; kc++) {
+          const float4 rv = *reinterpret_cast<const float4*>(&rs[kc * FK_TR + lane * 4]);
+#pragma unroll
+          for (int i = 0; i < QPT; i++) {
+            const float qv = qs[kc * TQ + warp * QPT + i];
+            acc[i][0] = __fmaf_rn(qv, rv.x, acc[i][0]);
+            acc[i][1] = __fmaf_rn(qv, rv.y, acc[i][1]);
+            acc[i][2] = __fmaf_rn(qv, rv.z, acc[i][2]);
+            acc[i][3] = __fmaf_rn(qv, rv.w, acc[i][3]);
+          }
+        }
+      }
+    }
+    // dist = ((-2 * dot) + |q|^2) + |r|^2 ; padding columns at +inf
+    float pn[4];
+#pragma unroll
+    for (int j = 0; j < 4; j++) {
+      const int r = r0 + lane * 4 + j;
+      pn[j] = r < N ? __ldg(a.pp + (size_t)b * N + r) : INF;
+    }
+#pragma unroll
+    for (int i = 0; i < QPT; i++) {
+      float4 o;
+      o.x = __fadd_rn(__fadd_rn(__fmul_rn(-2.0f, acc[i][0]), qn[i]), pn[0]);
+      o.y = __fadd_rn(__fadd_rn(__fmul_rn(-2.0f, acc[i][1]), qn[i]), pn[1]);
+      o.z = __fadd_rn(__fadd_rn(__fmul_rn(-2.0f, acc[i][2]), qn[i]), pn[2]);
+      o.w = __fadd_rn(__fadd_rn(__fmul_rn(-2.0f, acc[i][3]), qn[i]), pn[3]);
+      if (r0 + lane * 4 + 0 >= N) o.x = INF;
+      if (r0 + lane * 4 + 1 >= N) o.y = INF;
+      if (r0 + lane * 4 + 2 >= N) o.z = INF;
+      if (r0 + lane * 4 + 3 >= N) o.w = INF;
+      *reinterpret_cast<float4*>(&dist[(size_t)(warp * QPT + i) * npad + r0 + lane * 4]) = o;
+    }
+  }
+  __syncwarp();  // each warp selects from the rows it wrote itself
+
+  // ---- per-row selection of the k smallest (one warp per row, rows live in shared memory) ----------
+  const int k = a.k;
+  const int nsteps = npad / 32;
+#pragma unroll 1
+  for (int i = 0; i < QPT; i++) {
+    const int q = q0 + warp * QPT + i;
+    if (q >= S) break;  // warp-uniform
+    const float* row = dist + (size_t)(warp * QPT + i) * npad;
+    float lmin = INF;
+    for (int u = 0; u < nsteps; u++) lmin = fminf(lmin, row[u * 32 + lane]);
+    const float T = __shfl_sync(0xffffffffu, fk_sort_values(lmin, lane), k - 1);
+    int cnt = 0;
+    for (int u = 0; u < nsteps; u++) {
+      const float dj = row[u * 32 + lane];
+      const bool pass = dj <= T;
+      const unsigned mask = __ballot_sync(0xffffffffu, pass);
+      if (mask) {
+        const int pos = cnt + __popc(mask & ((1u << lane) - 1u));
+        if (pass && pos < 32) { bufd[warp][pos] = dj; bufi[warp][pos] = u * 32 + lane; }
+        cnt += __popc(mask);
+      }
+    }
+    __syncwarp();
+    float d = INF;
+    int ci = 0x7fffffff;
+    if (cnt <= 32) {
+      if (lane < cnt) { d = bufd[warp][lane]; ci = bufi[warp][lane]; }
+      warp_sort_pairs(d, ci, lane);
+    } else {
+      // many equal distances: streaming insertion into a sorted warp list, candidates in index order
+      float thr = INF;
+      for (int j0 = 0; j0 < N; j0 += 32) {
+        const float dj = (j0 + lane < N) ? row[j0 + lane] : INF;
+        unsigned mask = __ballot_sync(0xffffffffu, dj < thr);
+        while (mask) {
+          const int src = __ffs(mask) - 1;
+          mask &= mask - 1;
+          const float cd = __shfl_sync(0xffffffffu, dj, src);
+          const bool ok = cd < thr;
+          const float ud = __shfl_up_sync(0xffffffffu, d, 1);
+          const int ui = __shfl_up_sync(0xffffffffu, ci, 1);
+          const bool shift = ok && (lane > 0) && (ud > cd);
+          const bool ins = ok && (d > cd);
+          d = shift ? ud : (ins ? cd : d);
+          ci = shift ? ui : (ins ? j0 + src : ci);
+          thr = __shfl_sync(0xffffffffu, d, k - 1);
+        }
+      }
+    }
+    if (a.order == PS_ORDER_TOPK) warp_torch_topk_order(d, ci, lane, k);
+    if (lane < k) a.idx[((size_t)b * S + q) * k + lane] = ci;
+    __syncwarp();
+  }
+}
+
+static int pow2floor(long long v) { int p = 1; while ((long long)p * 2 <= v) p *= 2; return p; }
+
+// block width of ATen's reduce kernel for `rows` outputs of `d0` (vector) elements each
+// (ReduceConfig::set_block_dimension, Reduce.cuh:100-108, max_num_threads = 512 for float)
+static int torch_reduce_block_width(long long d0, long long rows) {
+  const int maxt = 512;
+  const int d0p = d0 < maxt ? pow2floor(d0) : maxt;
+  const int d1p = rows < maxt ? pow2floor(rows) : maxt;
+  int bw = d0p < 32 ? d0p : 32;
+  const int bh = d1p < maxt / bw ? d1p : maxt / bw;
+  bw = d0p < maxt / bh ? d0p : maxt / bh;
+  return bw;
+}
+
+static int rowsumsq_launch(const float* x, float* out, int B, int C, int N, long long sb, long long sn, long long sc,
+                           cudaStream_t stream, const char* who) {
+  const long long rows = (long long)B * N;
+  const int vec = (C >= 128) ? 1 : 0;  // "vectorize along input": dim0 >= 128 (Reduce.cuh:1099)
+  if (vec && (C & 3))
+    return set_error(PS_ERR_UNSUPPORTED, "%s: C=%d >= 128 must be a multiple of 4 (torch's vectorised row sum handles "
+                     "ragged rows with a head/tail split that is not reproduced)", who, C);
+  const int bw = torch_reduce_block_width(vec ? C / 4 : C, rows);
+  if (bw > 32)
+    return set_error(PS_ERR_UNSUPPORTED, "%s: fewer than 16 rows with C=%d: torch reduces such rows across warps, "
+                     "not reproduced", who, C);
+  rowsumsq_torch_kernel<<<ceil_div(rows, FK_WARPS), FK_THREADS, 0, stream>>>(x, out, C, N, sb, sn, sc, vec, bw, rows);
+  PS_LAUNCH_CHECK();
+  return PS_OK;
+}
+
+}  // namespace
+}  // namespace ps
+
+using namespace ps;
+
+// x layout flags: channel_major != 0 -> (B,C,N) (EdgeConv's tensors), else (B,N,C) (what query_knn_point receives)
+extern "C" int ps_knn_feat(const float* xr, const float* xq, int* idx, int B, int C, int N, int S, int k,
+                           int channel_major, int order, int dev, void* stream_) {
+  PS_REQUIRE(B >= 0 && C > 0 && N > 0 && S >= 0 && k > 0, "ps_knn_feat: bad sizes B=%d C=%d N=%d S=%d k=%d", B, C, N, S, k);
+  PS_REQUIRE(k <= N, "ps_knn_feat: k=%d exceeds the number of points N=%d", k, N);
+  PS_REQUIRE(order == PS_ORDER_SORT || order == PS_ORDER_TOPK, "ps_knn_feat: unknown result order %d", order);
+  if (k > 32) return set_error(PS_ERR_UNSUPPORTED, "ps_knn_feat: k=%d > 32 not supported", k);
+  if (B == 0 || S == 0) return PS_OK;
+  PS_REQUIRE(xr && xq && idx, "ps_knn_feat: null pointer");
+  PS_REQUIRE(B <= 65535, "ps_knn_feat: B=%d exceeds the grid y limit", B);
+  DeviceGuard guard(dev);
+  if (!guard.ok) return set_error(PS_ERR_CUDA, "ps_knn_feat: cannot select device %d", dev);
+  cudaStream_t stream = (cudaStream_t)stream_;
+  const int npad = (N + FK_TR - 1) / FK_TR * FK_TR;
+  int TQ = 0;
+  const size_t tile_bytes = (size_t)FK_KC * FK_TR * 4;
+  for (int t : {32, 16, 8})
+    if (!TQ && (size_t)t * npad * 4 + (size_t)FK_KC * t * 4 + tile_bytes <= 200 * 1024) TQ = t;
+  if (!TQ) return set_error(PS_ERR_UNSUPPORTED, "ps_knn_feat: N=%d reference points exceed the shared-memory distance block (max 6144)", N);
+  // a finer query tile when the grid would not fill the GPU
+  const int nsm = sm_count(dev);
+  while (TQ > 8 && (long long)B * ceil_div(S, TQ) < 2ll * nsm) TQ /= 2;
+
+  const bool self = (xq == xr) && (S == N);
+  float* norms = nullptr;
+  const size_t nn = (size_t)B * N + (self ? 0 : (size_t)B * S);
+  if (int rc = scratch_alloc((void**)&norms, nn * sizeof(float), dev, stream)) return rc;
+  FkArgs a;
+  a.xq = xq; a.xr = xr; a.idx = idx; a.C = C; a.N = N; a.S = S; a.k = k; a.order = order; a.npad = npad;
+  if (channel_major) { a.sbr = (long long)C * N; a.snr = 1; a.scr = N; a.sbq = (long long)C * S; a.snq = 1; a.scq = S; }
+  else { a.sbr = (long long)N * C; a.snr = C; a.scr = 1; a.sbq = (long long)S * C; a.snq = C; a.scq = 1; }
+  a.pp = norms;
+  a.qq = self ? norms : norms + (size_t)B * N;
+  if (int rc = rowsumsq_launch(xr, norms, B, C, N, a.sbr, a.snr, a.scr, stream, "ps_knn_feat")) { cudaFreeAsync(norms, stream); return rc; }
+  if (!self)
+    if (int rc = rowsumsq_launch(xq, norms + (size_t)B * N, B, C, S, a.sbq, a.snq, a.scq, stream, "ps_knn_feat")) { cudaFreeAsync(norms, stream); return rc; }
+  const dim3 grid(ceil_div(S, TQ), B);
+#define PS_FK(TQV)                                                                                  \
+  {                                                                                                 \
+    const size_t smem = (size_t)TQV * npad * 4 + (size_t)FK_KC * TQV * 4 + tile_bytes;              \
+    auto kern = knn_feat_kernel<TQV>;                                                               \
+    PS_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));    \
+    kern<<<grid, FK_THREADS, smem, stream>>>(a);                                                    \
+  }
+  if (TQ == 32) PS_FK(32) else if (TQ == 16) PS_FK(16) else PS_FK(8)
+#undef PS_FK
+  PS_LAUNCH_CHECK();
+  PS_CUDA(cudaFreeAsync(norms, stream));
+  return PS_OK;
+}

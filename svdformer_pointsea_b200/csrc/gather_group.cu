@@ -169,7 +169,7 @@ __global__ void __launch_bounds__(GG_THREADS) gather_direct_kernel(
 template <int CT>
 __global__ void __launch_bounds__(GG_THREADS) scatter_staged_kernel(
     const float* __restrict__ gout, const int* __restrict__ idx, float* __restrict__ gfeat, int C,
-    int N, int Mp, int vec_ok) {
+    int N, int Mp, int vec_ok, size_t gbs) {
   extern __shared__ __align__(16) float acc[];
   const int b = blockIdx.z, c0 = blockIdx.y * CT, tid = threadIdx.x;
   const int nrows = min(CT, C - c0);
@@ -187,7 +187,7 @@ __global__ void __launch_bounds__(GG_THREADS) scatter_staged_kernel(
 #pragma unroll
       for (int e = 0; e < 4; e++) ii[e] = p + e < Mp ? __ldg(ib + p + e) : -1;
     }
-    const float* gb = gout + ((size_t)b * C + c0) * Mp + p;
+    const float* gb = gout + (size_t)b * gbs + (size_t)c0 * Mp + p;
 #pragma unroll
     for (int r = 0; r < CT; r++) {
       if (r < nrows) {
@@ -213,12 +213,12 @@ __global__ void __launch_bounds__(GG_THREADS) scatter_staged_kernel(
 // ---- backward, global atomics (rows too long for shared memory; gfeat pre-zeroed by us) --------
 __global__ void __launch_bounds__(GG_THREADS) scatter_direct_kernel(
     const float* __restrict__ gout, const int* __restrict__ idx, float* __restrict__ gfeat, int C,
-    int N, int Mp) {
+    int N, int Mp, size_t gbs) {
   const int b = blockIdx.z, c = blockIdx.y;
   const int p = blockIdx.x * GG_THREADS + threadIdx.x;
   if (p >= Mp) return;
   const int i = __ldg(idx + (size_t)b * Mp + p);
-  atomicAdd(gfeat + ((size_t)b * C + c) * N + i, __ldg(gout + ((size_t)b * C + c) * Mp + p));
+  atomicAdd(gfeat + ((size_t)b * C + c) * N + i, __ldg(gout + (size_t)b * gbs + (size_t)c * Mp + p));
 }
 
 // ---- backward through an inverse index (dense grouping: every source point appears many times) ---
@@ -297,7 +297,8 @@ __global__ void __launch_bounds__(CSR_BUILD_THREADS) csr_build_kernel(const int*
 template <int NPT, int PF, int CSR_CPB>
 __global__ void __launch_bounds__(CSR_THREADS, 1) scatter_csr_kernel(const float* __restrict__ gout, const int* __restrict__ bnd_all,
                                                                      const unsigned short* __restrict__ list_all,
-                                                                     float* __restrict__ gfeat, int C, int N, int Mp, int nchunks) {
+                                                                     float* __restrict__ gfeat, int C, int N, int Mp, int nchunks,
+                                                                     size_t gbs) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
   u64* bars = reinterpret_cast<u64*>(smem_raw);          // full[2]
   float* stage0 = reinterpret_cast<float*>(smem_raw + 128);
@@ -318,7 +319,7 @@ __global__ void __launch_bounds__(CSR_THREADS, 1) scatter_csr_kernel(const float
     const int p0 = k * CSR_CHUNK, len = min(CSR_CHUNK, Mp - p0);
     const unsigned bar = smem_u32(&bars[item & 1]);
     mbar_arrive_expect_tx(bar, (unsigned)len * 4u);
-    bulk_g2s(smem_u32((item & 1) ? stage1 : stage0), gout + ((size_t)b * C + c) * Mp + p0, (unsigned)len * 4u, bar);
+    bulk_g2s(smem_u32((item & 1) ? stage1 : stage0), gout + (size_t)b * gbs + (size_t)c * Mp + p0, (unsigned)len * 4u, bar);
   };
   if (tid == 0) { issue(0); if (items > 1) issue(1); }
   float acc[NPT][CSR_CPB];
@@ -435,8 +436,11 @@ static int gather_fwd_impl(const float* feat, const int* idx, float* out, int B,
   return PS_OK;
 }
 
+// gbs = batch stride of gout in elements (C*Mp for a dense (B,C,Mp) tensor; 2*C*Mp when gout is the first
+// half of an EdgeConv feature gradient)
 static int gather_bwd_impl(const float* gout, const int* idx, float* gfeat, int B, int C, int N,
-                           int Mp, int dev, cudaStream_t stream, const char* who) {
+                           int Mp, int dev, cudaStream_t stream, const char* who, size_t gbs = 0) {
+  if (gbs == 0) gbs = (size_t)C * Mp;
   PS_REQUIRE(B >= 0 && C >= 0 && N > 0 && Mp >= 0, "%s: bad sizes B=%d C=%d N=%d M=%d", who, B, C, N, Mp);
   if (B == 0 || C == 0) return PS_OK;
   PS_REQUIRE(gfeat && (Mp == 0 || (gout && idx)), "%s: null pointer", who);
@@ -474,7 +478,7 @@ static int gather_bwd_impl(const float* gout, const int* idx, float* gfeat, int 
   {                                                                                                \
     auto kern = scatter_csr_kernel<NPTV, PFV, CPBV>;                                               \
     PS_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));   \
-    kern<<<dim3(ceil_div(C, CPBV), B), CSR_THREADS, smem, stream>>>(gout, bnd, list, gfeat, C, N, Mp, nchunks); \
+    kern<<<dim3(ceil_div(C, CPBV), B), CSR_THREADS, smem, stream>>>(gout, bnd, list, gfeat, C, N, Mp, nchunks, gbs); \
   }
     if (npt <= 1) PS_CSR(1, 12, 8) else if (npt <= 2) PS_CSR(2, 12, 8) else if (npt <= 4) PS_CSR(4, 8, 4) else PS_CSR(8, 4, 2)
 #undef PS_CSR
@@ -494,19 +498,163 @@ static int gather_bwd_impl(const float* gout, const int* idx, float* gfeat, int 
   {                                                                                              \
     auto kern = scatter_staged_kernel<CTV>;                                                      \
     PS_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
-    kern<<<grid, GG_THREADS, smem, stream>>>(gout, idx, gfeat, C, N, Mp, vec_ok);                        \
+    kern<<<grid, GG_THREADS, smem, stream>>>(gout, idx, gfeat, C, N, Mp, vec_ok, gbs);                   \
   }
     if (ct == 8) PS_SCATTER(8) else if (ct == 4) PS_SCATTER(4) else if (ct == 2) PS_SCATTER(2) else PS_SCATTER(1)
 #undef PS_SCATTER
     PS_LAUNCH_CHECK();
   } else {
     PS_CUDA(cudaMemsetAsync(gfeat, 0, (size_t)B * C * row_bytes, stream));
-    scatter_direct_kernel<<<dim3(ceil_div(Mp, GG_THREADS), C, B), GG_THREADS, 0, stream>>>(gout, idx, gfeat, C, N, Mp);
+    scatter_direct_kernel<<<dim3(ceil_div(Mp, GG_THREADS), C, B), GG_THREADS, 0, stream>>>(gout, idx, gfeat, C, N, Mp, gbs);
     PS_LAUNCH_CHECK();
   }
   return PS_OK;
 }
 
+// ---- EdgeConv front: cat(central - neighbour, central) -------------------------------------------
+// Replaces group_local + the tensor algebra at the top of EdgeConv.forward (models/model_utils.py:812-826,
+// 869-877: query_knn_point -> index_points -> permute -> .contiguous() -> unsqueeze/repeat -> subtract -> cat,
+// six full passes over (B,C,N,K)-sized tensors) by one pass:
+//   out[b, c,     n, k] = x[b,c,n] - x[b,c,idx[b,n,k]]
+//   out[b, C + c, n, k] = x[b,c,n]                              x (B,C,N), idx (B,N,K), out (B,2C,N,K)
+// Same CTA layout as gather_staged_kernel (rows staged by cp.async.bulk, 128-bit index loads and streaming
+// stores).  Algorithmic HBM bytes: 4*(B*N*K + B*C*N + 2*B*C*N*K).
+template <int CT>
+__global__ void __launch_bounds__(GG_THREADS) edge_staged_kernel(
+    const float* __restrict__ feat, const int* __restrict__ idx, float* __restrict__ out, int C,
+    int N, int K, int Mp, int slice_len, int use_bulk, int vec_ok) {
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  u64* bar = reinterpret_cast<u64*>(smem_raw);
+  float* rows = reinterpret_cast<float*>(smem_raw + 128);
+  const int b = blockIdx.z, c0 = blockIdx.y * CT, tid = threadIdx.x;
+  const int nrows = min(CT, C - c0);
+  const float* src = feat + ((size_t)b * C + c0) * N;
+  if (use_bulk) {
+    if (tid == 0) {
+      mbar_init(smem_u32(bar), 1);
+      asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+    if (tid == 0) {
+      mbar_arrive_expect_tx(smem_u32(bar), (unsigned)(nrows * N * 4));
+      for (int r = 0; r < nrows; r++)
+        bulk_g2s(smem_u32(rows + (size_t)r * N), src + (size_t)r * N, (unsigned)(N * 4), smem_u32(bar));
+    }
+  } else {
+    for (int i = tid; i < nrows * N; i += GG_THREADS) rows[i] = __ldg(src + i);
+  }
+  const int p_begin = blockIdx.x * slice_len;
+  const int p_end = min(Mp, p_begin + slice_len);
+  const int* ib = idx + (size_t)b * Mp;
+  const bool vec = vec_ok != 0;  // K % 4 == 0 (so 4 consecutive positions share their centre) and aligned bases
+  if (use_bulk) {
+    while (!mbar_try_wait(smem_u32(bar), 0)) {}
+  } else {
+    __syncthreads();
+  }
+  for (int p = p_begin + tid * 4; p < p_end; p += GG_THREADS * 4) {
+    int ii[4], nn[4];
+    const bool full = vec && (p + 4 <= p_end);
+    if (full) {
+      const int4 v = __ldg(reinterpret_cast<const int4*>(ib + p));
+      ii[0] = v.x; ii[1] = v.y; ii[2] = v.z; ii[3] = v.w;
+      nn[0] = nn[1] = nn[2] = nn[3] = p / K;
+    } else {
+#pragma unroll
+      for (int e = 0; e < 4; e++) {
+        ii[e] = p + e < p_end ? __ldg(ib + p + e) : 0;
+        nn[e] = p + e < p_end ? (p + e) / K : 0;
+      }
+    }
+    float* oe = out + ((size_t)b * 2 * C + c0) * Mp + p;       // edge half
+    float* oc = out + ((size_t)b * 2 * C + C + c0) * Mp + p;   // central half
+#pragma unroll
+    for (int r = 0; r < CT; r++) {
+      if (r < nrows) {
+        const float* row = rows + (size_t)r * N;
+        const float4 cen = make_float4(row[nn[0]], row[nn[1]], row[nn[2]], row[nn[3]]);
+        const float4 edg = make_float4(__fsub_rn(cen.x, row[ii[0]]), __fsub_rn(cen.y, row[ii[1]]),
+                                       __fsub_rn(cen.z, row[ii[2]]), __fsub_rn(cen.w, row[ii[3]]));
+        float* e_ = oe + (size_t)r * Mp;
+        float* c_ = oc + (size_t)r * Mp;
+        if (full) {
+          __stcs(reinterpret_cast<float4*>(e_), edg);
+          __stcs(reinterpret_cast<float4*>(c_), cen);
+        } else {
+          const float ev[4] = {edg.x, edg.y, edg.z, edg.w}, cv[4] = {cen.x, cen.y, cen.z, cen.w};
+#pragma unroll
+          for (int e = 0; e < 4; e++)
+            if (p + e < p_end) { e_[e] = ev[e]; c_[e] = cv[e]; }
+        }
+      }
+    }
+  }
+}
+
+// rows too long for shared memory: straight from L1/L2
+__global__ void __launch_bounds__(GG_THREADS) edge_direct_kernel(const float* __restrict__ feat, const int* __restrict__ idx,
+                                                                 float* __restrict__ out, int C, int N, int K, int Mp) {
+  const int b = blockIdx.z, c = blockIdx.y;
+  const int p = blockIdx.x * GG_THREADS + threadIdx.x;
+  if (p >= Mp) return;
+  const float* row = feat + ((size_t)b * C + c) * N;
+  const float cen = __ldg(row + p / K);
+  const float nb = __ldg(row + __ldg(idx + (size_t)b * Mp + p));
+  out[((size_t)b * 2 * C + c) * Mp + p] = __fsub_rn(cen, nb);
+  out[((size_t)b * 2 * C + C + c) * Mp + p] = cen;
+}
+
+// backward finish: gx[b,c,n] = sum_k (gE[b,c,n,k] + gC[b,c,n,k]) - gx[b,c,n]   (gx holds the scattered gE on entry)
+__global__ void __launch_bounds__(GG_THREADS) edge_bwd_finish_kernel(const float* __restrict__ gout, float* __restrict__ gx,
+                                                                     int C, int N, int K, long long total) {
+  const long long t = (long long)blockIdx.x * GG_THREADS + threadIdx.x;
+  if (t >= total) return;
+  const int n = (int)(t % N);
+  const int c = (int)((t / N) % C);
+  const int b = (int)(t / ((long long)N * C));
+  const float* ge = gout + (((size_t)b * 2 * C + c) * N + n) * K;
+  const float* gc = gout + (((size_t)b * 2 * C + C + c) * N + n) * K;
+  float s = 0.f;
+  for (int k = 0; k < K; k++) s += __ldg(ge + k) + __ldg(gc + k);
+  gx[t] = s - gx[t];
+}
+
+// ---- index_points: row gather on point-major tensors (models/model_utils.py:828-845) -----------------
+//   out[b,m,:] = points[b, idx[b,m], :]      points (B,N,C), idx (B,M) (any trailing shape flattened), out (B,M,C)
+template <int VEC>
+__global__ void __launch_bounds__(GG_THREADS) index_points_kernel(const float* __restrict__ pts, const int* __restrict__ idx,
+                                                                  float* __restrict__ out, int N, int M, int C, long long total) {
+  const long long t = (long long)blockIdx.x * GG_THREADS + threadIdx.x;  // one thread per VEC output elements
+  if (t >= total) return;
+  const int cv = C / VEC;
+  const int c = (int)(t % cv) * VEC;
+  const long long row = t / cv;  // b*M + m
+  const int b = (int)(row / M);
+  const int i = __ldg(idx + row);
+  const float* s = pts + ((size_t)b * N + i) * C + c;
+  float* o = out + (size_t)row * C + c;
+  if (VEC == 4) __stcs(reinterpret_cast<float4*>(o), __ldg(reinterpret_cast<const float4*>(s)));
+  else *o = __ldg(s);
+}
+template <int VEC>
+__global__ void __launch_bounds__(GG_THREADS) index_points_grad_kernel(const float* __restrict__ gout, const int* __restrict__ idx,
+                                                                       float* __restrict__ gpts, int N, int M, int C, long long total) {
+  const long long t = (long long)blockIdx.x * GG_THREADS + threadIdx.x;
+  if (t >= total) return;
+  const int cv = C / VEC;
+  const int c = (int)(t % cv) * VEC;
+  const long long row = t / cv;
+  const int b = (int)(row / M);
+  const int i = __ldg(idx + row);
+  float* d = gpts + ((size_t)b * N + i) * C + c;
+  const float* g = gout + (size_t)row * C + c;
+  if (VEC == 4) {
+    const float4 v = __ldcs(reinterpret_cast<const float4*>(g));
+    atomicAdd(reinterpret_cast<float4*>(d), v);  // red.global.add.v4.f32 (sm_90+)
+  } else {
+    atomicAdd(d, __ldg(g));
+  }
+}
 }  // namespace ps
 
 using namespace ps;
@@ -528,4 +676,93 @@ extern "C" int ps_group_bwd(const float* grad_out, const int* idx, float* grad_f
                             int C, int N, int S, int K, int dev, void* stream) {
   PS_REQUIRE(S >= 0 && K >= 0 && (long long)S * K < (1ll << 31), "ps_group_bwd: bad S=%d K=%d", S, K);
   return gather_bwd_impl(grad_out, idx, grad_features, B, C, N, S * K, dev, (cudaStream_t)stream, "ps_group_bwd");
+}
+
+extern "C" int ps_edge_features_fwd(const float* x, const int* idx, float* out, int B, int C, int N, int K,
+                                    int dev, void* stream_) {
+  PS_REQUIRE(B >= 0 && C >= 0 && N > 0 && K >= 0 && (long long)N * K < (1ll << 31), "ps_edge_features_fwd: bad sizes B=%d C=%d N=%d K=%d", B, C, N, K);
+  if (B == 0 || C == 0 || K == 0) return PS_OK;
+  PS_REQUIRE(x && idx && out, "ps_edge_features_fwd: null pointer");
+  PS_REQUIRE(B <= 65535 && C <= 65535, "ps_edge_features_fwd: B or C exceeds the grid limit");
+  DeviceGuard guard(dev);
+  if (!guard.ok) return set_error(PS_ERR_CUDA, "ps_edge_features_fwd: cannot select device %d", dev);
+  cudaStream_t stream = (cudaStream_t)stream_;
+  const int nsm = sm_count(dev);
+  const int Mp = N * K;
+  const size_t row_bytes = (size_t)N * 4;
+  constexpr int CT = 8;
+  if (row_bytes * CT + 128 <= GG_SMEM_MAX / 2) {
+    const int vec_ok = ((K & 3) == 0) && ((reinterpret_cast<uintptr_t>(idx) & 15) == 0) && ((reinterpret_cast<uintptr_t>(out) & 15) == 0);
+    const int ctiles = ceil_div(C, CT);
+    int nslice = ceil_div((long long)nsm * 16, (long long)B * ctiles);
+    const int min_len = 2 * N > 2048 ? 2 * N : 2048;
+    const int max_slice = Mp / min_len > 0 ? Mp / min_len : 1;
+    if (nslice > max_slice) nslice = max_slice;
+    if (nslice < 1) nslice = 1;
+    int slice_len = ceil_div(Mp, nslice);
+    slice_len = (slice_len + 1023) / 1024 * 1024;
+    nslice = ceil_div(Mp, slice_len);
+    const int use_bulk = ((N & 3) == 0) && ((reinterpret_cast<uintptr_t>(x) & 15) == 0);
+    const size_t smem = 128 + row_bytes * CT;
+    auto kern = edge_staged_kernel<CT>;
+    PS_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    kern<<<dim3(nslice, ctiles, B), GG_THREADS, smem, stream>>>(x, idx, out, C, N, K, Mp, slice_len, use_bulk, vec_ok);
+  } else {
+    edge_direct_kernel<<<dim3(ceil_div(Mp, GG_THREADS), C, B), GG_THREADS, 0, stream>>>(x, idx, out, C, N, K, Mp);
+  }
+  PS_LAUNCH_CHECK();
+  return PS_OK;
+}
+
+extern "C" int ps_edge_features_bwd(const float* grad_out, const int* idx, float* grad_x, int B, int C, int N,
+                                    int K, int dev, void* stream_) {
+  PS_REQUIRE(B >= 0 && C >= 0 && N > 0 && K >= 0 && (long long)N * K < (1ll << 31), "ps_edge_features_bwd: bad sizes B=%d C=%d N=%d K=%d", B, C, N, K);
+  if (B == 0 || C == 0) return PS_OK;
+  cudaStream_t stream = (cudaStream_t)stream_;
+  // 1. scatter of the edge half through the grouping backward (grad_out batch stride = 2*C*N*K)
+  if (int rc = gather_bwd_impl(grad_out, idx, grad_x, B, C, N, N * K, dev, stream, "ps_edge_features_bwd", (size_t)2 * C * N * K)) return rc;
+  if (K == 0) return PS_OK;
+  DeviceGuard guard(dev);
+  if (!guard.ok) return set_error(PS_ERR_CUDA, "ps_edge_features_bwd: cannot select device %d", dev);
+  // 2. centre terms minus the scatter
+  const long long total = (long long)B * C * N;
+  edge_bwd_finish_kernel<<<ceil_div(total, GG_THREADS), GG_THREADS, 0, stream>>>(grad_out, grad_x, C, N, K, total);
+  PS_LAUNCH_CHECK();
+  return PS_OK;
+}
+
+extern "C" int ps_index_points_fwd(const float* points, const int* idx, float* out, int B, int N, int M, int C,
+                                   int dev, void* stream_) {
+  PS_REQUIRE(B >= 0 && N > 0 && M >= 0 && C >= 0, "ps_index_points_fwd: bad sizes B=%d N=%d M=%d C=%d", B, N, M, C);
+  if (B == 0 || M == 0 || C == 0) return PS_OK;
+  PS_REQUIRE(points && idx && out, "ps_index_points_fwd: null pointer");
+  DeviceGuard guard(dev);
+  if (!guard.ok) return set_error(PS_ERR_CUDA, "ps_index_points_fwd: cannot select device %d", dev);
+  cudaStream_t stream = (cudaStream_t)stream_;
+  const bool v4 = ((C & 3) == 0) && ((reinterpret_cast<uintptr_t>(points) & 15) == 0) && ((reinterpret_cast<uintptr_t>(out) & 15) == 0);
+  const long long total = (long long)B * M * (v4 ? C / 4 : C);
+  PS_REQUIRE(total / GG_THREADS < (1ll << 31) - 1, "ps_index_points_fwd: tensor too large");
+  if (v4) index_points_kernel<4><<<ceil_div(total, GG_THREADS), GG_THREADS, 0, stream>>>(points, idx, out, N, M, C, total);
+  else index_points_kernel<1><<<ceil_div(total, GG_THREADS), GG_THREADS, 0, stream>>>(points, idx, out, N, M, C, total);
+  PS_LAUNCH_CHECK();
+  return PS_OK;
+}
+
+extern "C" int ps_index_points_bwd(const float* grad_out, const int* idx, float* grad_points, int B, int N, int M,
+                                   int C, int dev, void* stream_) {
+  PS_REQUIRE(B >= 0 && N > 0 && M >= 0 && C >= 0, "ps_index_points_bwd: bad sizes B=%d N=%d M=%d C=%d", B, N, M, C);
+  if (B == 0 || C == 0) return PS_OK;
+  PS_REQUIRE(grad_points && (M == 0 || (grad_out && idx)), "ps_index_points_bwd: null pointer");
+  DeviceGuard guard(dev);
+  if (!guard.ok) return set_error(PS_ERR_CUDA, "ps_index_points_bwd: cannot select device %d", dev);
+  cudaStream_t stream = (cudaStream_t)stream_;
+  PS_CUDA(cudaMemsetAsync(grad_points, 0, (size_t)B * N * C * sizeof(float), stream));
+  if (M == 0) return PS_OK;
+  const bool v4 = ((C & 3) == 0) && ((reinterpret_cast<uintptr_t>(grad_points) & 15) == 0) && ((reinterpret_cast<uintptr_t>(grad_out) & 15) == 0);
+  const long long total = (long long)B * M * (v4 ? C / 4 : C);
+  PS_REQUIRE(total / GG_THREADS < (1ll << 31) - 1, "ps_index_points_bwd: tensor too large");
+  if (v4) index_points_grad_kernel<4><<<ceil_div(total, GG_THREADS), GG_THREADS, 0, stream>>>(grad_out, idx, grad_points, N, M, C, total);
+  else index_points_grad_kernel<1><<<ceil_div(total, GG_THREADS), GG_THREADS, 0, stream>>>(grad_out, idx, grad_points, N, M, C, total);
+  PS_LAUNCH_CHECK();
+  return PS_OK;
 }

@@ -17,6 +17,7 @@
 //      insertion over the same shared-memory tile.
 // ~1100 warp instructions per query instead of ~2700 for the streaming insertion.
 #include "common.cuh"
+#include "select.cuh"
 
 namespace ps {
 namespace {
@@ -38,21 +39,6 @@ __device__ __forceinline__ float ks_dist(float qx, float qy, float qz, float qq,
   return __fadd_rn(__fadd_rn(__fmul_rn(-2.0f, dot), qq), c.w);
 }
 
-__device__ __forceinline__ void ks_sort_pairs(float& d, int& i, int lane) {
-#pragma unroll
-  for (int k = 2; k <= 32; k <<= 1) {
-#pragma unroll
-    for (int j = k >> 1; j > 0; j >>= 1) {
-      const float od = __shfl_xor_sync(0xffffffffu, d, j);
-      const int oi = __shfl_xor_sync(0xffffffffu, i, j);
-      const bool up = ((lane & k) == 0);
-      const bool lower = ((lane & j) == 0);
-      const bool other_less = (od < d) || (od == d && oi < i);
-      const bool take = (lower == up) ? other_less : !other_less;
-      if (take) { d = od; i = oi; }
-    }
-  }
-}
 // values only, ascending (NaN never reaches here: lane minima come from fminf)
 __device__ __forceinline__ float ks_sort_values(float v, int lane) {
 #pragma unroll
@@ -69,11 +55,13 @@ __device__ __forceinline__ float ks_sort_values(float v, int lane) {
 
 // QW queries per warp share every candidate load: the kernel is bound by shared-memory bandwidth
 // otherwise (each query streams the 32 KB tile twice; measured 0.20 ms at C3 with QW = 1).
-template <int VAR, int QW>
+// EPI = 0: plain (dist, index) order, indices only (the C3 kernel, 48 registers); EPI = 1: result order and
+// fused coordinate grouping selected at run time
+template <int VAR, int QW, int EPI>
 __global__ void __launch_bounds__(KS_THREADS) knn_select_kernel(const float* __restrict__ xyz,
                                                                 const float* __restrict__ new_xyz,
-                                                                int* __restrict__ idx, int N, int S, int k,
-                                                                int skip, int qpc) {
+                                                                int* __restrict__ idx, float* __restrict__ gxyz,
+                                                                int N, int S, int k, int skip, int qpc, int order) {
   __shared__ float4 sp[KS_TILE];
   __shared__ float bufd[KS_WARPS][QW][32];
   __shared__ int bufi[KS_WARPS][QW][32];
@@ -141,7 +129,7 @@ __global__ void __launch_bounds__(KS_THREADS) knn_select_kernel(const float* __r
       int ci = 0x7fffffff;
       if (cnt[w] <= 32) {
         if (lane < cnt[w]) { d = bufd[warp][w][lane]; ci = bufi[warp][w][lane]; }
-        ks_sort_pairs(d, ci, lane);
+        warp_sort_pairs(d, ci, lane);
       } else {
         // 4. rare: more than 32 candidates at or below the threshold (many equal distances):
         // streaming insertion into a sorted warp list, candidates in index order
@@ -165,8 +153,20 @@ __global__ void __launch_bounds__(KS_THREADS) knn_select_kernel(const float* __r
           }
         }
       }
+      if (EPI && order == PS_ORDER_TOPK) warp_torch_topk_order(d, ci, lane, KK);
       const int s = s0 + w;
-      if (s < s_end && lane >= skip && lane < KK) idx[((size_t)b * S + s) * k + (lane - skip)] = ci;
+      if (s < s_end && lane >= skip && lane < KK) {
+        idx[((size_t)b * S + s) * k + (lane - skip)] = ci;
+        if (EPI && gxyz) {
+          // fused grouping of the coordinates + centre subtraction (models/model_utils.py:344-345):
+          // grouped_xyz[b,c,s,j] = xyz[b,idx[b,s,j],c] - new_xyz[b,s,c]
+          const float4 c = sp[ci];
+          float* o = gxyz + ((size_t)b * 3 * S + s) * k + (lane - skip);
+          o[0] = __fsub_rn(c.x, qx[w]);
+          o[(size_t)S * k] = __fsub_rn(c.y, qy[w]);
+          o[(size_t)2 * S * k] = __fsub_rn(c.z, qz[w]);
+        }
+      }
     }
     __syncwarp();  // the buffers are reused by this warp's next group of queries
   }
@@ -175,16 +175,19 @@ __global__ void __launch_bounds__(KS_THREADS) knn_select_kernel(const float* __r
 }  // namespace
 
 // PS_OK when handled, 1 when the shape needs the streaming kernel, negative on error.
-int knn_select_launch(const float* xyz, const float* new_xyz, int* idx, int B, int N, int S, int k, int skip,
-                      int var, int nsm, cudaStream_t stream) {
+int knn_select_launch(const float* xyz, const float* new_xyz, int* idx, float* gxyz, int B, int N, int S, int k,
+                      int skip, int order, int var, int nsm, cudaStream_t stream) {
   if (N > KS_TILE || k + skip > 16) return 1;
   int qpc = 64;  // queries per CTA (a multiple of 8 warps x 4 queries while it stays >= 32)
   while (qpc > 32 && (long long)B * ceil_div(S, qpc) < (long long)nsm * 4) qpc /= 2;
   const dim3 grid(ceil_div(S, qpc), B);
   constexpr int QW = 4;
-  if (var == 1) knn_select_kernel<1, QW><<<grid, KS_THREADS, 0, stream>>>(xyz, new_xyz, idx, N, S, k, skip, qpc);
-  else if (var == 2) knn_select_kernel<2, QW><<<grid, KS_THREADS, 0, stream>>>(xyz, new_xyz, idx, N, S, k, skip, qpc);
-  else knn_select_kernel<0, QW><<<grid, KS_THREADS, 0, stream>>>(xyz, new_xyz, idx, N, S, k, skip, qpc);
+#define PS_KS(VARV, EPIV) knn_select_kernel<VARV, QW, EPIV><<<grid, KS_THREADS, 0, stream>>>(xyz, new_xyz, idx, gxyz, N, S, k, skip, qpc, order)
+  const bool epi = gxyz != nullptr || order != PS_ORDER_SORT;
+  if (var == 1) { if (epi) PS_KS(1, 1); else PS_KS(1, 0); }
+  else if (var == 2) { if (epi) PS_KS(2, 1); else PS_KS(2, 0); }
+  else { if (epi) PS_KS(0, 1); else PS_KS(0, 0); }
+#undef PS_KS
   PS_LAUNCH_CHECK();
   return PS_OK;
 }

@@ -12,6 +12,7 @@
 // sorted ascending by (distance, index).  A candidate is inserted only when it beats the current
 // k-th distance (ballot + shuffle-shift), which happens ~k*ln(N/k) times per query.
 #include "common.cuh"
+#include "select.cuh"
 
 namespace ps {
 
@@ -59,8 +60,8 @@ __device__ __forceinline__ void warp_bitonic_sort(float& d, int& i, int lane) {
 template <int R, int VAR>
 __global__ void __launch_bounds__(NB_THREADS) knn_kernel(const float* __restrict__ xyz,
                                                          const float* __restrict__ new_xyz,
-                                                         int* __restrict__ idx, int N, int S, int k,
-                                                         int skip, int qpc) {
+                                                         int* __restrict__ idx, float* __restrict__ gxyz,
+                                                         int N, int S, int k, int skip, int qpc, int order) {
   __shared__ float4 sp[NB_TILE];
   const int b = blockIdx.y, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const float* cloud = xyz + (size_t)b * N * 3;
@@ -176,11 +177,21 @@ __global__ void __launch_bounds__(NB_THREADS) knn_kernel(const float* __restrict
       }
     }
     if (valid) {
+      if (R == 1 && order == PS_ORDER_TOPK) warp_torch_topk_order(ld[0], li[0], lane, KK);
       int* o = idx + ((size_t)b * S + s) * k;
 #pragma unroll
       for (int r = 0; r < R; r++) {
         const int e = r * 32 + lane;
-        if (e >= skip && e < KK) o[e - skip] = li[r];
+        if (e >= skip && e < KK) {
+          o[e - skip] = li[r];
+          if (gxyz) {  // fused coordinate grouping + centre subtraction (models/model_utils.py:344-345)
+            const float* cp = cloud + (size_t)li[r] * 3;
+            float* g = gxyz + ((size_t)b * 3 * S + s) * k + (e - skip);
+            g[0] = __fsub_rn(__ldg(cp + 0), qx);
+            g[(size_t)S * k] = __fsub_rn(__ldg(cp + 1), qy);
+            g[(size_t)2 * S * k] = __fsub_rn(__ldg(cp + 2), qz);
+          }
+        }
       }
     }
   }
@@ -344,26 +355,29 @@ static int knn_variant() {
 
 template <int R>
 static void launch_knn(int var, dim3 grid, cudaStream_t st, const float* xyz, const float* new_xyz,
-                       int* idx, int N, int S, int k, int skip, int qpc) {
-  if (var == 1) knn_kernel<R, 1><<<grid, NB_THREADS, 0, st>>>(xyz, new_xyz, idx, N, S, k, skip, qpc);
-  else if (var == 2) knn_kernel<R, 2><<<grid, NB_THREADS, 0, st>>>(xyz, new_xyz, idx, N, S, k, skip, qpc);
-  else knn_kernel<R, 0><<<grid, NB_THREADS, 0, st>>>(xyz, new_xyz, idx, N, S, k, skip, qpc);
+                       int* idx, float* gxyz, int N, int S, int k, int skip, int qpc, int order) {
+  if (var == 1) knn_kernel<R, 1><<<grid, NB_THREADS, 0, st>>>(xyz, new_xyz, idx, gxyz, N, S, k, skip, qpc, order);
+  else if (var == 2) knn_kernel<R, 2><<<grid, NB_THREADS, 0, st>>>(xyz, new_xyz, idx, gxyz, N, S, k, skip, qpc, order);
+  else knn_kernel<R, 0><<<grid, NB_THREADS, 0, st>>>(xyz, new_xyz, idx, gxyz, N, S, k, skip, qpc, order);
 }
 
 }  // namespace ps
 
 using namespace ps;
 
-extern "C" int ps_knn(const float* xyz, const float* new_xyz, int* idx, int B, int N, int S, int k,
-                      int skip, int dev, void* stream_) {
-  PS_REQUIRE(B >= 0 && N > 0 && S >= 0 && k > 0 && skip >= 0, "ps_knn: bad sizes B=%d N=%d S=%d k=%d skip=%d", B, N, S, k, skip);
-  PS_REQUIRE(k + skip <= N, "ps_knn: k+skip=%d exceeds the number of points N=%d", k + skip, N);
-  if (k + skip > 128) return set_error(PS_ERR_UNSUPPORTED, "ps_knn: k+skip=%d > 128 not supported", k + skip);
+static int knn_impl(const float* xyz, const float* new_xyz, int* idx, float* gxyz, int B, int N, int S, int k,
+                    int skip, int order, int dev, void* stream_, const char* who) {
+  PS_REQUIRE(B >= 0 && N > 0 && S >= 0 && k > 0 && skip >= 0, "%s: bad sizes B=%d N=%d S=%d k=%d skip=%d", who, B, N, S, k, skip);
+  PS_REQUIRE(k + skip <= N, "%s: k+skip=%d exceeds the number of points N=%d", who, k + skip, N);
+  PS_REQUIRE(order == PS_ORDER_SORT || order == PS_ORDER_TOPK, "%s: unknown result order %d", who, order);
+  if (k + skip > 128) return set_error(PS_ERR_UNSUPPORTED, "%s: k+skip=%d > 128 not supported", who, k + skip);
+  if (order == PS_ORDER_TOPK && (k > 32 || skip != 0))
+    return set_error(PS_ERR_UNSUPPORTED, "%s: torch.topk result order is reproduced for k <= 32, skip == 0 (k=%d skip=%d)", who, k, skip);
   if (B == 0 || S == 0) return PS_OK;
-  PS_REQUIRE(xyz && new_xyz && idx, "ps_knn: null pointer");
-  PS_REQUIRE(B <= 65535, "ps_knn: B=%d exceeds the grid y limit", B);
+  PS_REQUIRE(xyz && new_xyz && idx, "%s: null pointer", who);
+  PS_REQUIRE(B <= 65535, "%s: B=%d exceeds the grid y limit", who, B);
   DeviceGuard guard(dev);
-  if (!guard.ok) return set_error(PS_ERR_CUDA, "ps_knn: cannot select device %d", dev);
+  if (!guard.ok) return set_error(PS_ERR_CUDA, "%s: cannot select device %d", who, dev);
   cudaStream_t stream = (cudaStream_t)stream_;
   const int nsm = sm_count(dev);
   // queries per CTA: a multiple of 8 (one per warp per round); enough CTAs for ~4 per SM
@@ -375,15 +389,31 @@ extern "C" int ps_knn(const float* xyz, const float* new_xyz, int* idx, int B, i
   {
     const char* e = getenv("PS_KNN_SELECT");  // PS_KNN_SELECT=0 forces the streaming kernel (A/B, tests)
     if (!(e && atoi(e) == 0)) {
-      const int rc = knn_select_launch(xyz, new_xyz, idx, B, N, S, k, skip, var, nsm, stream);
+      const int rc = knn_select_launch(xyz, new_xyz, idx, gxyz, B, N, S, k, skip, order, var, nsm, stream);
       if (rc <= 0) return rc;
     }
   }
-  if (KK <= 32) launch_knn<1>(var, grid, stream, xyz, new_xyz, idx, N, S, k, skip, qpc);
-  else if (KK <= 64) launch_knn<2>(var, grid, stream, xyz, new_xyz, idx, N, S, k, skip, qpc);
-  else launch_knn<4>(var, grid, stream, xyz, new_xyz, idx, N, S, k, skip, qpc);
+  if (KK <= 32) launch_knn<1>(var, grid, stream, xyz, new_xyz, idx, gxyz, N, S, k, skip, qpc, order);
+  else if (KK <= 64) launch_knn<2>(var, grid, stream, xyz, new_xyz, idx, gxyz, N, S, k, skip, qpc, order);
+  else launch_knn<4>(var, grid, stream, xyz, new_xyz, idx, gxyz, N, S, k, skip, qpc, order);
   PS_LAUNCH_CHECK();
   return PS_OK;
+}
+
+extern "C" int ps_knn(const float* xyz, const float* new_xyz, int* idx, int B, int N, int S, int k,
+                      int skip, int dev, void* stream) {
+  return knn_impl(xyz, new_xyz, idx, nullptr, B, N, S, k, skip, PS_ORDER_SORT, dev, stream, "ps_knn");
+}
+
+extern "C" int ps_knn_point(const float* xyz, const float* new_xyz, int* idx, int B, int N, int S, int k,
+                            int dev, void* stream) {
+  return knn_impl(xyz, new_xyz, idx, nullptr, B, N, S, k, 0, PS_ORDER_TOPK, dev, stream, "ps_knn_point");
+}
+
+extern "C" int ps_knn_group_xyz(const float* xyz, const float* new_xyz, int* idx, float* grouped_xyz, int B,
+                                int N, int S, int k, int dev, void* stream) {
+  PS_REQUIRE(grouped_xyz || B == 0 || S == 0, "ps_knn_group_xyz: null grouped_xyz");
+  return knn_impl(xyz, new_xyz, idx, grouped_xyz, B, N, S, k, 0, PS_ORDER_SORT, dev, stream, "ps_knn_group_xyz");
 }
 
 extern "C" int ps_ball_query(const float* new_xyz, const float* xyz, int* idx, int B, int N, int S,

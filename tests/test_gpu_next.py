@@ -1,0 +1,263 @@
+"""GPU parity of the SURVEY 8(f) "next" rows, through the C ABI: feature-space kNN in torch.topk order,
+the fused sample_and_group_knn core, EdgeConv edge features, index_points and the evaluation metrics.
+
+Checked against (1) the CPU oracle, (2) tests/golden/next.npz (the reference's torch expressions + its own CUDA
+ops, generated on a B200), (3) the reference's torch expressions evaluated live by torch on the same GPU.
+Bars: indices bit-exact (including torch.topk's order among equal distances); gathered / subtracted
+features bit-exact; gradients and metric means within 1e-5 relative.
+"""
+import numpy as np
+import pytest
+import torch
+
+from conftest import load_golden, make_cloud
+from oracle import oracle as O
+
+pytestmark = pytest.mark.gpu
+
+import svdformer_pointsea_b200 as ps  # noqa: E402
+from svdformer_pointsea_b200 import model_ops as mo  # noqa: E402
+from svdformer_pointsea_b200 import pointnet2_utils as pu  # noqa: E402
+
+DEV = "cuda:0"
+
+
+def t(a):
+    return torch.from_numpy(np.ascontiguousarray(a)).to(DEV)
+
+
+def pm(x):
+    return np.ascontiguousarray(np.asarray(x).transpose(0, 2, 1))
+
+
+def rel(a, b):
+    a, b = np.asarray(a, np.float64), np.asarray(b, np.float64)
+    return np.abs(a - b).max() / max(np.abs(b).max(), 1e-30)
+
+
+# ---------------------------------------------------------------- kNN in torch.topk order
+@pytest.mark.parametrize("name", ["edge3", "edge3dup", "edge64", "edge256", "edge64post"])
+def test_knn_self_matches_golden_torch_topk(name):
+    z = load_golden("next")
+    x, k = z[f"{name}.x"], int(z[f"{name}.k"])
+    got = mo.knn_self(t(x), k).cpu().numpy()
+    assert np.array_equal(got, z[f"{name}.idx"])
+    # the point-major entry (what query_knn_point receives) gives the same answer
+    xt = t(pm(x))
+    assert np.array_equal(ps.query_knn_point(k, xt, xt).cpu().numpy(), z[f"{name}.idx"].astype(np.int64))
+
+
+@pytest.mark.parametrize("B,C,N,S,k", [(2, 3, 700, 700, 16), (2, 3, 3000, 64, 8), (3, 64, 512, 512, 8), (2, 256, 300, 300, 4),
+                                       (2, 5, 130, 40, 32), (1, 128, 1500, 100, 16), (2, 17, 2100, 50, 5), (1, 64, 4000, 33, 16)])
+@pytest.mark.parametrize("order", [0, 1])
+def test_knn_feat_vs_oracle(B, C, N, S, k, order):
+    g = torch.Generator().manual_seed(C * 1000 + N)
+    if C == 3:
+        xr = make_cloud(g, B, N, dup=N // 4)
+    else:
+        xr = torch.randn(B, N, C, generator=g)
+        xr[:, N // 2:N // 2 + N // 8] = xr[:, :N // 8]  # exact duplicates -> exact ties
+    xq = xr[:, :S].contiguous() if S <= N and (S == N or C != 3) else torch.randn(B, S, C, generator=g)
+    want = O.knn_feat(xr.numpy(), xq.numpy(), k, order=order)
+    got = mo.knn_feat_raw(xr.to(DEV), xq.to(DEV), k, channel_major=False, order=order).cpu().numpy()
+    assert np.array_equal(got, want)
+    # channel-major layout (EdgeConv's tensors)
+    got_cm = mo.knn_feat_raw(xr.permute(0, 2, 1).contiguous().to(DEV), xq.permute(0, 2, 1).contiguous().to(DEV), k,
+                             channel_major=True, order=order).cpu().numpy()
+    assert np.array_equal(got_cm, want)
+    if C == 3 and order == 1:
+        assert np.array_equal(mo.knn_point_raw(xr.to(DEV), xq.to(DEV), k).cpu().numpy(), want)
+
+
+@pytest.mark.parametrize("B,C,N,k", [(4, 3, 2048, 16), (8, 3, 1024, 16), (4, 64, 512, 8), (2, 256, 512, 4), (2, 64, 1024, 8)])
+def test_query_knn_point_vs_torch_cuda_live(B, C, N, k):
+    """The reference expression (square_distance + topk) run by torch on this GPU, with duplicated points:
+    B*N slices x N elements puts torch.topk on its multi-block radix path for the larger cases."""
+    g = torch.Generator().manual_seed(77 + C + N)
+    x = (make_cloud(g, B, N, dup=N // 3) if C == 3 else torch.randn(B, N, C, generator=g)).to(DEV)
+    if C != 3:
+        x[:, N // 2:N // 2 + N // 6] = x[:, :N // 6]
+    want = O.torch_query_knn_point(k, x, x)
+    got = ps.query_knn_point(k, x, x)
+    same_rows = (got == want).all(-1).float().mean().item()
+    assert same_rows == 1.0, f"rows identical to torch.topk: {same_rows:.6f}"
+
+
+def test_query_knn_point_errors():
+    x = torch.randn(1, 40, 8, device=DEV)
+    with pytest.raises(ps.PointSeaError):
+        ps.query_knn_point(41, x, x)          # k > N
+    with pytest.raises(ps.PointSeaError):
+        ps.query_knn_point(33, torch.randn(1, 64, 8, device=DEV), x)  # k > 32 unsupported
+    with pytest.raises(ps.PointSeaError):
+        ps.query_knn_point(4, x.cpu(), x.cpu())
+
+
+# ---------------------------------------------------------------- sample_and_group_knn
+@pytest.mark.parametrize("name", ["sg", "sgdup"])
+def test_sample_and_group_knn_matches_golden(name):
+    z = load_golden("next")
+    xyz = t(z[f"{name}.xyz"])
+    pts = t(z[f"{name}.points"]) if f"{name}.points" in z.files else None
+    new_xyz, new_points, idx, gxyz = ps.sample_and_group_knn(xyz, pts, int(z[f"{name}.npoint"]), int(z[f"{name}.k"]))
+    assert np.array_equal(new_xyz.cpu().numpy(), z[f"{name}.new_xyz"])
+    assert idx.dtype == torch.int32 and np.array_equal(idx.cpu().numpy(), z[f"{name}.idx"])
+    assert np.array_equal(gxyz.cpu().numpy(), z[f"{name}.grouped_xyz"])
+    assert np.array_equal(new_points.cpu().numpy(), z[f"{name}.new_points"])
+
+
+@pytest.mark.parametrize("B,N,S,k", [(2, 2048, 512, 16), (3, 512, 128, 16), (1, 5000, 300, 16), (2, 100, 100, 40)])
+def test_knn_group_xyz_fused_equals_unfused(B, N, S, k, monkeypatch):
+    g = torch.Generator().manual_seed(N + S)
+    xyz = make_cloud(g, B, N, dup=N // 5).to(DEV)
+    ctr = xyz[:, :S].contiguous()
+    for sel in ("1", "0"):  # threshold-selection kernel and streaming kernel
+        monkeypatch.setenv("PS_KNN_SELECT", sel)
+        idx, gx = mo.knn_group_xyz_raw(xyz, ctr, k)
+        want_idx = pu.knn_raw(xyz, ctr, k)
+        assert torch.equal(idx, want_idx)
+        want = pu.group_raw(xyz.permute(0, 2, 1).contiguous(), want_idx) - ctr.permute(0, 2, 1).unsqueeze(3)
+        assert torch.equal(gx, want)
+    oi, og = O.knn_group_xyz(xyz.cpu().numpy(), ctr.cpu().numpy(), k)
+    assert np.array_equal(idx.cpu().numpy(), oi) and np.array_equal(gx.cpu().numpy(), og)
+
+
+def test_sample_and_group_knn_gradients_match_the_reference_expression():
+    g = torch.Generator().manual_seed(3)
+    xyz = (torch.rand(2, 3, 300, generator=g) - 0.5).to(DEV).requires_grad_(True)
+    pts = torch.randn(2, 6, 300, generator=g).to(DEV).requires_grad_(True)
+    new_xyz, new_points, idx, gxyz = ps.sample_and_group_knn(xyz, pts, 64, 8)
+    w = torch.randn_like(new_points)
+    (new_points * w).sum().backward()
+    g_xyz, g_pts = xyz.grad.clone(), pts.grad.clone()
+    xyz.grad = pts.grad = None
+    # the reference expression on the unfused ops (models/model_utils.py:340-352)
+    xyz_flipped = xyz.permute(0, 2, 1).contiguous()
+    nx = pu.gather_operation(xyz, pu.furthest_point_sample(xyz_flipped, 64))
+    ii = pu.query_knn(8, xyz_flipped, nx.permute(0, 2, 1).contiguous())
+    gx = pu.grouping_operation(xyz, ii)
+    gx = gx - nx.unsqueeze(3).repeat(1, 1, 1, 8)
+    ref_points = torch.cat([gx, pu.grouping_operation(pts, ii)], 1)
+    assert torch.equal(ref_points, new_points) and torch.equal(ii, idx)
+    (ref_points * w).sum().backward()
+    assert rel(g_xyz.cpu().numpy(), xyz.grad.cpu().numpy()) < 1e-5
+    assert rel(g_pts.cpu().numpy(), pts.grad.cpu().numpy()) < 1e-5
+
+
+# ---------------------------------------------------------------- EdgeConv front, index_points
+@pytest.mark.parametrize("B,C,N,K", [(2, 3, 700, 16), (2, 64, 512, 8), (1, 256, 512, 4), (2, 5, 333, 7), (1, 2, 30000, 4), (2, 9, 64, 1)])
+def test_edge_features_fwd_bwd_vs_oracle(B, C, N, K):
+    g = torch.Generator().manual_seed(B + C + N)
+    x = torch.randn(B, C, N, generator=g)
+    idx = torch.randint(0, N, (B, N, K), generator=g, dtype=torch.int32)
+    out = mo.edge_features_raw(x.to(DEV), idx.to(DEV))
+    assert np.array_equal(out.cpu().numpy(), O.edge_features(x.numpy(), idx.numpy()))
+    go = torch.randn(B, 2 * C, N, K, generator=g)
+    gx = mo.edge_features_grad_raw(go.to(DEV), idx.to(DEV))
+    assert rel(gx.cpu().numpy(), O.edge_features_grad(go.numpy(), idx.numpy())) < 1e-5
+
+
+def test_edge_features_match_golden_and_reference_expression_live():
+    z = load_golden("next")
+    x = t(z["edge3dup.x"])
+    feat = ps.edge_features(x, int(z["edge3dup.k"]))
+    assert np.array_equal(feat.cpu().numpy(), z["edge3dup.feat"])
+    # live, at EdgeConv's real shapes (C=64 N=512 k=8; C=3 N=2048 k=16), forward and gradient
+    for (B, C, N, k) in ((4, 64, 512, 8), (2, 3, 2048, 16)):
+        g = torch.Generator().manual_seed(C)
+        xx = (torch.randn(B, C, N, generator=g) if C != 3 else make_cloud(g, B, N).permute(0, 2, 1).contiguous()).to(DEV)
+        a = xx.clone().requires_grad_(True)
+        b = xx.clone().requires_grad_(True)
+        ours = ps.edge_features(a, k)
+        want, _ = O.torch_edge_features(b, k)
+        assert torch.equal(ours, want)
+        w = torch.randn_like(want)
+        (ours * w).sum().backward()
+        (want * w).sum().backward()
+        assert rel(a.grad.cpu().numpy(), b.grad.cpu().numpy()) < 1e-5
+
+
+def test_edgeconv_module_equals_reference_module_expression():
+    torch.manual_seed(0)
+    conv = ps.EdgeConv(64, 256, 8).to(DEV).eval()
+    x = torch.randn(2, 64, 512, device=DEV)
+    with torch.no_grad():
+        ours = conv(x)
+        feat, _ = O.torch_edge_features(x, 8)
+        want = conv.conv(feat).max(dim=-1)[0]
+    assert torch.equal(ours, want)
+
+
+@pytest.mark.parametrize("B,N,C,shape", [(2, 100, 3, (50,)), (2, 512, 64, (512, 8)), (1, 2048, 7, (300, 5)), (3, 64, 256, (64, 4))])
+def test_index_points_fwd_bwd(B, N, C, shape):
+    g = torch.Generator().manual_seed(N + C)
+    pts = torch.randn(B, N, C, generator=g).to(DEV).requires_grad_(True)
+    idx = torch.randint(0, N, (B,) + shape, generator=g).to(DEV)
+    out = ps.index_points(pts, idx)
+    want = O.torch_index_points(pts.detach(), idx)
+    assert torch.equal(out, want)
+    w = torch.randn_like(out)
+    (out * w).sum().backward()
+    og = O.index_points_grad(w.cpu().numpy(), idx.cpu().numpy(), N)
+    assert rel(pts.grad.cpu().numpy(), og) < 1e-5
+
+
+def test_group_local_equals_reference_expression():
+    g = torch.Generator().manual_seed(11)
+    x = make_cloud(g, 2, 800).permute(0, 2, 1).contiguous().to(DEV)
+    gx, idx = ps.group_local(x, k=20, return_idx=True)
+    xt = x.transpose(2, 1).contiguous()
+    widx = O.torch_query_knn_point(20, xt, xt)
+    assert torch.equal(idx, widx)
+    assert torch.equal(gx, O.torch_index_points(xt, widx).permute(0, 3, 1, 2))
+
+
+# ---------------------------------------------------------------- metrics
+@pytest.mark.parametrize("name", ["dcd", "dcddup", "dcdnear"])
+def test_metrics_match_golden(name):
+    z = load_golden("next")
+    x, gt = t(z[f"{name}.x"]), t(z[f"{name}.gt"])
+    loss, cd_p, cd_t, d1, d2, i1, i2 = ps.calc_dcd(x, gt, return_raw=True)
+    assert np.array_equal(d1.cpu().numpy(), z[f"{name}.dist1"]) and np.array_equal(i2.cpu().numpy(), z[f"{name}.idx2"])
+    assert np.allclose(loss.cpu().numpy(), z[f"{name}.dcd"], rtol=1e-5, atol=1e-7)
+    assert rel(cd_p.cpu().numpy(), z[f"{name}.cd_p"]) < 1e-5 and rel(cd_t.cpu().numpy(), z[f"{name}.cd_t"]) < 1e-5
+    nr = ps.calc_dcd(x, gt, alpha=40, n_lambda=0.5, non_reg=True)[0]
+    assert np.allclose(nr.cpu().numpy(), z[f"{name}.dcd_nonreg"], rtol=1e-5, atol=1e-7)
+    cd = ps.calc_cd(x, gt, calc_f1=True)
+    assert np.allclose(cd[2].cpu().numpy(), z[f"{name}.f1"], rtol=1e-5, atol=1e-7)
+    f, p1, p2 = ps.fscore(d1, d2, threshold=0.01)
+    assert np.allclose(f.cpu().numpy(), z[f"{name}.f1_t01"], rtol=1e-5, atol=1e-7)
+    f, p1, p2 = ps.fscore(d1, d2)
+    assert np.allclose(p1.cpu().numpy(), z[f"{name}.p1"], rtol=1e-6) and np.allclose(p2.cpu().numpy(), z[f"{name}.p2"], rtol=1e-6)
+
+
+@pytest.mark.parametrize("B,n_x,n_gt", [(4, 2048, 2048), (2, 16384, 16384), (2, 8192, 16384), (1, 30000, 25000)])
+def test_metrics_vs_reference_expressions_live(B, n_x, n_gt):
+    """Full sizes (PCN 16384-point evaluation; the last case uses the global-memory histograms)."""
+    g = torch.Generator().manual_seed(n_x)
+    gt = make_cloud(g, B, n_gt)
+    x = (gt[:, torch.randperm(n_gt, generator=g)[:n_x]] if n_x <= n_gt else make_cloud(g, B, n_x))
+    x = (x + 0.004 * torch.randn(x.shape, generator=g)).to(DEV)
+    gt = gt.to(DEV)
+    loss, cd_p, cd_t, d1, d2, i1, i2 = ps.calc_dcd(x, gt, return_raw=True)
+    want = O.torch_dcd_from_raw(d1, d2, i1, i2, n_x, n_gt)
+    assert torch.allclose(loss, want, rtol=1e-5, atol=1e-7)
+    wp, wt = O.torch_cd_terms(d1, d2)
+    assert torch.allclose(cd_p, wp, rtol=1e-5) and torch.allclose(cd_t, wt, rtol=1e-5)
+    wf, w1, w2 = O.torch_fscore(d1, d2)
+    f, p1, p2 = ps.fscore(d1, d2)
+    assert torch.allclose(f, wf, rtol=1e-5, atol=1e-7) and torch.allclose(p1, w1, rtol=1e-6) and torch.allclose(p2, w2, rtol=1e-6)
+    om = O.chamfer_metrics(d1.cpu().numpy(), d2.cpu().numpy(), i1.cpu().numpy(), i2.cpu().numpy(), frac1=n_gt / n_x, frac2=n_x / n_gt)
+    got = ps.chamfer_metrics_raw(d1, d2, i1, i2, frac1=n_gt / n_x, frac2=n_x / n_gt).cpu().numpy()
+    assert np.allclose(got, om, rtol=1e-5, atol=1e-7)
+    sep = ps.calc_cd(x, gt, separate=True)
+    assert sep[0].shape == (2, B) and sep[1].shape == (2, B)
+
+
+def test_patch_model_utils_rebinds_names():
+    import types
+    m = types.ModuleType("fake_model_utils")
+    m.EdgeConv = type("EdgeConv", (torch.nn.Module,), {})
+    ps.patch_model_utils(m)
+    assert m.query_knn is pu.query_knn and m.sample_and_group_knn is ps.sample_and_group_knn
+    assert m.EdgeConv.forward is ps.EdgeConv.forward
