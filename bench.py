@@ -347,6 +347,25 @@ def bench_ops(ps, pu, dev, flush, peaks, peaks_src, rank):
     out["group_bwd"] = {"ms": round(min(ms), 4), "ms_median": round(statistics.median(ms), 4),
                         "gbs": round(byts / t / 1e9, 1), "frac_hbm": round(byts / t / 1e9 / peaks["hbm_gbs"], 4)}
     del go, holder
+    # SURVEY 8(f) rows at the models' shapes (EdgeConv(64,256,8) of SVDFormer's local encoder; PCN evaluation)
+    from svdformer_pointsea_b200 import model_ops as mo
+    g = torch.Generator().manual_seed(1234 + 6 + rank)
+    x = torch.randn(32, 64, 512, generator=g).to(dev)
+    eidx = mo.knn_self(x, 8)
+    ms = timed(lambda: mo.knn_self(x, 8), 10, 3, flush)
+    nxt = {"feature_knn": {"config": "B=32 C=64 N=512 k=8 (torch.topk order)", "ms": round(min(ms), 4),
+                           "gpair_per_s": round(32 * 512 * 512 / (min(ms) * 1e-3) / 1e9, 1),
+                           "tflops": round(2.0 * 64 * 32 * 512 * 512 / (min(ms) * 1e-3) / 1e12, 2)}}
+    ms = timed(lambda: mo.edge_features_raw(x, eidx), 20, 3, flush)
+    byts = 4 * (32 * 512 * 8 + 32 * 64 * 512 + 2 * 32 * 64 * 512 * 8)
+    nxt["edge_features_fwd"] = {"config": "B=32 C=64 N=512 k=8 -> (32,128,512,8)", "ms": round(min(ms), 4),
+                                "gbs": round(byts / (statistics.median(ms) * 1e-3) / 1e9, 1)}
+    gt = make_cloud(g, 32, 16384).to(dev)
+    pred = gt + 0.004 * torch.randn(32, 16384, 3, generator=g).to(dev)
+    d1, d2, i1, i2 = ps.chamfer_forward(gt, pred)
+    ms = timed(lambda: ps.chamfer_metrics_raw(d1, d2, i1, i2), 20, 3, flush)
+    nxt["metrics_epilogue"] = {"config": "calc_cd + fscore + calc_dcd, B=32, 16384 vs 16384", "ms": round(min(ms), 4)}
+    out["next"] = nxt
     return out
 
 

@@ -28,7 +28,7 @@ namespace {
 constexpr int FK_THREADS = 256;
 constexpr int FK_WARPS = FK_THREADS / 32;
 constexpr int FK_KC = 16;   // channels per shared-memory stage
-constexpr int FK_TR = 128;  // reference points per accumulator pass
+constexpr int FK_TR = 256;  // reference points per accumulator pass (each lane: 2 x 4 consecutive)
 
 // One warp per row; lane t plays torch's reduce thread t (block width bw <= 32).
 __global__ void __launch_bounds__(FK_THREADS) rowsumsq_torch_kernel(const float* __restrict__ x, float* __restrict__ out,
@@ -93,6 +93,9 @@ __device__ __forceinline__ float fk_sort_values(float v, int lane) {
 template <int TQ>
 __global__ void __launch_bounds__(FK_THREADS) knn_feat_kernel(const FkArgs a) {
   constexpr int QPT = TQ / FK_WARPS;  // queries per thread in the tile loop = rows per warp in the selection
+  constexpr int NQ = FK_KC * TQ / FK_THREADS;     // staged query values per thread (TQ=32: 2, 16: 1, 8: 0.5 -> 1)
+  constexpr int NQR = NQ > 0 ? NQ : 1;
+  constexpr int NR = FK_KC * FK_TR / FK_THREADS;  // staged reference values per thread
   extern __shared__ __align__(16) float smem[];
   float* dist = smem;                          // TQ x npad
   float* qs = dist + (size_t)TQ * a.npad;      // FK_KC x TQ
@@ -112,76 +115,97 @@ __global__ void __launch_bounds__(FK_THREADS) knn_feat_kernel(const FkArgs a) {
     qn[i] = q < S ? __ldg(a.qq + (size_t)b * S + q) : 0.f;
   }
 
+  // global -> register prefetch of one (FK_KC channels) x (TQ queries | FK_TR references) stage; the loads
+  // of stage s+1 are in flight while stage s is consumed from shared memory
+  float pq[NQR], pr[NR];
+  auto fetch = [&](int r0, int c0) {
+#pragma unroll
+    for (int j = 0; j < NQR; j++) {
+      const int i = tid + j * FK_THREADS;
+      const int kc = i / TQ, q = i % TQ;
+      pq[j] = (i < FK_KC * TQ && c0 + kc < C && q0 + q < S) ? __ldg(xq + (size_t)(q0 + q) * a.snq + (size_t)(c0 + kc) * a.scq) : 0.f;
+    }
+#pragma unroll
+    for (int j = 0; j < NR; j++) {
+      const int i = tid + j * FK_THREADS;
+      const int kc = i / FK_TR, r = i % FK_TR;
+      pr[j] = (c0 + kc < C && r0 + r < N) ? __ldg(xr + (size_t)(r0 + r) * a.snr + (size_t)(c0 + kc) * a.scr) : 0.f;
+    }
+  };
+  auto commit = [&]() {
+#pragma unroll
+    for (int j = 0; j < NQR; j++) {
+      const int i = tid + j * FK_THREADS;
+      if (i < FK_KC * TQ) qs[i] = pq[j];  // qs[kc * TQ + q], i = kc * TQ + q
+    }
+#pragma unroll
+    for (int j = 0; j < NR; j++) rs[tid + j * FK_THREADS] = pr[j];  // rs[kc * FK_TR + r]
+  };
+
+  const int nstage = (C + FK_KC - 1) / FK_KC;
   for (int r0 = 0; r0 < npad; r0 += FK_TR) {
-    float acc[QPT][4];
+    float acc[QPT][8];
 #pragma unroll
     for (int i = 0; i < QPT; i++)
 #pragma unroll
-      for (int j = 0; j < 4; j++) acc[i][j] = 0.f;
-    for (int c0 = 0; c0 < C; c0 += FK_KC) {
+      for (int j = 0; j < 8; j++) acc[i][j] = 0.f;
+    fetch(r0, 0);
+    for (int st = 0; st < nstage; st++) {
+      const int c0 = st * FK_KC;
       const int kcn = min(FK_KC, C - c0);
+      __syncthreads();  // the previous stage has been consumed
+      commit();
       __syncthreads();
-      for (int i = tid; i < FK_KC * TQ; i += FK_THREADS) {
-        const int kc = i / TQ, q = i % TQ;
-        float v = 0.f;
-        if (kc < kcn && q0 + q < S) v = __ldg(xq + (size_t)(q0 + q) * a.snq + (size_t)(c0 + kc) * a.scq);
-        qs[kc * TQ + q] = v;
-      }
-      for (int i = tid; i < FK_KC * FK_TR; i += FK_THREADS) {
-        const int kc = i / FK_TR, r = i % FK_TR;
-        float v = 0.f;
-        if (kc < kcn && r0 + r < N) v = __ldg(xr + (size_t)(r0 + r) * a.snr + (size_t)(c0 + kc) * a.scr);
-        rs[kc * FK_TR + r] = v;
-      }
-      __syncthreads();
+      if (st + 1 < nstage) fetch(r0, c0 + FK_KC);
       // ascending-channel FMA chain per (query, reference) pair; a partial last stage stops at kcn so that
       // no padded product enters the chain
+      auto step = [&](int kc) {
+        const float4 r0v = *reinterpret_cast<const float4*>(&rs[kc * FK_TR + lane * 4]);
+        const float4 r1v = *reinterpret_cast<const float4*>(&rs[kc * FK_TR + 128 + lane * 4]);
+        float qv[QPT];
+        if (QPT == 4) {
+          const float4 t = *reinterpret_cast<const float4*>(&qs[kc * TQ + warp * 4]);
+          qv[0] = t.x; qv[1 % QPT] = t.y; qv[2 % QPT] = t.z; qv[3 % QPT] = t.w;
+        } else {
+#pragma unroll
+          for (int i = 0; i < QPT; i++) qv[i] = qs[kc * TQ + warp * QPT + i];
+        }
+#pragma unroll
+        for (int i = 0; i < QPT; i++) {
+          acc[i][0] = __fmaf_rn(qv[i], r0v.x, acc[i][0]);
+          acc[i][1] = __fmaf_rn(qv[i], r0v.y, acc[i][1]);
+          acc[i][2] = __fmaf_rn(qv[i], r0v.z, acc[i][2]);
+          acc[i][3] = __fmaf_rn(qv[i], r0v.w, acc[i][3]);
+          acc[i][4] = __fmaf_rn(qv[i], r1v.x, acc[i][4]);
+          acc[i][5] = __fmaf_rn(qv[i], r1v.y, acc[i][5]);
+          acc[i][6] = __fmaf_rn(qv[i], r1v.z, acc[i][6]);
+          acc[i][7] = __fmaf_rn(qv[i], r1v.w, acc[i][7]);
+        }
+      };
       if (kcn == FK_KC) {
 #pragma unroll
-        for (int kc = 0; kc < FK_KC; kc++) {
-          const float4 rv = *reinterpret_cast<const float4*>(&rs[kc * FK_TR + lane * 4]);
-#pragma unroll
-          for (int i = 0; i < QPT; i++) {
-            const float qv = qs[kc * TQ + warp * QPT + i];
-            acc[i][0] = __fmaf_rn(qv, rv.x, acc[i][0]);
-            acc[i][1] = __fmaf_rn(qv, rv.y, acc[i][1]);
-            acc[i][2] = __fmaf_rn(qv, rv.z, acc[i][2]);
-            acc[i][3] = __fmaf_rn(qv, rv.w, acc[i][3]);
-          }
-        }
+        for (int kc = 0; kc < FK_KC; kc++) step(kc);
       } else {
-        for (int kc = 0; kc < kcn; kc++) {
-          const float4 rv = *reinterpret_cast<const float4*>(&rs[kc * FK_TR + lane * 4]);
-#pragma unroll
-          for (int i = 0; i < QPT; i++) {
-            const float qv = qs[kc * TQ + warp * QPT + i];
-            acc[i][0] = __fmaf_rn(qv, rv.x, acc[i][0]);
-            acc[i][1] = __fmaf_rn(qv, rv.y, acc[i][1]);
-            acc[i][2] = __fmaf_rn(qv, rv.z, acc[i][2]);
-            acc[i][3] = __fmaf_rn(qv, rv.w, acc[i][3]);
-          }
-        }
+        for (int kc = 0; kc < kcn; kc++) step(kc);
       }
     }
     // dist = ((-2 * dot) + |q|^2) + |r|^2 ; padding columns at +inf
-    float pn[4];
 #pragma unroll
-    for (int j = 0; j < 4; j++) {
-      const int r = r0 + lane * 4 + j;
-      pn[j] = r < N ? __ldg(a.pp + (size_t)b * N + r) : INF;
-    }
+    for (int h = 0; h < 2; h++) {
+      const int rb = r0 + h * 128 + lane * 4;
+      float pn[4];
 #pragma unroll
-    for (int i = 0; i < QPT; i++) {
-      float4 o;
-      o.x = __fadd_rn(__fadd_rn(__fmul_rn(-2.0f, acc[i][0]), qn[i]), pn[0]);
-      o.y = __fadd_rn(__fadd_rn(__fmul_rn(-2.0f, acc[i][1]), qn[i]), pn[1]);
-      o.z = __fadd_rn(__fadd_rn(__fmul_rn(-2.0f, acc[i][2]), qn[i]), pn[2]);
-      o.w = __fadd_rn(__fadd_rn(__fmul_rn(-2.0f, acc[i][3]), qn[i]), pn[3]);
-      if (r0 + lane * 4 + 0 >= N) o.x = INF;
-      if (r0 + lane * 4 + 1 >= N) o.y = INF;
-      if (r0 + lane * 4 + 2 >= N) o.z = INF;
-      if (r0 + lane * 4 + 3 >= N) o.w = INF;
-      *reinterpret_cast<float4*>(&dist[(size_t)(warp * QPT + i) * npad + r0 + lane * 4]) = o;
+      for (int j = 0; j < 4; j++) pn[j] = rb + j < N ? __ldg(a.pp + (size_t)b * N + rb + j) : INF;
+#pragma unroll
+      for (int i = 0; i < QPT; i++) {
+        float o[4];
+#pragma unroll
+        for (int j = 0; j < 4; j++) {
+          o[j] = __fadd_rn(__fadd_rn(__fmul_rn(-2.0f, acc[i][h * 4 + j]), qn[i]), pn[j]);
+          if (rb + j >= N) o[j] = INF;
+        }
+        *reinterpret_cast<float4*>(&dist[(size_t)(warp * QPT + i) * npad + rb]) = make_float4(o[0], o[1], o[2], o[3]);
+      }
     }
   }
   __syncwarp();  // each warp selects from the rows it wrote itself

@@ -238,6 +238,8 @@ __global__ void __launch_bounds__(GG_THREADS) scatter_direct_kernel(
 constexpr int CSR_CHUNK = 16384;   // positions per stage (64 KB of fp32)
 constexpr int CSR_THREADS = 1024;  // measured on C3: 512 thr 0.195 ms, 1024 thr 0.172 ms
 constexpr int CSR_BUILD_THREADS = 1024;
+constexpr int CSR_HEAVY = 32;      // a source with more entries than this in one chunk is summed by a whole warp
+constexpr int CSR_MAX_HEAVY = CSR_CHUNK / (CSR_HEAVY + 1) + 1;
 
 __global__ void __launch_bounds__(CSR_BUILD_THREADS) csr_build_kernel(const int* __restrict__ idx, int* __restrict__ bnd_all,
                                                                      unsigned short* __restrict__ list_all, int N, int Mp,
@@ -247,6 +249,8 @@ __global__ void __launch_bounds__(CSR_BUILD_THREADS) csr_build_kernel(const int*
   int* cur = sm_i + (N + 1);   // N
   unsigned short* list = reinterpret_cast<unsigned short*>(cur + N);  // CSR_CHUNK
   __shared__ int warp_tot[CSR_BUILD_THREADS / 32];
+  __shared__ int heavy[CSR_CHUNK / (CSR_HEAVY + 1) + 1];
+  __shared__ int nheavy;
   const int k = blockIdx.x, b = blockIdx.y, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int p0 = k * CSR_CHUNK, len = min(CSR_CHUNK, Mp - p0);
   const int* ib = idx + (size_t)b * Mp + p0;
@@ -276,11 +280,19 @@ __global__ void __launch_bounds__(CSR_BUILD_THREADS) csr_build_kernel(const int*
   int base = incl - run + (warp ? warp_tot[warp - 1] : 0);
   for (int n = lo; n < hi; n++) { const int c = cnt[n]; cur[n] = base; cnt[n] = base; base += c; }  // cnt now holds the offsets
   __syncthreads();
-  if (tid == 0) cnt[N] = len;
-  for (int p = tid; p < len; p += CSR_BUILD_THREADS) list[atomicAdd(&cur[__ldg(ib + p)], 1)] = (unsigned short)p;
+  if (tid == 0) { cnt[N] = len; nheavy = 0; }
+  __syncthreads();
+  // Light sources (<= CSR_HEAVY entries): cursor fill + a short insertion sort per list.  Heavy sources
+  // (hubs of a kNN graph in feature space; index 0 of a zero-filled ball query) would make that sort
+  // quadratic, so their lists are produced already sorted by a warp that scans the chunk in order.
+  for (int p = tid; p < len; p += CSR_BUILD_THREADS) {
+    const int src = __ldg(ib + p);
+    if (cnt[src + 1] - cnt[src] <= CSR_HEAVY) list[atomicAdd(&cur[src], 1)] = (unsigned short)p;
+  }
   __syncthreads();
   for (int n = tid; n < N; n += CSR_BUILD_THREADS) {  // ascending positions inside each list
     const int s = cnt[n], e = cnt[n + 1];
+    if (e - s > CSR_HEAVY) { heavy[atomicAdd(&nheavy, 1)] = n; continue; }
     for (int i = s + 1; i < e; i++) {
       const unsigned short v = list[i];
       int j = i - 1;
@@ -289,8 +301,36 @@ __global__ void __launch_bounds__(CSR_BUILD_THREADS) csr_build_kernel(const int*
     }
   }
   __syncthreads();
+  for (int h = warp; h < nheavy; h += CSR_BUILD_THREADS / 32) {
+    const int n = heavy[h];
+    int base = cnt[n];
+    for (int p0w = 0; p0w < len; p0w += 32) {
+      const int p = p0w + lane;
+      const bool hit = p < len && __ldg(ib + p) == n;
+      const unsigned mask = __ballot_sync(0xffffffffu, hit);
+      if (hit) list[base + __popc(mask & ((1u << lane) - 1u))] = (unsigned short)p;
+      base += __popc(mask);
+    }
+  }
+  __syncthreads();
   for (int n = tid; n <= N; n += CSR_BUILD_THREADS) bnd[n] = cnt[n];
   for (int i = tid; i < len; i += CSR_BUILD_THREADS) out[i] = list[i];
+}
+
+// Hubs of one staged channel chunk: each warp sums the entries of a heavy source with lane-strided partial sums
+// and a fixed shuffle tree (deterministic).  Kept out of line so that its registers do not add to the pressure
+// of the unrolled channel loop (64-register budget at 1024 threads).
+__device__ __noinline__ void csr_heavy_pass(const float* st, const unsigned short* list, const int* h_lo, const int* h_cnt,
+                                            float* h_sum, int nh) {
+  const int lane = threadIdx.x & 31;
+  for (int h = threadIdx.x >> 5; h < nh; h += CSR_THREADS / 32) {
+    const int hl = h_lo[h], hc = h_cnt[h];
+    float hs = 0.f;
+    for (int e = lane; e < hc; e += 32) hs += st[list[hl + e]];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) hs += __shfl_xor_sync(0xffffffffu, hs, o);
+    if (lane == 0) h_sum[h] = hs;
+  }
 }
 
 // NPT sources per thread, PF list entries per source cached in registers, CPB channels per CTA
@@ -305,6 +345,9 @@ __global__ void __launch_bounds__(CSR_THREADS, 1) scatter_csr_kernel(const float
   float* stage1 = stage0 + CSR_CHUNK;
   unsigned short* list = reinterpret_cast<unsigned short*>(stage1 + CSR_CHUNK);  // CSR_CHUNK
   int* bnd = reinterpret_cast<int*>(list + CSR_CHUNK);                           // N + 1
+  __shared__ int h_lo[CSR_MAX_HEAVY], h_cnt[CSR_MAX_HEAVY];
+  __shared__ float h_sum[2][CSR_MAX_HEAVY];
+  __shared__ int nh;
   const int b = blockIdx.y, c0 = blockIdx.x * CSR_CPB, tid = threadIdx.x;
   const int nch = min(CSR_CPB, C - c0);
   const int items = nch * nchunks;
@@ -338,6 +381,7 @@ __global__ void __launch_bounds__(CSR_THREADS, 1) scatter_csr_kernel(const float
     for (int i = tid; i < len / 2; i += CSR_THREADS)
       reinterpret_cast<unsigned*>(list)[i] = __ldg(reinterpret_cast<const unsigned*>(gl) + i);
     if ((len & 1) && tid == 0) list[len - 1] = __ldg(gl + len - 1);
+    if (tid == 0) nh = 0;
     __syncthreads();
     int lo[NPT], cntv[NPT];
     int pp[NPT][PF];
@@ -346,9 +390,16 @@ __global__ void __launch_bounds__(CSR_THREADS, 1) scatter_csr_kernel(const float
       const int n = tid + i * CSR_THREADS;
       lo[i] = 0; cntv[i] = 0;
       if (n < N) { lo[i] = bnd[n]; cntv[i] = bnd[n + 1] - lo[i]; }
+      if (cntv[i] > CSR_HEAVY) {
+        // hub: its entries are summed by a whole warp per channel (below); this thread only keeps the slot
+        const int slot = atomicAdd(&nh, 1);
+        h_lo[slot] = lo[i]; h_cnt[slot] = cntv[i];
+        lo[i] = slot; cntv[i] = -1;
+      }
 #pragma unroll
       for (int u = 0; u < PF; u++) pp[i][u] = (u < cntv[i]) ? (int)list[lo[i] + u] : -1;
     }
+    __syncthreads();  // heavy slots visible
 #pragma unroll
     for (int c = 0; c < CSR_CPB; c++) {
       if (c < nch) {
@@ -363,7 +414,11 @@ __global__ void __launch_bounds__(CSR_THREADS, 1) scatter_csr_kernel(const float
           for (int q = PF; q < cntv[i]; q++) a += st[list[lo[i] + q]];  // long lists: remainder from shared memory
           acc[i][c] = a;
         }
+        if (nh > 0) csr_heavy_pass(st, list, h_lo, h_cnt, h_sum[item & 1], nh);
         __syncthreads();  // every thread is done with this stage before it is refilled
+#pragma unroll
+        for (int i = 0; i < NPT; i++)
+          if (cntv[i] < 0) acc[i][c] += h_sum[item & 1][lo[i]];
         if (tid == 0 && item + 2 < items) issue(item + 2);
         item++;
       }
@@ -455,7 +510,9 @@ static int gather_bwd_impl(const float* gout, const int* idx, float* gfeat, int 
   const int vec_ok = ((Mp & 3) == 0) && ((reinterpret_cast<uintptr_t>(idx) & 15) == 0) && ((reinterpret_cast<uintptr_t>(gout) & 15) == 0);
   // Dense grouping (each source referenced >= 4 times on average, several channels): inverse-index
   // path.  Needs 16-byte aligned rows for the bulk copies and N small enough for the build kernel.
-  bool use_csr = (long long)Mp >= 4ll * N && C >= 4 && N <= 8 * CSR_THREADS && (Mp & 3) == 0 &&
+  // (measured at the models' shapes, tools/sweep_scatter.py: below ~4096 positions per cloud the fixed cost of
+  // the build + the 1024-thread persistent CTAs loses to the shared-memory accumulators)
+  bool use_csr = (long long)Mp >= 4ll * N && Mp >= 4096 && C >= 4 && N <= 8 * CSR_THREADS && (Mp & 3) == 0 &&
                  (reinterpret_cast<uintptr_t>(gout) & 15) == 0;
   if (const char* e = getenv("PS_SCATTER_CSR")) use_csr = use_csr && atoi(e) != 0;
   if (use_csr) {
@@ -605,6 +662,26 @@ __global__ void __launch_bounds__(GG_THREADS) edge_direct_kernel(const float* __
 }
 
 // backward finish: gx[b,c,n] = sum_k (gE[b,c,n,k] + gC[b,c,n,k]) - gx[b,c,n]   (gx holds the scattered gE on entry)
+// LPR = K/4 lanes share one (b,c,n) row: every lane loads one float4 of each half (fully coalesced), the
+// row sum is finished with shuffles.  LPR in {1,2,4,8}; other K take the scalar kernel below.
+template <int LPR>
+__global__ void __launch_bounds__(GG_THREADS) edge_bwd_finish_vec_kernel(const float* __restrict__ gout, float* __restrict__ gx,
+                                                                         int C, int N, long long rows_per_b, long long total_rows) {
+  const long long t = (long long)blockIdx.x * GG_THREADS + threadIdx.x;  // one thread per float4 of a row
+  const long long row = t / LPR;                                         // (b, c, n) flattened
+  const bool valid = row < total_rows;
+  float s = 0.f;
+  if (valid) {
+    const long long b = row / rows_per_b, r = row % rows_per_b;         // rows_per_b = C*N
+    const size_t base = ((size_t)b * 2 * rows_per_b + r) * (LPR * 4) + (size_t)(t % LPR) * 4;
+    const float4 e = __ldcs(reinterpret_cast<const float4*>(gout + base));
+    const float4 c = __ldcs(reinterpret_cast<const float4*>(gout + base + (size_t)rows_per_b * (LPR * 4)));
+    s = ((e.x + c.x) + (e.y + c.y)) + ((e.z + c.z) + (e.w + c.w));
+  }
+#pragma unroll
+  for (int o = LPR >> 1; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+  if (valid && (t % LPR) == 0) gx[row] = s - gx[row];
+}
 __global__ void __launch_bounds__(GG_THREADS) edge_bwd_finish_kernel(const float* __restrict__ gout, float* __restrict__ gx,
                                                                      int C, int N, int K, long long total) {
   const long long t = (long long)blockIdx.x * GG_THREADS + threadIdx.x;
@@ -621,20 +698,41 @@ __global__ void __launch_bounds__(GG_THREADS) edge_bwd_finish_kernel(const float
 
 // ---- index_points: row gather on point-major tensors (models/model_utils.py:828-845) -----------------
 //   out[b,m,:] = points[b, idx[b,m], :]      points (B,N,C), idx (B,M) (any trailing shape flattened), out (B,M,C)
+// grid = (row blocks, B); a CTA copies IP_ROWS consecutive output rows; one thread per VEC elements, 4 in flight
+constexpr int IP_ROWS = 64;
 template <int VEC>
 __global__ void __launch_bounds__(GG_THREADS) index_points_kernel(const float* __restrict__ pts, const int* __restrict__ idx,
-                                                                  float* __restrict__ out, int N, int M, int C, long long total) {
-  const long long t = (long long)blockIdx.x * GG_THREADS + threadIdx.x;  // one thread per VEC output elements
-  if (t >= total) return;
-  const int cv = C / VEC;
-  const int c = (int)(t % cv) * VEC;
-  const long long row = t / cv;  // b*M + m
-  const int b = (int)(row / M);
-  const int i = __ldg(idx + row);
-  const float* s = pts + ((size_t)b * N + i) * C + c;
-  float* o = out + (size_t)row * C + c;
-  if (VEC == 4) __stcs(reinterpret_cast<float4*>(o), __ldg(reinterpret_cast<const float4*>(s)));
-  else *o = __ldg(s);
+                                                                  float* __restrict__ out, int N, int M, int C) {
+  __shared__ int sidx[IP_ROWS];
+  const int b = blockIdx.y, m0 = blockIdx.x * IP_ROWS, tid = threadIdx.x;
+  const int rows = min(IP_ROWS, M - m0);
+  if (tid < rows) sidx[tid] = __ldg(idx + (size_t)b * M + m0 + tid);
+  __syncthreads();
+  const int cv = C / VEC;              // vector elements per row
+  const int total = rows * cv;
+  const float* src = pts + (size_t)b * N * C;
+  float* dst = out + ((size_t)b * M + m0) * C;
+  for (int e0 = tid; e0 < total; e0 += GG_THREADS * 4) {
+    if (VEC == 4) {
+      float4 v[4];
+#pragma unroll
+      for (int u = 0; u < 4; u++) {
+        const int e = e0 + u * GG_THREADS;
+        if (e < total) { const int r = e / cv, c = (e - r * cv) * 4; v[u] = __ldg(reinterpret_cast<const float4*>(src + (size_t)sidx[r] * C + c)); }
+      }
+#pragma unroll
+      for (int u = 0; u < 4; u++) {
+        const int e = e0 + u * GG_THREADS;
+        if (e < total) __stcs(reinterpret_cast<float4*>(dst + (size_t)e * 4), v[u]);
+      }
+    } else {
+#pragma unroll
+      for (int u = 0; u < 4; u++) {
+        const int e = e0 + u * GG_THREADS;
+        if (e < total) { const int r = e / cv, c = e - r * cv; dst[e] = __ldg(src + (size_t)sidx[r] * C + c); }
+      }
+    }
+  }
 }
 template <int VEC>
 __global__ void __launch_bounds__(GG_THREADS) index_points_grad_kernel(const float* __restrict__ gout, const int* __restrict__ idx,
@@ -726,7 +824,19 @@ extern "C" int ps_edge_features_bwd(const float* grad_out, const int* idx, float
   if (!guard.ok) return set_error(PS_ERR_CUDA, "ps_edge_features_bwd: cannot select device %d", dev);
   // 2. centre terms minus the scatter
   const long long total = (long long)B * C * N;
-  edge_bwd_finish_kernel<<<ceil_div(total, GG_THREADS), GG_THREADS, 0, stream>>>(grad_out, grad_x, C, N, K, total);
+  const bool vec = (K == 4 || K == 8 || K == 16 || K == 32) && (reinterpret_cast<uintptr_t>(grad_out) & 15) == 0;
+  if (vec) {
+    const int lpr = K / 4;
+    const long long threads = total * lpr;
+    PS_REQUIRE(threads / GG_THREADS < (1ll << 31) - 1, "ps_edge_features_bwd: tensor too large");
+    const int grid = ceil_div(threads, GG_THREADS);
+    if (lpr == 1) edge_bwd_finish_vec_kernel<1><<<grid, GG_THREADS, 0, stream>>>(grad_out, grad_x, C, N, (long long)C * N, total);
+    else if (lpr == 2) edge_bwd_finish_vec_kernel<2><<<grid, GG_THREADS, 0, stream>>>(grad_out, grad_x, C, N, (long long)C * N, total);
+    else if (lpr == 4) edge_bwd_finish_vec_kernel<4><<<grid, GG_THREADS, 0, stream>>>(grad_out, grad_x, C, N, (long long)C * N, total);
+    else edge_bwd_finish_vec_kernel<8><<<grid, GG_THREADS, 0, stream>>>(grad_out, grad_x, C, N, (long long)C * N, total);
+  } else {
+    edge_bwd_finish_kernel<<<ceil_div(total, GG_THREADS), GG_THREADS, 0, stream>>>(grad_out, grad_x, C, N, K, total);
+  }
   PS_LAUNCH_CHECK();
   return PS_OK;
 }
@@ -740,10 +850,10 @@ extern "C" int ps_index_points_fwd(const float* points, const int* idx, float* o
   if (!guard.ok) return set_error(PS_ERR_CUDA, "ps_index_points_fwd: cannot select device %d", dev);
   cudaStream_t stream = (cudaStream_t)stream_;
   const bool v4 = ((C & 3) == 0) && ((reinterpret_cast<uintptr_t>(points) & 15) == 0) && ((reinterpret_cast<uintptr_t>(out) & 15) == 0);
-  const long long total = (long long)B * M * (v4 ? C / 4 : C);
-  PS_REQUIRE(total / GG_THREADS < (1ll << 31) - 1, "ps_index_points_fwd: tensor too large");
-  if (v4) index_points_kernel<4><<<ceil_div(total, GG_THREADS), GG_THREADS, 0, stream>>>(points, idx, out, N, M, C, total);
-  else index_points_kernel<1><<<ceil_div(total, GG_THREADS), GG_THREADS, 0, stream>>>(points, idx, out, N, M, C, total);
+  PS_REQUIRE(B <= 65535 && (long long)IP_ROWS * C < (1ll << 30), "ps_index_points_fwd: B or C too large");
+  const dim3 grid(ceil_div(M, IP_ROWS), B);
+  if (v4) index_points_kernel<4><<<grid, GG_THREADS, 0, stream>>>(points, idx, out, N, M, C);
+  else index_points_kernel<1><<<grid, GG_THREADS, 0, stream>>>(points, idx, out, N, M, C);
   PS_LAUNCH_CHECK();
   return PS_OK;
 }

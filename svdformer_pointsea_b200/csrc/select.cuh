@@ -39,6 +39,10 @@ __device__ __forceinline__ void warp_sort_pairs(float& d, int& i, int lane) {
 // Lanes 0..k-1 hold the k best in ascending (d, i) order (k <= 32; other lanes are ignored).
 // Afterwards lanes 0..k-1 hold the same set in torch.topk's order (see PS_ORDER_TOPK above).
 __device__ __forceinline__ void warp_torch_topk_order(float& d, int& i, int lane, int k) {
+  // All k distances distinct (the common case): any correct sorting network gives the ascending order we
+  // already hold, so torch's result is identical and the emulation below is skipped.
+  const float prev = __shfl_up_sync(0xffffffffu, d, 1);
+  if (__ballot_sync(0xffffffffu, lane > 0 && lane < k && prev == d) == 0u) return;
   const float kth = __shfl_sync(0xffffffffu, d, k - 1);
   // 1. torch's gather order: (d == kth, index) ascending; invalid lanes to the end
   unsigned key_hi = lane < k ? (d == kth ? 1u : 0u) : 2u;

@@ -261,3 +261,33 @@ def test_patch_model_utils_rebinds_names():
     ps.patch_model_utils(m)
     assert m.query_knn is pu.query_knn and m.sample_and_group_knn is ps.sample_and_group_knn
     assert m.EdgeConv.forward is ps.EdgeConv.forward
+
+
+# ---------------------------------------------------------------- hub sources in the grouping backward
+@pytest.mark.parametrize("B,C,N,S,K,mode", [(2, 16, 512, 512, 16, "hubs"), (2, 8, 2048, 2048, 16, "zeros"), (3, 12, 3000, 2048, 16, "hubs"),
+                                            (2, 16, 512, 512, 16, "knn64")])
+def test_group_backward_with_hub_sources(B, C, N, S, K, mode):
+    """Inverse-index path with sources referenced hundreds or thousands of times (kNN hubs in feature
+    space; a ball query that found nothing returns index 0 everywhere): exact result, bounded time, and
+    bit-identical on repetition."""
+    g = torch.Generator().manual_seed(S + K)
+    if mode == "zeros":
+        idx = torch.zeros(B, S, K, dtype=torch.int32)
+    elif mode == "knn64":
+        f = torch.randn(B, 64, N, generator=g).to(DEV)
+        idx = mo.knn_self(f, K).cpu()
+    else:
+        idx = torch.randint(0, N, (B, S, K), generator=g, dtype=torch.int32)
+        hub = torch.rand(B, S, K, generator=g) < 0.3
+        idx[hub] = (torch.randint(0, 5, (int(hub.sum()),), generator=g, dtype=torch.int32) * 7)
+    go = torch.randn(B, C, S, K, generator=g)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    got = pu.group_grad_raw(go.to(DEV), idx.to(DEV), N)
+    e0.record()
+    got2 = pu.group_grad_raw(go.to(DEV), idx.to(DEV), N)
+    e1.record()
+    torch.cuda.synchronize()
+    assert e0.elapsed_time(e1) < 20.0, "hub lists must not make the inverse-index build quadratic"
+    assert torch.equal(got, got2)
+    want = O.group_grad(go.numpy(), idx.numpy(), N)
+    assert rel(got.cpu().numpy(), want) < 1e-5

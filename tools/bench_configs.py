@@ -93,12 +93,15 @@ def c4_arm(arm, iters, knn):
         import pointnet2_ops  # noqa: F401  (binds the reference wrappers to the reference kernels)
         pointnet2_ops._ext = ref_pn
     from types import SimpleNamespace as NS
-    from models.SVDFormer import Model
     import models.model_utils as mu
-    from utils.loss_utils import get_loss
     if knn == "ours" and arm == "ours":
         import svdformer_pointsea_b200 as ps
         mu.query_knn = ps.query_knn  # the optional one-line swap of INTEGRATION.md
+    if knn == "all" and arm == "ours":
+        import svdformer_pointsea_b200 as ps
+        ps.patch_model_utils(mu)     # every call-site function (kNN, sample_and_group_knn, EdgeConv front, ...)
+    from models.SVDFormer import Model  # after the patch: it does `from models.model_utils import *`
+    from utils.loss_utils import get_loss
     cfg = NS(NETWORK=NS(step1=4, step2=8, merge_points=512, local_points=512, view_distance=0.7),
              DATASET=NS(TEST_DATASET="ShapeNet"))
     torch.manual_seed(1)
@@ -138,7 +141,7 @@ def c4(args):
     if args.arm != "both":
         return c4_arm(args.arm, args.iters, args.knn)
     lines = []
-    for arm, knn in (("ours", "torch"), ("ours", "ours"), ("ref", "torch")):
+    for arm, knn in (("ours", "torch"), ("ours", "ours"), ("ours", "all"), ("ref", "torch")):
         p = subprocess.run([sys.executable, __file__, "c4", "--arm", arm, "--iters", str(args.iters), "--knn", knn],
                            capture_output=True, text=True)
         last = [ln for ln in p.stdout.strip().splitlines() if ln.startswith("{")]
@@ -207,7 +210,7 @@ if __name__ == "__main__":
     ap = argparse.ArgumentParser()
     ap.add_argument("config", choices=["c4", "c5"])
     ap.add_argument("--arm", default="both", choices=["ours", "ref", "both"])
-    ap.add_argument("--knn", default="torch", choices=["torch", "ours"])
+    ap.add_argument("--knn", default="torch", choices=["torch", "ours", "all"])
     ap.add_argument("--iters", type=int, default=5)
     ap.add_argument("--no-check", action="store_true")
     a = ap.parse_args()
