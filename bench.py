@@ -139,7 +139,7 @@ def run_ours(args):
     import svdformer_pointsea_b200 as ps
     from svdformer_pointsea_b200 import _lib as L
     from svdformer_pointsea_b200 import pointnet2_utils as pu
-    from svdformer_pointsea_b200.dist import chamfer_metric_means
+    from svdformer_pointsea_b200.dist import PipelinedSums
 
     rank = int(os.environ.get("RANK", 0))
     local_rank = int(os.environ.get("LOCAL_RANK", 0))
@@ -149,6 +149,8 @@ def run_ours(args):
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
     if world > 1:
+        if os.environ.get("NCCL_DEBUG", "VERSION").upper() == "VERSION":
+            os.environ["NCCL_DEBUG"] = "WARN"  # keep NCCL's version banner off stdout: rank 0 prints ONE JSON line
         dist.init_process_group("nccl", device_id=dev)
     ps.load_library()
     peaks, peaks_src = measured_peaks()
@@ -164,6 +166,7 @@ def run_ours(args):
         flush_buf.zero_()
 
     fwd_ms = []
+    reducer = PipelinedSums()
 
     def step(record_fwd=False):
         if record_fwd:
@@ -173,13 +176,23 @@ def run_ours(args):
         if record_fwd:
             e1.record()
             fwd_ms.append((e0, e1))
-        means = chamfer_metric_means(d1, d2)  # fused partial sums + ONE all-reduce when world > 1
+        # fused partial sums + ONE all-reduce when world > 1, issued asynchronously and joined one step
+        # later (the reduced loss is an output of the step, not an input of its backward)
+        vec = ps.chamfer_sums(d1, d2)
+        if args.reduce == "pipelined":
+            prev = reducer.submit(vec)
+        elif args.reduce == "inline" and world > 1:
+            dist.all_reduce(vec, op=dist.ReduceOp.SUM)
+            prev = vec
+        else:
+            prev = vec
         g1, g2 = ps.chamfer_backward(x1, x2, gd1, gd2, i1, i2)
-        return means, g1, g2
+        return prev, g1, g2
 
     # ---- warm-up, fp32 peak, then the timed K steps -------------------------------------------
     for _ in range(max(args.warmup, 3)):
         step()
+    reducer.flush()
     torch.cuda.synchronize()
     fp32_peak = L.measure_fp32_peak(local_rank, 5)
     if world > 1:
@@ -189,17 +202,21 @@ def run_ours(args):
     sampler.start()
     L.launch_count(reset=True)
     evs = []
+    t_host0 = time.perf_counter()
     for _ in range(args.steps):
         flush()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
         step(record_fwd=True)
+        if len(evs) == args.steps - 1:
+            reducer.flush()  # the last step's reduction completes inside the timed region
         e1.record()
         evs.append((e0, e1))
     torch.cuda.synchronize()
     launches = L.launch_count(reset=True)
     if world > 1:
         dist.barrier()
+    host_ms = (time.perf_counter() - t_host0) * 1e3 / args.steps
     total_ms = sum(a.elapsed_time(b) for a, b in evs)
     fwd_avg_ms = sum(a.elapsed_time(b) for a, b in fwd_ms) / len(fwd_ms)
     tt = torch.tensor([total_ms], device=dev, dtype=torch.float64)
@@ -246,7 +263,8 @@ def run_ours(args):
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": {"workload": WORKLOAD, "B_per_gpu": B, "N": N, "M": M,
                    "l2": "256 MB buffer written between timed iterations (L2 flush)",
-                   "collective": "one all-reduce(sum) of 6 doubles (loss partial sums + counts) per step" if world > 1 else "none (1 GPU)",
+                   "collective": "one all-reduce(sum) of 6 doubles (loss partial sums + counts) per step, issued asynchronously on "
+                                 "NCCL's stream and joined one step later (the last one inside the timed region)" if world > 1 else "none (1 GPU)",
                    "parallelism": f"batch-sharded x{world}"},
         "e2e": {"value": round(e2e_value, 2), "unit": "Gpair/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                 "api": "svdformer_pointsea_b200.chamfer_host -> ps_chamfer_host (pinned host buffers in and out, chunked "
@@ -254,7 +272,7 @@ def run_ours(args):
                 "chunk": args.e2e_chunk, "ms_per_step": round(sum(e2e_ms) / len(e2e_ms), 4),
                 "serial_ms_per_step": round(sum(serial_ms) / len(serial_ms), 4),
                 "serial_note": "same work as copy-in, device entry points, copy-out on one stream (no overlap)"},
-        "gpu_launches": int(launches),
+        "gpu_launches": int(launches), "host_issue_ms_per_step": round(host_ms, 4), "reduce": args.reduce if world > 1 else "none (1 GPU)",
         "clocks": clocks,
         "roofline": {"kernel": "chamfer_sym_kernel (forward, both directions in one pass)", "bound": "fp32",
                      "achieved": round(pairs_per_step * FLOP_PER_PAIR / (fwd_avg_ms * 1e-3) / 1e12, 2),
@@ -451,6 +469,8 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--e2e-chunk", type=int, default=0, help="clouds per pipeline chunk of the host-buffer call (0: library default)")
+    ap.add_argument("--reduce", default="pipelined", choices=["pipelined", "inline", "none"],
+                    help="how the per-step all-reduce of the loss sums is issued when N > 1 (A/B; 'none' is not a valid bench)")
     ap.add_argument("--no-ops", action="store_true", help="skip the FPS/kNN/gather/group section")
     ap.add_argument("--no-cpu", action="store_true", help="skip the CPU baseline legs")
     args = ap.parse_args()

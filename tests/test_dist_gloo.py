@@ -77,3 +77,43 @@ def test_loss_sums_single_process_and_autograd():
     m = sums.reduce()["t"]
     m.backward()
     assert torch.allclose(m, (x * 2).mean()) and torch.allclose(x.grad, torch.full_like(x, 2 / 21))
+
+
+def _pipelined_worker(rank, world, port, q):
+    import torch.distributed as dist
+    from svdformer_pointsea_b200.dist import PipelinedSums
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    red = PipelinedSums()
+    outs = []
+    for step in range(4):
+        vec = torch.tensor([float(rank + 1) * (step + 1), 1.0], dtype=torch.float64)
+        prev = red.submit(vec)  # result of the PREVIOUS step
+        outs.append(None if prev is None else prev.tolist())
+    outs.append(red.flush().tolist())
+    assert red.flush() is None
+    q.put((rank, outs))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_pipelined_sums_return_the_previous_steps_reduction():
+    world = 2
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_pipelined_worker, args=(r, world, port, q)) for r in range(world)]
+    [p.start() for p in procs]
+    res = sorted(q.get(timeout=120) for _ in range(world))
+    [p.join(timeout=60) for p in procs]
+    for _, outs in res:
+        assert outs[0] is None
+        # step s reduces (1 + 2) * (s + 1) and the two counts
+        assert outs[1:] == [[3.0 * (s + 1), 2.0] for s in range(4)]
+
+
+def test_pipelined_sums_without_a_process_group():
+    from svdformer_pointsea_b200.dist import PipelinedSums
+    red = PipelinedSums()
+    a, b = torch.tensor([1.0, 2.0]), torch.tensor([3.0, 4.0])
+    assert red.submit(a) is None and red.submit(b) is a and red.flush() is b
