@@ -291,3 +291,69 @@ def test_group_backward_with_hub_sources(B, C, N, S, K, mode):
     assert torch.equal(got, got2)
     want = O.group_grad(go.numpy(), idx.numpy(), N)
     assert rel(got.cpu().numpy(), want) < 1e-5
+
+
+# ---------------------------------------------------------------- edge cases of the new entry points
+def test_next_ops_empty_and_degenerate_inputs():
+    x = torch.randn(0, 8, 16, device=DEV)
+    assert mo.knn_feat_raw(x, x, 4, channel_major=True).shape == (0, 16, 4)
+    assert mo.edge_features_raw(x, torch.zeros(0, 16, 4, dtype=torch.int32, device=DEV)).shape == (0, 16, 16, 4)
+    pts = torch.randn(2, 9, 5, device=DEV)
+    assert ps.index_points(pts, torch.zeros(2, 0, dtype=torch.long, device=DEV)).shape == (2, 0, 5)
+    assert ps.chamfer_metrics_raw(torch.zeros(0, 4, device=DEV), torch.zeros(0, 6, device=DEV)).shape == (0, 8)
+    # k == N (every point is a neighbour), one point, one channel
+    y = torch.randn(2, 1, 7, device=DEV)
+    got = mo.knn_feat_raw(y, y, 7, channel_major=True, order=0).cpu().numpy()
+    want = O.knn_feat(np.ascontiguousarray(y.cpu().numpy().transpose(0, 2, 1)), np.ascontiguousarray(y.cpu().numpy().transpose(0, 2, 1)), 7, order=0)
+    assert np.array_equal(got, want)
+    one = torch.randn(1, 4, 1, device=DEV)
+    assert mo.knn_feat_raw(one, one, 1, channel_major=True).cpu().tolist() == [[[0]]]
+    # all distances identical (all-zero features): torch.topk order of a full tie
+    z0 = torch.zeros(1, 40, 6, device=DEV)
+    assert torch.equal(ps.query_knn_point(8, z0, z0), O.torch_query_knn_point(8, z0, z0))
+    z3 = torch.zeros(1, 50, 3, device=DEV)
+    assert torch.equal(ps.query_knn_point(16, z3, z3), O.torch_query_knn_point(16, z3, z3))
+
+
+def test_next_ops_unaligned_views_and_odd_sizes():
+    """Odd N / K / C (no 128-bit path, no bulk copies) and tensors that start 4 bytes into an allocation."""
+    g = torch.Generator().manual_seed(5)
+    B, C, N, K = 2, 7, 301, 3
+    base = torch.randn(B * C * N + 1, generator=g).to(DEV)
+    x = base[1:].view(B, C, N)                       # contiguous but only 4-byte aligned
+    idx_base = torch.randint(0, N, (B * N * K + 1,), generator=g, dtype=torch.int32).to(DEV)
+    idx = idx_base[1:].view(B, N, K)
+    out = mo.edge_features_raw(x, idx)
+    assert np.array_equal(out.cpu().numpy(), O.edge_features(x.cpu().numpy(), idx.cpu().numpy()))
+    go_base = torch.randn(B * 2 * C * N * K + 1, generator=g).to(DEV)
+    go = go_base[1:].view(B, 2 * C, N, K)
+    gx = mo.edge_features_grad_raw(go, idx)
+    assert rel(gx.cpu().numpy(), O.edge_features_grad(go.cpu().numpy(), idx.cpu().numpy())) < 1e-5
+    kn = mo.knn_feat_raw(x, x, 5, channel_major=True, order=1).cpu().numpy()
+    xt = np.ascontiguousarray(x.cpu().numpy().transpose(0, 2, 1))
+    assert np.array_equal(kn, O.knn_feat(xt, xt, 5, order=1))
+    pts = base[1:1 + B * 43 * 7].view(B, 43, 7)
+    ii = torch.randint(0, 43, (B, 29), generator=g).to(DEV)
+    assert torch.equal(ps.index_points(pts, ii), O.torch_index_points(pts, ii))
+    # K = 12 (multiple of 4, not a power of two): vector forward, scalar backward finish
+    idx12 = torch.randint(0, 64, (2, 64, 12), generator=g, dtype=torch.int32).to(DEV)
+    x12 = torch.randn(2, 8, 64, generator=g).to(DEV)
+    assert np.array_equal(mo.edge_features_raw(x12, idx12).cpu().numpy(), O.edge_features(x12.cpu().numpy(), idx12.cpu().numpy()))
+    go12 = torch.randn(2, 16, 64, 12, generator=g).to(DEV)
+    assert rel(mo.edge_features_grad_raw(go12, idx12).cpu().numpy(), O.edge_features_grad(go12.cpu().numpy(), idx12.cpu().numpy())) < 1e-5
+
+
+def test_feature_knn_unsupported_shapes_raise():
+    with pytest.raises(ps.PointSeaError):   # C >= 128 must be a multiple of 4 (torch's ragged vector reduction is not reproduced)
+        x = torch.randn(2, 130, 64, device=DEV)
+        mo.knn_feat_raw(x, x, 4, channel_major=True)
+    with pytest.raises(ps.PointSeaError):   # too many reference points for the shared-memory distance block
+        x = torch.randn(1, 4, 7000, device=DEV)
+        mo.knn_feat_raw(x, x, 4, channel_major=True)
+
+
+def test_patch_loss_utils_rebinds_names():
+    import types
+    m = types.ModuleType("fake_loss_utils")
+    ps.patch_loss_utils(m)
+    assert m.calc_dcd is ps.calc_dcd and m.calc_cd is ps.calc_cd and m.fscore is ps.fscore
