@@ -148,6 +148,10 @@ def run_ours(args):
         raise SystemExit("bench.py needs a CUDA device; the product path has no CPU fallback")
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
+    numa_cpus = None
+    if world > 1:
+        from svdformer_pointsea_b200.dist import bind_to_gpu_numa_node
+        numa_cpus = bind_to_gpu_numa_node(local_rank)  # before any pinned allocation (first touch)
     if world > 1:
         if os.environ.get("NCCL_DEBUG", "VERSION").upper() == "VERSION":
             os.environ["NCCL_DEBUG"] = "WARN"  # keep NCCL's version banner off stdout: rank 0 prints ONE JSON line
@@ -167,26 +171,30 @@ def run_ours(args):
 
     fwd_ms = []
     reducer = PipelinedSums()
+    fwd_out = (torch.empty(B, N, device=dev), torch.empty(B, M, device=dev),
+               torch.empty(B, N, device=dev, dtype=torch.int32), torch.empty(B, M, device=dev, dtype=torch.int32))
+    bwd_out = (torch.empty(B, N, 3, device=dev), torch.empty(B, M, 3, device=dev))
+    sum_bufs = [torch.empty(6, device=dev, dtype=torch.float64) for _ in range(2)]  # step i's sums stay alive while in flight
+    step_no = [0]
 
     def step(record_fwd=False):
         if record_fwd:
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             e0.record()
-        d1, d2, i1, i2 = ps.chamfer_forward(x1, x2)
+        # caller-allocated outputs, as the reference's pybind forward/backward take them (chamfer_cuda.cpp:17-28)
+        d1, d2, i1, i2 = ps.chamfer_forward(x1, x2, out=fwd_out)
         if record_fwd:
             e1.record()
             fwd_ms.append((e0, e1))
-        # fused partial sums + ONE all-reduce when world > 1, issued asynchronously and joined one step
-        # later (the reduced loss is an output of the step, not an input of its backward)
-        vec = ps.chamfer_sums(d1, d2)
-        if args.reduce == "pipelined":
-            prev = reducer.submit(vec)
-        elif args.reduce == "inline" and world > 1:
+        # fused partial sums + ONE all-reduce when world > 1.  The reduced loss is an output of the step, not
+        # an input of its backward: the collective is issued after the backward's launches (its host-side
+        # cost must not delay them), runs on NCCL's stream, and is joined one step later.
+        vec = ps.chamfer_sums(d1, d2, out=sum_bufs[step_no[0] & 1])
+        step_no[0] += 1
+        if args.reduce == "inline" and world > 1:
             dist.all_reduce(vec, op=dist.ReduceOp.SUM)
-            prev = vec
-        else:
-            prev = vec
-        g1, g2 = ps.chamfer_backward(x1, x2, gd1, gd2, i1, i2)
+        g1, g2 = ps.chamfer_backward(x1, x2, gd1, gd2, i1, i2, out=bwd_out)
+        prev = reducer.submit(vec) if args.reduce == "pipelined" else vec
         return prev, g1, g2
 
     # ---- warm-up, fp32 peak, then the timed K steps -------------------------------------------
@@ -269,7 +277,7 @@ def run_ours(args):
         "e2e": {"value": round(e2e_value, 2), "unit": "Gpair/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                 "api": "svdformer_pointsea_b200.chamfer_host -> ps_chamfer_host (pinned host buffers in and out, chunked "
                        "H2D / kernels / D2H overlap on three streams)",
-                "chunk": args.e2e_chunk, "ms_per_step": round(sum(e2e_ms) / len(e2e_ms), 4),
+                "chunk": args.e2e_chunk, "numa_bound_cpus": (len(numa_cpus) if numa_cpus else None), "ms_per_step": round(sum(e2e_ms) / len(e2e_ms), 4),
                 "serial_ms_per_step": round(sum(serial_ms) / len(serial_ms), 4),
                 "serial_note": "same work as copy-in, device entry points, copy-out on one stream (no overlap)"},
         "gpu_launches": int(launches), "host_issue_ms_per_step": round(host_ms, 4), "reduce": args.reduce if world > 1 else "none (1 GPU)",

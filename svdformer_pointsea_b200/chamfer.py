@@ -13,8 +13,16 @@ from torch.autograd import Function
 from . import _lib as L
 
 
-def chamfer_forward(xyz1, xyz2):
-    """(dist1, dist2, idx1, idx2) for xyz1 (B,N,3), xyz2 (B,M,3); no autograd."""
+def _check_out(t, name, dtype, shape, like):
+    L.require(t, name, dtype, len(shape))
+    if tuple(t.shape) != tuple(shape) or t.device != like.device:
+        raise L.PointSeaError(f"{name} must be a {tuple(shape)} tensor on {like.device}, got {tuple(t.shape)} on {t.device}")
+    return t
+
+
+def chamfer_forward(xyz1, xyz2, out=None):
+    """(dist1, dist2, idx1, idx2) for xyz1 (B,N,3), xyz2 (B,M,3); no autograd.  `out` may carry the four
+    preallocated outputs, as the reference's pybind `chamfer_3D.forward` takes them (chamfer_cuda.cpp:17-19)."""
     L.require(xyz1, "xyz1", torch.float32, 3)
     L.require(xyz2, "xyz2", torch.float32, 3)
     if xyz1.size(2) != 3 or xyz2.size(2) != 3 or xyz1.size(0) != xyz2.size(0):
@@ -22,17 +30,26 @@ def chamfer_forward(xyz1, xyz2):
     dev = L.same_device(xyz1, xyz2)
     B, N, _ = xyz1.shape
     M = xyz2.size(1)
-    dist1 = torch.empty(B, N, device=xyz1.device, dtype=torch.float32)
-    dist2 = torch.empty(B, M, device=xyz1.device, dtype=torch.float32)
-    idx1 = torch.empty(B, N, device=xyz1.device, dtype=torch.int32)
-    idx2 = torch.empty(B, M, device=xyz1.device, dtype=torch.int32)
+    if out is not None:
+        dist1, dist2, idx1, idx2 = out
+        _check_out(dist1, "dist1", torch.float32, (B, N), xyz1)
+        _check_out(dist2, "dist2", torch.float32, (B, M), xyz1)
+        _check_out(idx1, "idx1", torch.int32, (B, N), xyz1)
+        _check_out(idx2, "idx2", torch.int32, (B, M), xyz1)
+    else:
+        dist1 = torch.empty(B, N, device=xyz1.device, dtype=torch.float32)
+        dist2 = torch.empty(B, M, device=xyz1.device, dtype=torch.float32)
+        idx1 = torch.empty(B, N, device=xyz1.device, dtype=torch.int32)
+        idx2 = torch.empty(B, M, device=xyz1.device, dtype=torch.int32)
     rc = L.load().ps_chamfer_fwd(L.ptr(xyz1), L.ptr(xyz2), L.ptr(dist1), L.ptr(dist2), L.ptr(idx1), L.ptr(idx2),
                                  B, N, M, dev, L.stream_ptr(dev))
     L.check(rc, "ps_chamfer_fwd")
     return dist1, dist2, idx1, idx2
 
 
-def chamfer_backward(xyz1, xyz2, graddist1, graddist2, idx1, idx2):
+def chamfer_backward(xyz1, xyz2, graddist1, graddist2, idx1, idx2, out=None):
+    """(gradxyz1, gradxyz2); `out` may carry the two preallocated gradient buffers (they are overwritten, no
+    zero-filling needed — the reference's `chamfer_3D.backward` needs them pre-zeroed, dist_chamfer_3D.py:56-60)."""
     L.require(graddist1, "graddist1", torch.float32, 2)
     L.require(graddist2, "graddist2", torch.float32, 2)
     L.require(idx1, "idx1", torch.int32, 2)
@@ -40,22 +57,30 @@ def chamfer_backward(xyz1, xyz2, graddist1, graddist2, idx1, idx2):
     dev = L.same_device(xyz1, xyz2, graddist1, graddist2, idx1, idx2)
     B, N, _ = xyz1.shape
     M = xyz2.size(1)
-    gradxyz1 = torch.empty_like(xyz1)
-    gradxyz2 = torch.empty_like(xyz2)
+    if out is not None:
+        gradxyz1, gradxyz2 = out
+        _check_out(gradxyz1, "gradxyz1", torch.float32, (B, N, 3), xyz1)
+        _check_out(gradxyz2, "gradxyz2", torch.float32, (B, M, 3), xyz1)
+    else:
+        gradxyz1 = torch.empty_like(xyz1)
+        gradxyz2 = torch.empty_like(xyz2)
     rc = L.load().ps_chamfer_bwd(L.ptr(xyz1), L.ptr(xyz2), L.ptr(graddist1), L.ptr(graddist2), L.ptr(idx1),
                                  L.ptr(idx2), L.ptr(gradxyz1), L.ptr(gradxyz2), B, N, M, dev, L.stream_ptr(dev))
     L.check(rc, "ps_chamfer_bwd")
     return gradxyz1, gradxyz2
 
 
-def chamfer_sums(dist1, dist2):
+def chamfer_sums(dist1, dist2, out=None):
     """One-launch reduction of Chamfer outputs: float64 tensor [sum sqrt(d1), sum sqrt(d2), sum d1,
     sum d2, numel(d1), numel(d2)] on the device (no host sync, no autograd) — the partial sums behind
     utils/loss_utils.py:10-31 and the only data the multi-GPU path all-reduces."""
     L.require(dist1, "dist1", torch.float32, dist1.dim())
     L.require(dist2, "dist2", torch.float32, dist2.dim())
     dev = L.same_device(dist1, dist2)
-    out = torch.empty(6, device=dist1.device, dtype=torch.float64)
+    if out is None:
+        out = torch.empty(6, device=dist1.device, dtype=torch.float64)
+    else:
+        _check_out(out, "out", torch.float64, (6,), dist1)
     rc = L.load().ps_chamfer_sums(L.ptr(dist1), L.ptr(dist2), L.ptr(out), dist1.numel(), dist2.numel(), dev,
                                   L.stream_ptr(dev))
     L.check(rc, "ps_chamfer_sums")

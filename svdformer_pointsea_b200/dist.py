@@ -10,6 +10,36 @@ import torch
 import torch.distributed as dist
 
 
+def bind_to_gpu_numa_node(device_index):
+    """Pin the calling process to the CPU cores NVML reports as local to GPU `device_index` (its NUMA node).
+    With one process per GPU on a multi-socket host, pinned host buffers are then first-touched on the
+    socket the GPU hangs off, so host<->device copies of different ranks do not cross the inter-socket link.
+    Call before allocating pinned memory.  Returns the CPU set, or None when NVML / affinity is unavailable
+    (containers may forbid it) — never raises."""
+    try:
+        import os
+        import pynvml
+        pynvml.nvmlInit()
+        vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+        phys = device_index
+        if vis:
+            try:
+                phys = int(vis.split(",")[device_index])
+            except Exception:
+                phys = device_index
+        h = pynvml.nvmlDeviceGetHandleByIndex(phys)
+        ncpu = os.cpu_count() or 1
+        words = pynvml.nvmlDeviceGetCpuAffinity(h, (ncpu + 63) // 64)
+        cpus = {64 * w + b for w, mask in enumerate(words) for b in range(64) if (mask >> b) & 1}
+        allowed = os.sched_getaffinity(0)
+        cpus = (cpus & allowed) or None
+        if cpus:
+            os.sched_setaffinity(0, cpus)
+        return cpus
+    except Exception:
+        return None
+
+
 def shard_bounds(B, rank, world):
     """Clouds [lo, hi) of a batch of B owned by `rank` out of `world` (uneven shards allowed)."""
     return (B * rank) // world, (B * (rank + 1)) // world
