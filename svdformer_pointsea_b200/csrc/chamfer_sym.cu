@@ -40,7 +40,34 @@ struct SymParams {
   int natiles;      // A tiles per cloud
   int nsplit;       // B splits per cloud
   int split_len;    // multiple of CS_STEP
+  // Tail balancing: CTAs are dispatched in blockIdx order, so the last `units - ubig` units form the final,
+  // partially filled wave.  Each of them is cut into `fsub` sub-units of sub_len targets (own CTAs), which
+  // lets that wave finish in ~1/fsub of a full unit's time instead of a whole one.
+  int ubig;         // units [0, ubig) run whole
+  int fsub;         // sub-units per tail unit (1: none)
+  int sub_len;      // multiple of CS_STEP
 };
+
+// blockIdx -> (cloud, A tile, [t0, t1) of B); false when the sub-unit is empty
+__device__ __forceinline__ bool sym_decode_unit(const SymParams& p, int& b, int& at, int& t0, int& t1) {
+  int unit = blockIdx.x, sub = -1;
+  if (unit >= p.ubig) {
+    const int r = unit - p.ubig;
+    unit = p.ubig + r / p.fsub;
+    sub = r % p.fsub;
+  }
+  const int split = unit % p.nsplit;
+  unit /= p.nsplit;
+  at = unit % p.natiles;
+  b = unit / p.natiles;
+  t0 = split * p.split_len;
+  t1 = min(p.nb, t0 + p.split_len);
+  if (sub >= 0) {
+    t0 += sub * p.sub_len;
+    t1 = min(t1, t0 + p.sub_len);
+  }
+  return t0 < t1;
+}
 
 static __global__ void sym_unpack_kernel(const u64* __restrict__ keys, float* __restrict__ dist,
                                          int* __restrict__ idx, size_t n) {
@@ -64,11 +91,8 @@ __global__ void __launch_bounds__(CS_THREADS, 2) chamfer_sym_kernel(const SymPar
   float* ay = ax + TA;
   float* az = ay + TA;
 
-  int unit = blockIdx.x;
-  const int split = unit % p.nsplit;
-  unit /= p.nsplit;
-  const int at = unit % p.natiles;
-  const int b = unit / p.natiles;
+  int b, at, t0, t1;
+  if (!sym_decode_unit(p, b, at, t0, t1)) return;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int na = p.na, nb = p.nb;
   const float INF = __int_as_float(0x7f800000);
@@ -93,8 +117,6 @@ __global__ void __launch_bounds__(CS_THREADS, 2) chamfer_sym_kernel(const SymPar
     cstep[q] = 0;
   }
 
-  const int t0 = split * p.split_len;
-  const int t1 = min(nb, t0 + p.split_len);
   const float* bcloud = p.b + (size_t)b * nb * 3;
 
   for (int ts = t0; ts < t1; ts += CS_TILE) {
@@ -269,11 +291,8 @@ __global__ void __launch_bounds__(CS_THREADS, QP >= 8 ? 2 : (QP == 4 ? 3 : 4)) c
   // [q][thread]: step of the last strict improvement of best[q]
   const unsigned cstep_addr = smem_u32(reinterpret_cast<int*>(az + TA) + threadIdx.x);
 
-  int unit = blockIdx.x;
-  const int split = unit % p.nsplit;
-  unit /= p.nsplit;
-  const int at = unit % p.natiles;
-  const int b = unit / p.natiles;
+  int b, at, t0, t1;
+  if (!sym_decode_unit(p, b, at, t0, t1)) return;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int na = p.na, nb = p.nb;
   const float INF = __int_as_float(0x7f800000);
@@ -299,8 +318,6 @@ __global__ void __launch_bounds__(CS_THREADS, QP >= 8 ? 2 : (QP == 4 ? 3 : 4)) c
     nax[pp] = pack2(-x[0], -x[1]); nay[pp] = pack2(-y[0], -y[1]); naz[pp] = pack2(-z[0], -z[1]);
   }
 
-  const int t0 = split * p.split_len;
-  const int t1 = min(nb, t0 + p.split_len);
   const float* bcloud = p.b + (size_t)b * nb * 3;
 
   for (int ts = t0; ts < t1; ts += CP_TILE) {
@@ -498,7 +515,27 @@ int chamfer_fwd_symmetric(const float* xyz1, const float* xyz2, float* dist1, fl
   PS_CUDA(cudaMemsetAsync(scratch, 0xFF, (nka + nkb) * sizeof(u64), stream));
   p.keys_a = scratch;
   p.keys_b = scratch + nka;
-  const int grid = B * p.natiles * p.nsplit;
+  // tail balancing (see SymParams): cut the units of the last, partially filled wave
+  const long long units = (long long)B * p.natiles * p.nsplit;
+  p.ubig = (int)units;
+  p.fsub = 1;
+  p.sub_len = p.split_len;
+  {
+    int tail = 1;
+    if (const char* e = getenv("PS_CHAMFER_TAIL")) tail = atoi(e);
+    const long long full = units / slots, rem = units % slots;
+    if (tail && full >= 1 && rem > 0) {
+      double best = (double)full + 1.0;
+      for (int f = 2; f <= 4; f *= 2) {
+        const int sl = (ceil_div(p.split_len, f) + CS_STEP - 1) / CS_STEP * CS_STEP;
+        if (sl < 128) break;
+        const double cost = (double)full + (double)ceil_div(rem * f, slots) / f + 0.02 * f;  // small bias against needless cuts
+        if (cost < best - 1e-9) { best = cost; p.fsub = f; p.sub_len = sl; }
+      }
+      if (p.fsub > 1) p.ubig = (int)(units - rem);
+    }
+  }
+  const int grid = (int)(p.ubig + (units - p.ubig) * p.fsub);
   int rc;
   if (variant == 2) {
     if (Q == 16) rc = launch_symp<8>(p, grid, stream);
