@@ -242,9 +242,17 @@ def run_ours(args):
     h2d = sum(t.numel() * t.element_size() for t in (h_x1, h_x2, h_gd1, h_gd2))
     d2h = sum(t.numel() * t.element_size() for t in h_out)
 
+    h_sums = torch.empty(6, dtype=torch.float64).pin_memory()
+    d2h_step = h_sums.numel() * h_sums.element_size()
+
     def e2e_step():
-        # the public host-buffer call: chunked upload / kernels / download on three streams
-        # (csrc/host_pipeline.cu); non-blocking, so the CUDA events of `timed` bracket all of it
+        # the public host-buffer training step: clouds + upstream gradients uploaded in chunks, forward, loss sums,
+        # backward; the step's RESULT (six loss sums) is read back, the gradients stay on the device for the
+        # optimizer (csrc/host_pipeline.cu).  Non-blocking: the CUDA events of `timed` bracket all of it.
+        ps.chamfer_host_step(h_x1, h_x2, h_gd1, h_gd2, grad_out=bwd_out, sums_out=h_sums, chunk=args.e2e_chunk, blocking=False)
+
+    def e2e_full_step():
+        # same, with EVERY output downloaded as well (dist, idx, gradients: 11.8 MB more over PCIe per step)
         ps.chamfer_host(h_x1, h_x2, h_gd1, h_gd2, out=h_out, chunk=args.e2e_chunk, blocking=False)
 
     def e2e_serial_step():
@@ -258,6 +266,7 @@ def run_ours(args):
             dst.copy_(src, non_blocking=True)
 
     serial_ms = timed(e2e_serial_step, max(3, args.steps // 4), 3, flush)
+    full_ms = timed(e2e_full_step, max(5, args.steps // 2), 3, flush)
     e2e_ms = timed(e2e_step, args.steps, max(args.warmup, 3), flush)
     te = torch.tensor([sum(e2e_ms)], device=dev, dtype=torch.float64)
     if world > 1:
@@ -274,9 +283,14 @@ def run_ours(args):
                    "collective": "one all-reduce(sum) of 6 doubles (loss partial sums + counts) per step, issued asynchronously on "
                                  "NCCL's stream and joined one step later (the last one inside the timed region)" if world > 1 else "none (1 GPU)",
                    "parallelism": f"batch-sharded x{world}"},
-        "e2e": {"value": round(e2e_value, 2), "unit": "Gpair/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                "api": "svdformer_pointsea_b200.chamfer_host -> ps_chamfer_host (pinned host buffers in and out, chunked "
-                       "H2D / kernels / D2H overlap on three streams)",
+        "e2e": {"value": round(e2e_value, 2), "unit": "Gpair/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h_step,
+                "api": "svdformer_pointsea_b200.chamfer_host_step -> ps_chamfer_host_step (pinned host clouds + upstream "
+                       "gradients in, the six loss sums out; gradients left in device buffers; chunked H2D / kernels / D2H "
+                       "overlap on three streams, one CUDA graph launch per step)",
+                "full_readback_ms_per_step": round(sum(full_ms) / len(full_ms), 4),
+                "full_readback_gpair_per_s": round(pairs_per_step / (sum(full_ms) / len(full_ms) * 1e-3) / 1e9, 2),
+                "full_readback_d2h_bytes_per_step": d2h,
+                "full_readback_note": "ps_chamfer_host: dist, idx and gradients downloaded too (rank-local, not max over ranks)",
                 "chunk": args.e2e_chunk, "numa_bound_cpus": (len(numa_cpus) if numa_cpus else None), "ms_per_step": round(sum(e2e_ms) / len(e2e_ms), 4),
                 "serial_ms_per_step": round(sum(serial_ms) / len(serial_ms), 4),
                 "serial_note": "same work as copy-in, device entry points, copy-out on one stream (no overlap)"},

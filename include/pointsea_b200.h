@@ -81,6 +81,18 @@ int ps_chamfer_host(const float* xyz1, const float* xyz2, float* dist1, float* d
                     int* idx2, const float* graddist1, const float* graddist2, float* gradxyz1,
                     float* gradxyz2, int B, int N, int M, int chunk, int dev, void* stream);
 
+/* Training-style step on HOST-resident inputs: the clouds (and, for the backward, the upstream gradients) are
+ * uploaded in chunks exactly as in ps_chamfer_host, but only the step's RESULT crosses PCIe on the way back —
+ * sums6 (HOST, 6 doubles, the layout of ps_chamfer_sums: what the loss / metric of utils/loss_utils.py:10-31 is
+ * made of).  The gradients are written straight into the caller's DEVICE buffers dev_gradxyz1 (B,N,3) /
+ * dev_gradxyz2 (B,M,3), where the optimizer consumes them (the reference's Function also returns device tensors,
+ * dist_chamfer_3D.py:44-47); dist/idx never leave the staging slots.  graddist1 == graddist2 == NULL => forward +
+ * sums only.  Enqueue-only like ps_chamfer_host; sums6 and the gradients are complete once `stream` has passed
+ * this point. */
+int ps_chamfer_host_step(const float* xyz1, const float* xyz2, const float* graddist1, const float* graddist2,
+                         float* dev_gradxyz1, float* dev_gradxyz2, double* sums6, int B, int N, int M, int chunk,
+                         int dev, void* stream);
+
 /* ---- Furthest point sampling ------------------------------------------------------------
  * Replaces furthest_point_sampling_kernel_wrapper (pointnet2_ops/_ext-src/src/sampling_gpu.cu:175-229,
  * kernel :69-173; pybind `_ext.furthest_point_sampling`, sampling.cpp:66-87).

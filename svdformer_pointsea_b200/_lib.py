@@ -24,6 +24,7 @@ _SIGNATURES = {
     "ps_chamfer_fwd": [_P, _P, _P, _P, _P, _P, _c_int, _c_int, _c_int, _c_int, _P],
     "ps_chamfer_bwd": [_P, _P, _P, _P, _P, _P, _P, _P, _c_int, _c_int, _c_int, _c_int, _P],
     "ps_chamfer_host": [_P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _c_int, _c_int, _c_int, _c_int, _c_int, _P],
+    "ps_chamfer_host_step": [_P, _P, _P, _P, _P, _P, _P, _c_int, _c_int, _c_int, _c_int, _c_int, _P],
     "ps_chamfer_sums": [_P, _P, _P, ctypes.c_longlong, ctypes.c_longlong, _c_int, _P],
     "ps_fps": [_P, _P, _c_int, _c_int, _c_int, _c_int, _P],
     "ps_fps_sample": [_P, _P, _P, _c_int, _c_int, _c_int, _c_int, _P],

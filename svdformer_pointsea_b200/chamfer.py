@@ -141,6 +141,55 @@ def chamfer_host(xyz1, xyz2, graddist1=None, graddist2=None, out=None, chunk=0, 
     return tuple(out)
 
 
+def chamfer_host_step(xyz1, xyz2, graddist1=None, graddist2=None, grad_out=None, sums_out=None, chunk=0, device=None,
+                      blocking=True):
+    """One training-style Chamfer step on HOST clouds: upload in chunks, forward, loss sums, backward — and only
+    the six loss sums come back over PCIe.
+
+    xyz1/xyz2 (and graddist1/2 for the backward) are CPU tensors, pinned for the overlap to happen.  Returns
+    `(sums, gradxyz1, gradxyz2)`: `sums` a pinned float64 CPU tensor [sum sqrt d1, sum sqrt d2, sum d1, sum d2, n1, n2]
+    (`sums_out` to reuse one), the gradients CUDA tensors on `device` (`grad_out=(g1, g2)` to reuse buffers; None
+    without graddist).  With `blocking=False` everything is valid once the current stream of `device` has been
+    synchronised.  Values equal chamfer_forward + chamfer_sums + chamfer_backward on the same clouds."""
+    if xyz1.dim() != 3 or xyz2.dim() != 3 or xyz1.size(2) != 3 or xyz2.size(2) != 3 or xyz1.size(0) != xyz2.size(0):
+        raise L.PointSeaError(f"chamfer expects (B,N,3) and (B,M,3), got {tuple(xyz1.shape)} {tuple(xyz2.shape)}")
+    B, N, _ = xyz1.shape
+    M = xyz2.size(1)
+    _require_host(xyz1, "xyz1", torch.float32, (B, N, 3))
+    _require_host(xyz2, "xyz2", torch.float32, (B, M, 3))
+    with_bwd = graddist1 is not None or graddist2 is not None
+    if with_bwd:
+        if graddist1 is None or graddist2 is None:
+            raise L.PointSeaError("chamfer_host_step: backward needs both graddist1 and graddist2")
+        _require_host(graddist1, "graddist1", torch.float32, (B, N))
+        _require_host(graddist2, "graddist2", torch.float32, (B, M))
+    if not torch.cuda.is_available():
+        raise L.PointSeaError("chamfer_host_step needs a CUDA device (there is no CPU implementation)")
+    index = torch.cuda.current_device() if device is None else torch.device(device).index
+    L._check_device(index)
+    dev = torch.device("cuda", index)
+    if sums_out is None:
+        sums_out = torch.empty(6, dtype=torch.float64).pin_memory()
+    _require_host(sums_out, "sums_out", torch.float64, (6,))
+    g1 = g2 = None
+    if with_bwd:
+        if grad_out is None:
+            grad_out = (torch.empty(B, N, 3, device=dev), torch.empty(B, M, 3, device=dev))
+        g1, g2 = grad_out
+        for t, nm, shape in ((g1, "gradxyz1", (B, N, 3)), (g2, "gradxyz2", (B, M, 3))):
+            L.require(t, nm, torch.float32, 3)
+            if tuple(t.shape) != shape or t.device != dev:
+                raise L.PointSeaError(f"{nm} must be a {shape} tensor on {dev}")
+    rc = L.load().ps_chamfer_host_step(L.ptr(xyz1), L.ptr(xyz2), L.ptr(graddist1) if with_bwd else None,
+                                       L.ptr(graddist2) if with_bwd else None, L.ptr(g1) if with_bwd else None,
+                                       L.ptr(g2) if with_bwd else None, L.ptr(sums_out), B, N, M, int(chunk), index,
+                                       L.stream_ptr(index))
+    L.check(rc, "ps_chamfer_host_step")
+    if blocking:
+        torch.cuda.current_stream(index).synchronize()
+    return sums_out, g1, g2
+
+
 class chamfer_3DFunction(Function):
     """Drop-in for dist_chamfer_3D.chamfer_3DFunction (dist_chamfer_3D.py:26-64)."""
 

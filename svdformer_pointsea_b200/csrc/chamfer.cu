@@ -389,7 +389,7 @@ extern "C" int ps_chamfer_bwd(const float* xyz1, const float* xyz2, const float*
 // multi-GPU path all-reduces.
 namespace ps {
 __global__ void __launch_bounds__(256) chamfer_sums_kernel(const float* __restrict__ d1, const float* __restrict__ d2,
-                                                           double* __restrict__ out, long long n1, long long n2) {
+                                                           double* __restrict__ out, long long n1, long long n2, int accumulate) {
   double s[4] = {0.0, 0.0, 0.0, 0.0};
   const long long stride = (long long)gridDim.x * blockDim.x;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n1; i += stride) {
@@ -417,7 +417,24 @@ __global__ void __launch_bounds__(256) chamfer_sums_kernel(const float* __restri
     for (int w = 0; w < 8; w++) t += sh[w][threadIdx.x];
     atomicAdd(out + threadIdx.x, t);
   }
-  if (blockIdx.x == 0 && threadIdx.x == 4) { out[4] = (double)n1; out[5] = (double)n2; }  // element counts
+  if (blockIdx.x == 0 && threadIdx.x == 4) {  // element counts
+    if (accumulate) { atomicAdd(out + 4, (double)n1); atomicAdd(out + 5, (double)n2); }
+    else { out[4] = (double)n1; out[5] = (double)n2; }
+  }
+}
+
+// accumulate != 0: adds this call's six numbers to `out` (the chunked host pipeline zeroes it once per step)
+int chamfer_sums_launch(const float* dist1, const float* dist2, double* out6, long long n1, long long n2, int accumulate,
+                        int dev, cudaStream_t stream) {
+  if (!accumulate) PS_CUDA(cudaMemsetAsync(out6, 0, 6 * sizeof(double), stream));
+  const long long n = n1 > n2 ? n1 : n2;
+  if (n == 0) return PS_OK;
+  int grid = ceil_div(n, 256 * 8);
+  const int cap = sm_count(dev) * 4;
+  if (grid > cap) grid = cap;
+  chamfer_sums_kernel<<<grid, 256, 0, stream>>>(dist1, dist2, out6, n1, n2, accumulate);
+  PS_LAUNCH_CHECK();
+  return PS_OK;
 }
 }  // namespace ps
 
@@ -427,13 +444,5 @@ extern "C" int ps_chamfer_sums(const float* dist1, const float* dist2, double* o
   DeviceGuard guard(dev);
   if (!guard.ok) return set_error(PS_ERR_CUDA, "ps_chamfer_sums: cannot select device %d", dev);
   cudaStream_t stream = (cudaStream_t)stream_;
-  PS_CUDA(cudaMemsetAsync(out4, 0, 6 * sizeof(double), stream));
-  const long long n = n1 > n2 ? n1 : n2;
-  if (n == 0) return PS_OK;
-  int grid = ceil_div(n, 256 * 8);
-  const int cap = sm_count(dev) * 4;
-  if (grid > cap) grid = cap;
-  chamfer_sums_kernel<<<grid, 256, 0, stream>>>(dist1, dist2, out4, n1, n2);
-  PS_LAUNCH_CHECK();
-  return PS_OK;
+  return chamfer_sums_launch(dist1, dist2, out4, n1, n2, 0, dev, stream);
 }

@@ -66,6 +66,10 @@ int scratch_alloc(void** ptr, size_t bytes, int dev, cudaStream_t stream);
 int chamfer_fwd_symmetric(const float* xyz1, const float* xyz2, float* dist1, float* dist2, int* idx1,
                           int* idx2, int B, int N, int M, int dev, cudaStream_t stream);
 
+// chamfer.cu: the six loss sums of ps_chamfer_sums; accumulate != 0 adds to out6 instead of overwriting it
+int chamfer_sums_launch(const float* dist1, const float* dist2, double* out6, long long n1, long long n2, int accumulate,
+                        int dev, cudaStream_t stream);
+
 // knn_select.cu: PS_OK when handled, 1 when the streaming kernel in neighbors.cu should run instead
 int knn_select_launch(const float* xyz, const float* new_xyz, int* idx, float* gxyz, int B, int N, int S, int k,
                       int skip, int order, int var, int nsm, cudaStream_t stream);

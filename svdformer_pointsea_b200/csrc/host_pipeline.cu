@@ -32,7 +32,7 @@ constexpr int MAX_CHUNKS = 64;
 
 
 struct PipeKey {
-  const void* p[10];
+  const void* p[13];
   int B, N, M, nchunks;
   int sizes[MAX_CHUNKS];
 };
@@ -50,10 +50,11 @@ struct HostPipe {
   cudaStream_t s_cap = nullptr;   // origin stream of the captures
   cudaEvent_t ev_last = nullptr;  // end of the most recent call on this device (any caller stream)
   bool ready = false;
-  cudaStream_t s_in = nullptr, s_run = nullptr, s_out = nullptr;
+  cudaStream_t s_in = nullptr, s_run = nullptr, s_bwd = nullptr, s_out = nullptr;
   cudaEvent_t ev_in[SLOTS], ev_gin[SLOTS], ev_fwd[SLOTS], ev_run[SLOTS], ev_out[SLOTS], ev_begin = nullptr, ev_end = nullptr;
   void* slot[SLOTS] = {nullptr, nullptr, nullptr};
   size_t slot_bytes = 0;
+  double* d_sums = nullptr;  // 6 doubles: loss partial sums of the current call (ps_chamfer_host_step)
 };
 
 static HostPipe* pipe_for(int dev) {
@@ -66,6 +67,7 @@ static int pipe_init(HostPipe& hp) {
   PS_CUDA(cudaStreamCreateWithFlags(&hp.s_in, cudaStreamNonBlocking));
   PS_CUDA(cudaStreamCreateWithFlags(&hp.s_run, cudaStreamNonBlocking));
   PS_CUDA(cudaStreamCreateWithFlags(&hp.s_out, cudaStreamNonBlocking));
+  PS_CUDA(cudaStreamCreateWithFlags(&hp.s_bwd, cudaStreamNonBlocking));
   for (int i = 0; i < SLOTS; i++) {
     PS_CUDA(cudaEventCreateWithFlags(&hp.ev_in[i], cudaEventDisableTiming));
     PS_CUDA(cudaEventCreateWithFlags(&hp.ev_gin[i], cudaEventDisableTiming));
@@ -77,6 +79,7 @@ static int pipe_init(HostPipe& hp) {
   PS_CUDA(cudaEventCreateWithFlags(&hp.ev_last, cudaEventDisableTiming));
   PS_CUDA(cudaEventCreateWithFlags(&hp.ev_begin, cudaEventDisableTiming));
   PS_CUDA(cudaEventCreateWithFlags(&hp.ev_end, cudaEventDisableTiming));
+  PS_CUDA(cudaMalloc(&hp.d_sums, 6 * sizeof(double)));
   hp.ready = true;
   return PS_OK;
 }
@@ -136,6 +139,10 @@ struct PipeArgs {
   int nchunks;
   int sizes[MAX_CHUNKS];
   bool with_bwd;
+  // ps_chamfer_host_step: gradients written straight into the caller's DEVICE buffers (never downloaded), the six
+  // loss sums accumulated on the device and downloaded once (48 bytes); dist/idx stay in the staging slots
+  float *dev_g1 = nullptr, *dev_g2 = nullptr;
+  double* h_sums = nullptr;
   size_t o_x1, o_x2, o_d1, o_d2, o_i1, o_i2, o_gd1, o_gd2, o_g1, o_g2;
 };
 
@@ -181,23 +188,31 @@ static int enqueue_pipeline(HostPipe& hp, const PipeArgs& a, cudaStream_t origin
     if (c >= SLOTS) PS_CUDA(cudaStreamWaitEvent(hp.s_run, hp.ev_out[s], 0));
     if (int rc = ps_chamfer_fwd(d_x1, d_x2, d_d1, d_d2, d_i1, d_i2, nb, a.N, a.M, a.dev, hp.s_run)) return rc;
     PS_CUDA(cudaEventRecord(hp.ev_fwd[s], hp.s_run));
-    if (a.with_bwd) {
-      PS_CUDA(cudaStreamWaitEvent(hp.s_run, hp.ev_gin[s], 0));
-      if (int rc = ps_chamfer_bwd(d_x1, d_x2, d_gd1, d_gd2, d_i1, d_i2, d_g1, d_g2, nb, a.N, a.M, a.dev, hp.s_run)) return rc;
+    // loss sums + backward on their own stream: a handful of small, latency-bound kernels that fill the gaps of
+    // the NEXT chunk's forward instead of delaying it (the forward of chunk c+1 only needs its own upload)
+    PS_CUDA(cudaStreamWaitEvent(hp.s_bwd, hp.ev_fwd[s], 0));
+    if (a.h_sums) {
+      if (c == 0) PS_CUDA(cudaMemsetAsync(hp.d_sums, 0, 6 * sizeof(double), hp.s_bwd));
+      if (int rc = chamfer_sums_launch(d_d1, d_d2, hp.d_sums, (long long)c1, (long long)c2, 1, a.dev, hp.s_bwd)) return rc;
     }
-    PS_CUDA(cudaEventRecord(hp.ev_run[s], hp.s_run));
+    if (a.with_bwd) {
+      PS_CUDA(cudaStreamWaitEvent(hp.s_bwd, hp.ev_gin[s], 0));
+      float* g1 = a.dev_g1 ? a.dev_g1 + h1 * 3 : d_g1;
+      float* g2 = a.dev_g2 ? a.dev_g2 + h2 * 3 : d_g2;
+      if (int rc = ps_chamfer_bwd(d_x1, d_x2, d_gd1, d_gd2, d_i1, d_i2, g1, g2, nb, a.N, a.M, a.dev, hp.s_bwd)) return rc;
+    }
+    PS_CUDA(cudaEventRecord(hp.ev_run[s], hp.s_bwd));
 
     // download: distances and indices as soon as the forward is done, gradients after the backward
     PS_CUDA(cudaStreamWaitEvent(hp.s_out, hp.ev_fwd[s], 0));
-    COPY(a.dist1 + h1, d_d1, c1 * 4, cudaMemcpyDeviceToHost, hp.s_out);
-    COPY(a.dist2 + h2, d_d2, c2 * 4, cudaMemcpyDeviceToHost, hp.s_out);
-    COPY(a.idx1 + h1, d_i1, c1 * 4, cudaMemcpyDeviceToHost, hp.s_out);
-    COPY(a.idx2 + h2, d_i2, c2 * 4, cudaMemcpyDeviceToHost, hp.s_out);
+    if (a.dist1) COPY(a.dist1 + h1, d_d1, c1 * 4, cudaMemcpyDeviceToHost, hp.s_out);
+    if (a.dist2) COPY(a.dist2 + h2, d_d2, c2 * 4, cudaMemcpyDeviceToHost, hp.s_out);
+    if (a.idx1) COPY(a.idx1 + h1, d_i1, c1 * 4, cudaMemcpyDeviceToHost, hp.s_out);
+    if (a.idx2) COPY(a.idx2 + h2, d_i2, c2 * 4, cudaMemcpyDeviceToHost, hp.s_out);
     PS_CUDA(cudaStreamWaitEvent(hp.s_out, hp.ev_run[s], 0));
-    if (a.with_bwd) {
-      COPY(a.gradxyz1 + h1 * 3, d_g1, c1 * 12, cudaMemcpyDeviceToHost, hp.s_out);
-      COPY(a.gradxyz2 + h2 * 3, d_g2, c2 * 12, cudaMemcpyDeviceToHost, hp.s_out);
-    }
+    if (a.with_bwd && a.gradxyz1) COPY(a.gradxyz1 + h1 * 3, d_g1, c1 * 12, cudaMemcpyDeviceToHost, hp.s_out);
+    if (a.with_bwd && a.gradxyz2) COPY(a.gradxyz2 + h2 * 3, d_g2, c2 * 12, cudaMemcpyDeviceToHost, hp.s_out);
+    if (a.h_sums && c == a.nchunks - 1) COPY(a.h_sums, hp.d_sums, 6 * sizeof(double), cudaMemcpyDeviceToHost, hp.s_out);
     PS_CUDA(cudaEventRecord(hp.ev_out[s], hp.s_out));
   }
   // downloads are in order on s_out: `origin` continues once the last one has landed
@@ -218,17 +233,12 @@ static void drop_graphs(HostPipe& hp) {
 
 using namespace ps;
 
-extern "C" int ps_chamfer_host(const float* xyz1, const float* xyz2, float* dist1, float* dist2, int* idx1,
-                               int* idx2, const float* graddist1, const float* graddist2, float* gradxyz1,
-                               float* gradxyz2, int B, int N, int M, int chunk, int dev, void* stream_) {
+static int host_pipeline_call(const float* xyz1, const float* xyz2, float* dist1, float* dist2, int* idx1,
+                              int* idx2, const float* graddist1, const float* graddist2, float* gradxyz1,
+                              float* gradxyz2, float* dev_g1, float* dev_g2, double* h_sums, int B, int N, int M,
+                              int chunk, int dev, void* stream_) {
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
-  PS_REQUIRE(B >= 0 && N >= 0 && M >= 0, "ps_chamfer_host: negative size");
-  if (B == 0 || (N == 0 && M == 0)) return PS_OK;
-  PS_REQUIRE(N > 0 && M > 0, "ps_chamfer_host: both clouds need at least one point (N=%d, M=%d)", N, M);
-  PS_REQUIRE(xyz1 && xyz2 && dist1 && dist2 && idx1 && idx2, "ps_chamfer_host: null pointer");
   const bool with_bwd = graddist1 != nullptr || graddist2 != nullptr;
-  if (with_bwd)
-    PS_REQUIRE(graddist1 && graddist2 && gradxyz1 && gradxyz2, "ps_chamfer_host: backward needs graddist1, graddist2, gradxyz1, gradxyz2");
   HostPipe* hpp = pipe_for(dev);
   PS_REQUIRE(hpp != nullptr, "ps_chamfer_host: bad device %d", dev);
   DeviceGuard guard(dev);
@@ -242,6 +252,7 @@ extern "C" int ps_chamfer_host(const float* xyz1, const float* xyz2, float* dist
   a.xyz1 = xyz1; a.xyz2 = xyz2; a.graddist1 = graddist1; a.graddist2 = graddist2;
   a.dist1 = dist1; a.dist2 = dist2; a.gradxyz1 = gradxyz1; a.gradxyz2 = gradxyz2;
   a.idx1 = idx1; a.idx2 = idx2;
+  a.dev_g1 = dev_g1; a.dev_g2 = dev_g2; a.h_sums = h_sums;
   a.B = B; a.N = N; a.M = M; a.chunk = chunk; a.dev = dev; a.with_bwd = with_bwd;
   // slot layout (all sub-buffers 256-byte aligned so the vectorised kernels see aligned clouds)
   const size_t n1 = (size_t)chunk * N, n2 = (size_t)chunk * M;
@@ -281,7 +292,7 @@ extern "C" int ps_chamfer_host(const float* xyz1, const float* xyz2, float* dist
   }
   if (use_graph) {
     // copies from / to pageable memory cannot be captured (the runtime stages them synchronously)
-    const void* hostp[10] = {xyz1, xyz2, dist1, dist2, idx1, idx2, graddist1, graddist2, gradxyz1, gradxyz2};
+    const void* hostp[11] = {xyz1, xyz2, dist1, dist2, idx1, idx2, graddist1, graddist2, gradxyz1, gradxyz2, h_sums};
     for (const void* hptr : hostp) {
       if (!hptr) continue;
       cudaPointerAttributes attr;
@@ -296,7 +307,7 @@ extern "C" int ps_chamfer_host(const float* xyz1, const float* xyz2, float* dist
   if (use_graph) {
     PipeKey key;
     memset(&key, 0, sizeof(key));
-    const void* ptrs[10] = {xyz1, xyz2, dist1, dist2, idx1, idx2, graddist1, graddist2, gradxyz1, gradxyz2};
+    const void* ptrs[13] = {xyz1, xyz2, dist1, dist2, idx1, idx2, graddist1, graddist2, gradxyz1, gradxyz2, dev_g1, dev_g2, h_sums};
     memcpy(key.p, ptrs, sizeof(ptrs));
     key.B = B; key.N = N; key.M = M; key.nchunks = a.nchunks;
     memcpy(key.sizes, a.sizes, sizeof(int) * a.nchunks);
@@ -339,4 +350,32 @@ extern "C" int ps_chamfer_host(const float* xyz1, const float* xyz2, float* dist
   if (rc) return rc;
   if (!caller_capturing) PS_CUDA(cudaEventRecord(hp.ev_last, stream));
   return PS_OK;
+}
+
+extern "C" int ps_chamfer_host(const float* xyz1, const float* xyz2, float* dist1, float* dist2, int* idx1,
+                               int* idx2, const float* graddist1, const float* graddist2, float* gradxyz1,
+                               float* gradxyz2, int B, int N, int M, int chunk, int dev, void* stream) {
+  PS_REQUIRE(B >= 0 && N >= 0 && M >= 0, "ps_chamfer_host: negative size");
+  if (B == 0 || (N == 0 && M == 0)) return PS_OK;
+  PS_REQUIRE(N > 0 && M > 0, "ps_chamfer_host: both clouds need at least one point (N=%d, M=%d)", N, M);
+  PS_REQUIRE(xyz1 && xyz2 && dist1 && dist2 && idx1 && idx2, "ps_chamfer_host: null pointer");
+  if (graddist1 != nullptr || graddist2 != nullptr)
+    PS_REQUIRE(graddist1 && graddist2 && gradxyz1 && gradxyz2, "ps_chamfer_host: backward needs graddist1, graddist2, gradxyz1, gradxyz2");
+  return host_pipeline_call(xyz1, xyz2, dist1, dist2, idx1, idx2, graddist1, graddist2, gradxyz1, gradxyz2, nullptr, nullptr,
+                            nullptr, B, N, M, chunk, dev, stream);
+}
+
+extern "C" int ps_chamfer_host_step(const float* xyz1, const float* xyz2, const float* graddist1, const float* graddist2,
+                                    float* dev_gradxyz1, float* dev_gradxyz2, double* sums6, int B, int N, int M,
+                                    int chunk, int dev, void* stream) {
+  PS_REQUIRE(B >= 0 && N >= 0 && M >= 0, "ps_chamfer_host_step: negative size");
+  if (B == 0 || (N == 0 && M == 0)) return PS_OK;
+  PS_REQUIRE(N > 0 && M > 0, "ps_chamfer_host_step: both clouds need at least one point (N=%d, M=%d)", N, M);
+  PS_REQUIRE(xyz1 && xyz2 && sums6, "ps_chamfer_host_step: null pointer");
+  const bool with_bwd = graddist1 != nullptr || graddist2 != nullptr;
+  if (with_bwd)
+    PS_REQUIRE(graddist1 && graddist2 && dev_gradxyz1 && dev_gradxyz2,
+               "ps_chamfer_host_step: backward needs graddist1, graddist2 (host) and dev_gradxyz1, dev_gradxyz2 (device)");
+  return host_pipeline_call(xyz1, xyz2, nullptr, nullptr, nullptr, nullptr, graddist1, graddist2, nullptr, nullptr,
+                            with_bwd ? dev_gradxyz1 : nullptr, with_bwd ? dev_gradxyz2 : nullptr, sums6, B, N, M, chunk, dev, stream);
 }

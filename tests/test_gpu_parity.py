@@ -579,3 +579,28 @@ def test_empty_batches_and_zero_sized_requests_are_no_ops():
     assert tuple(ps.query_knn(4, x, torch.empty(2, 0, 3, device=DEV)).shape) == (2, 0, 4)
     assert tuple(ps.ball_query(0.1, 4, x, torch.empty(2, 0, 3, device=DEV)).shape) == (2, 0, 4)
     torch.cuda.synchronize()
+
+
+def test_chamfer_host_step_matches_device_entry_points():
+    """ps_chamfer_host_step: host clouds in, loss sums out, gradients left in device buffers — equal to
+    forward + sums + backward on resident tensors, for ragged chunk plans and on replay of the captured graph."""
+    g = torch.Generator().manual_seed(77)
+    B, N, M = 7, 700, 1900
+    a, b = make_cloud(g, B, N, dup=100).pin_memory(), make_cloud(g, B, M, dup=300).pin_memory()
+    gd1, gd2 = torch.randn(B, N, generator=g).pin_memory(), torch.randn(B, M, generator=g).pin_memory()
+    A, Bc = a.to(DEV), b.to(DEV)
+    d1, d2, i1, i2 = ps.chamfer_forward(A, Bc)
+    want_sums = ps.chamfer_sums(d1, d2).cpu()
+    w1, w2 = ps.chamfer_backward(A, Bc, gd1.to(DEV), gd2.to(DEV), i1, i2)
+    for chunk in (0, 2, 7, 3):
+        for rep in range(2):  # second call replays the CUDA graph
+            sums, g1, g2 = ps.chamfer_host_step(a, b, gd1, gd2, chunk=chunk)
+            assert torch.allclose(sums, want_sums, rtol=1e-12, atol=0), (chunk, rep)
+            assert_close_rel(g1.cpu().numpy(), w1.cpu().numpy(), what="gradxyz1")
+            assert_close_rel(g2.cpu().numpy(), w2.cpu().numpy(), what="gradxyz2")
+    sums, g1, g2 = ps.chamfer_host_step(a, b)  # forward + sums only
+    assert g1 is None and g2 is None and torch.allclose(sums, want_sums, rtol=1e-12, atol=0)
+    with pytest.raises(ps.PointSeaError):
+        ps.chamfer_host_step(a, b, gd1, None)
+    with pytest.raises(ps.PointSeaError):
+        ps.chamfer_host_step(A, Bc)
