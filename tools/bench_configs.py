@@ -116,6 +116,11 @@ def c4_arm(arm, iters, knn):
     render = mu.PCViews(TRANS=-cfg.NETWORK.view_distance, RESOLUTION=224)
     out = {}
 
+    if world > 1 and arm == "ours":
+        # batch-sharded loss: the reference's get_loss over the GLOBAL batch = local Chamfer terms + ONE all-reduce
+        # of their partial sums (svdformer_pointsea_b200.dist.get_loss_sharded), identical on every rank
+        from svdformer_pointsea_b200.dist import get_loss_sharded as get_loss  # noqa: F811
+
     def step():
         with torch.no_grad():
             depth = torch.unsqueeze(render.get_img(partial), 1)
@@ -134,6 +139,10 @@ def c4_arm(arm, iters, knn):
            "ms_loss_min": round(min(tl), 3), "loss": float(out["loss"]), "losses": [float(x) for x in out["losses"]]}
     if rank == 0:
         print(json.dumps(res))
+    if world > 1:
+        import torch.distributed as dist
+        dist.barrier()
+        dist.destroy_process_group()
 
 
 def c4(args):
