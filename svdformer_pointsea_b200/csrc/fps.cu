@@ -21,6 +21,14 @@
 //     barrier.cluster in the loop: its .release costs a MEMBAR.ALL.GPU per iteration (measured,
 //     profiles/fps_r1_notes.md);
 //   * MODE 2 (C >= 8): CTA-level reduce first (one __syncthreads), then one st.async per CTA pair.
+//   * MODE 3 (C <= 4, the default there): same direct all-to-all as MODE 1, but with plain remote
+//     vector stores (st.shared::cluster.v4) and TAG POLLING instead of st.async + mbarrier: each 16-byte half
+//     of an entry carries the iteration number, and lane e of every warp spins on entry e of its OWN CTA's
+//     slot array (local ld.volatile) until both halves show the current tag.  The async-proxy path costs
+//     ~520 cycles even inside one CTA (profiles/microbench_r1.jsonl); a remote store is visible after ~1/2 of
+//     the 215-cycle DSMEM round trip and a local poll costs ~40.  With 4 fat warps per CTA the polling load on
+//     the LSU is small (the first attempt polled with 16 warps and lost to the barrier).  The spin is bounded:
+//     a protocol failure raises the error flag instead of hanging the GPU.
 //   The message carries the winner's coordinates, so the next iteration never touches global
 //   memory.  Two slot buffers suffice: a writer can only be at iteration j+2 after consuming all
 //   candidates of j+1, and a reader sends its j+1 candidate only after reading the slots of j.
@@ -58,6 +66,7 @@ struct FpsArgs {
   const float* xyz;
   int* idx;
   float* new_xyz;  // optional (B, npoint, 3): coordinates of the sampled points (fused fps_subsample)
+  int* err;        // optional device flag raised when a bounded spin gives up (MODE 3)
   int N, npoint;
   int L;     // log2(bs) of the reference launch
   int nper;  // ceil(N / bs)
@@ -107,12 +116,20 @@ __device__ __forceinline__ void st_async_v4(unsigned raddr, unsigned rbar, unsig
                ::"r"(raddr), "r"(a), "r"(b), "r"(c), "r"(d), "r"(rbar) : "memory");
 }
 
+__device__ __forceinline__ int4 ld_volatile_shared_v4(const void* p) {
+  int4 v;
+  asm volatile("ld.volatile.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(smem_u32(p)) : "memory");
+  return v;
+}
+constexpr int FPS_SPIN_LIMIT = 1 << 22;  // ~0.1 s of polling: far beyond any legitimate wait
+
 template <int PP, int T, int MODE>
 __global__ void __launch_bounds__(T, 1) fps_kernel(const FpsArgs a) {
   constexpr int P = 2 * PP;
   constexpr int WARPS = T / 32;
   constexpr bool CLUSTER = MODE != 0;
-  constexpr bool DIRECT = MODE == 1;
+  constexpr bool POLL = MODE == 3;
+  constexpr bool DIRECT = MODE == 1 || MODE == 3;
   extern __shared__ __align__(16) unsigned char smem_raw[];
   // layout: px[P*T] py[P*T] pz[P*T] pk[P*T] | mbar[2] (16 B) | slots[2][E] | wslots[2][WARPS] (MODE 2)
   float* px = reinterpret_cast<float*>(smem_raw);
@@ -163,7 +180,10 @@ __global__ void __launch_bounds__(T, 1) fps_kernel(const FpsArgs a) {
       x2[i / 2] = pack2(xv, 0.f); y2[i / 2] = pack2(yv, 0.f); z2[i / 2] = pack2(zv, 0.f);
     }
   }
-  if (CLUSTER && tid == 0) {
+  if (POLL) {  // tags of both buffers start at 0 (iteration tags are >= 1)
+    for (int e = tid; e < 2 * E; e += T) { slots[e].pad_a = 0u; slots[e].pad_b = 0u; }
+  }
+  if (CLUSTER && !POLL && tid == 0) {
     // one local arrive (the expect_tx) + E*32 bytes of st.async traffic complete a phase
     fps_mbar_init(smem_u32(&mbar[0]), 1);
     fps_mbar_init(smem_u32(&mbar[1]), 1);
@@ -205,6 +225,34 @@ __global__ void __launch_bounds__(T, 1) fps_kernel(const FpsArgs a) {
     const int wl = warp_argbest(tb, rk, tbw);
     const int buf = j & 1;
 
+    if constexpr (MODE == 0 && WARPS <= 4) {
+      // Single CTA of 4 warps (8 warps: the REDUX path below measured faster): the winning lane writes the warp's entry itself (no payload broadcast), and after the
+      // barrier EVERY lane folds the WARPS entries in registers — broadcast LDS.128 and WARPS-1 compares
+      // instead of a second round of REDUX / ballot / shuffles on the critical path of the iteration.
+      FpsEntry* ws = slots + buf * WARPS;
+      if (lane == wl) {
+        const int pi = bi * T + tid;
+        *reinterpret_cast<int4*>(&ws[warp]) = make_int4(tbw, (int)rk, __float_as_int(px[pi]), 0);
+        *reinterpret_cast<int4*>(reinterpret_cast<char*>(&ws[warp]) + 16) = make_int4(__float_as_int(py[pi]), __float_as_int(pz[pi]), pk[pi], 0);
+      }
+      __syncthreads();
+      int4 ba = *reinterpret_cast<const int4*>(&ws[0]);
+      int4 bb = *reinterpret_cast<const int4*>(reinterpret_cast<const char*>(&ws[0]) + 16);
+#pragma unroll
+      for (int w = 1; w < WARPS; w++) {
+        const int4 ca = *reinterpret_cast<const int4*>(&ws[w]);
+        const int4 cb = *reinterpret_cast<const int4*>(reinterpret_cast<const char*>(&ws[w]) + 16);
+        if (fps_better(ca.x, (unsigned)ca.y, ba.x, (unsigned)ba.y)) { ba = ca; bb = cb; }
+      }
+      lx = __int_as_float(ba.z); ly = __int_as_float(bb.x); lz = __int_as_float(bb.y);
+      int kf = bb.z;
+      if (ba.x < 0) {  // no eligible point anywhere: the reference's tree returns thread 0's besti = 0
+        kf = 0; lx = p0x; ly = p0y; lz = p0z;
+      }
+      if (g == 0) { out[j] = kf; if (oxyz) { oxyz[j * 3 + 0] = lx; oxyz[j * 3 + 1] = ly; oxyz[j * 3 + 2] = lz; } }
+      continue;
+    }
+
     // winner's payload to every lane of the warp
     float wx = 0.f, wy = 0.f, wz = 0.f;
     int wk = 0;
@@ -215,7 +263,15 @@ __global__ void __launch_bounds__(T, 1) fps_kernel(const FpsArgs a) {
     const unsigned s_z = __shfl_sync(0xffffffffu, __float_as_uint(wz), wl);
     const unsigned s_k = __shfl_sync(0xffffffffu, (unsigned)wk, wl);
 
-    if (DIRECT) {
+    if (POLL) {
+      // lane c stores the warp's candidate into slot (crank*WARPS+warp) of CTA c; both halves carry the tag j
+      if ((unsigned)lane < C) {
+        const unsigned e = crank * WARPS + warp;
+        const unsigned ra = mapa_shared(smem_u32(&slots[buf * E + e]), (unsigned)lane);
+        st_cluster_v4(ra, (unsigned)tbw, s_rk, s_x, (unsigned)j);
+        st_cluster_v4(ra + 16, s_y, s_z, s_k, (unsigned)j);
+      }
+    } else if (DIRECT) {
       // lane c pushes the warp's candidate to slot (crank*WARPS+warp) of CTA c: C pushes in flight
       if ((unsigned)lane < C) {
         const unsigned e = crank * WARPS + warp;
@@ -253,7 +309,7 @@ __global__ void __launch_bounds__(T, 1) fps_kernel(const FpsArgs a) {
         }
       }
     }
-    if (CLUSTER) {
+    if (CLUSTER && !POLL) {
       // buffer `buf` is used by iterations buf, buf+2, ... (buf=1: j=1,3,..; buf=0: j=2,4,..)
       const unsigned parity = (unsigned)((j - 1) >> 1) & 1u;
       while (!fps_mbar_try_wait(smem_u32(&mbar[buf]), parity)) {}
@@ -266,14 +322,37 @@ __global__ void __launch_bounds__(T, 1) fps_kernel(const FpsArgs a) {
     const FpsEntry* sl = slots + buf * E;
     constexpr int MAXE = DIRECT ? (WARPS * 4 + 31) / 32 : 1;  // entries per lane (C <= 4 when DIRECT)
     int4 va[MAXE], vb[MAXE];
+    if (POLL) {
+      // lane e spins on entry e of this CTA's own slot array until both halves carry tag j.  Two buffers are
+      // enough: a peer can only write iteration j+2 into this buffer after it has seen OUR iteration j+1
+      // entry, which this warp sends after leaving this loop.
+      int spins = 0;
+      bool ok;
+      do {
+        ok = true;
 #pragma unroll
-    for (int u = 0; u < MAXE; u++) {
-      const int e = lane + 32 * u;
-      va[u] = make_int4((int)0x80000000, -1, 0, 0);
-      vb[u] = make_int4(0, 0, 0, 0);
-      if (e < E) {
-        va[u] = *reinterpret_cast<const int4*>(&sl[e]);
-        vb[u] = *reinterpret_cast<const int4*>(reinterpret_cast<const char*>(&sl[e]) + 16);
+        for (int u = 0; u < MAXE; u++) {
+          const int e = lane + 32 * u;
+          va[u] = make_int4((int)0x80000000, -1, 0, j);
+          vb[u] = make_int4(0, 0, 0, j);
+          if (e < E) {
+            va[u] = ld_volatile_shared_v4(&sl[e]);
+            vb[u] = ld_volatile_shared_v4(reinterpret_cast<const char*>(&sl[e]) + 16);
+          }
+          ok = ok && va[u].w == j && vb[u].w == j;
+        }
+      } while (!__all_sync(0xffffffffu, ok) && ++spins < FPS_SPIN_LIMIT);
+      if (spins >= FPS_SPIN_LIMIT) { if (lane == 0 && a.err) atomicExch(a.err, 1); break; }  // bounded: never hang
+    } else {
+#pragma unroll
+      for (int u = 0; u < MAXE; u++) {
+        const int e = lane + 32 * u;
+        va[u] = make_int4((int)0x80000000, -1, 0, 0);
+        vb[u] = make_int4(0, 0, 0, 0);
+        if (e < E) {
+          va[u] = *reinterpret_cast<const int4*>(&sl[e]);
+          vb[u] = *reinterpret_cast<const int4*>(reinterpret_cast<const char*>(&sl[e]) + 16);
+        }
       }
     }
 #pragma unroll
@@ -369,7 +448,7 @@ static int ref_block_log2(int n) {
 template <int PP, int T, int MODE>
 static int launch_fps(const FpsArgs& a, int B, int C, cudaStream_t stream) {
   constexpr int P = 2 * PP, WARPS = T / 32;
-  const int E = (MODE == 1) ? WARPS * C : (MODE == 0 ? WARPS : C);
+  const int E = (MODE == 1 || MODE == 3) ? WARPS * C : (MODE == 0 ? WARPS : C);
   const size_t smem = (size_t)4 * P * T * sizeof(float) + 16 + (size_t)2 * E * sizeof(FpsEntry) +
                       (MODE == 2 ? (size_t)2 * WARPS * sizeof(FpsEntry) : 0);
   auto kern = fps_kernel<PP, T, MODE>;
@@ -446,10 +525,21 @@ static int cluster_capacity(int dev, int c, int nsm) {
   return cap;
 }
 
-// Per-iteration cost model in SM cycles (fitted to B200 measurements, profiles/fps_r1_notes.md):
-// every warp issues ~6.5 instructions per resident point plus ~90 for the exchange, T/128 warps
-// share a scheduler; the exchange itself costs ~150 cycles inside one CTA and ~600 across a
-// cluster (st.async + mbarrier round trip through distributed shared memory).
+// Per-iteration cost model in SM cycles, cost = base + slope * PP (PP = point pairs per thread), fitted to B200
+// measurements at B = 32 (tools/fps_time2.py with PS_FPS_CLUSTER / PS_FPS_THREADS forced; profiles/fps_r1_notes.md):
+// one warp per scheduler cannot hide its own dependency chains, so the per-pair cost is ~20 cycles rather than
+// the ~7 issue slots it needs, and every configuration carries 550-800 cycles of exchange + reduction latency.
+//   C=1 T=128: 565 + 23.5 PP     C=1 T=256: 725 + 43 PP
+//   C=2 T=128: 758 + 19.7 PP     C=2 T=256: 800 + 38 PP
+//   C=4 T=128: 800 + 16.7 PP     C=4 T=256: 860 + 33 PP
+//   C=8      : (T/128) * (13 PP + 90) + 940   (two-level exchange; B=4 N=16384 measured 1132 cycles at PP=8)
+//   C=16     : (T/128) * (13 PP + 90) + 1300  (only reachable when the cloud needs 16 CTAs)
+static double fps_iter_cost(int c, int t, int pp) {
+  if (c == 1) return t == 128 ? 565.0 + 23.5 * pp : 725.0 + 43.0 * pp;
+  if (c == 2) return t == 128 ? 758.0 + 19.7 * pp : 800.0 + 38.0 * pp;
+  if (c == 4) return t == 128 ? 800.0 + 16.7 * pp : 860.0 + 33.0 * pp;
+  return (t / 128) * (13.0 * pp + 90.0) + (c == 8 ? 940.0 : 1300.0);
+}
 static bool plan_fps(int B, int N, int L, int nper, int nsm, int dev, FpsPlan& best) {
   const long long R = (long long)nper << L;
   int force_c = 0, force_t = 0;
@@ -465,7 +555,7 @@ static bool plan_fps(int B, int N, int L, int nper, int nsm, int dev, FpsPlan& b
       while ((long long)2 * pp * c * t < R) pp *= 2;
       if (pp > 16) continue;
       const int waves = ceil_div(B, cluster_capacity(dev, c, nsm));  // clusters that do not fit wait for a free GPC slot
-      const double cost = waves * ((t / 128) * (6.5 * 2 * pp + 90.0) + (c == 1 ? 150.0 : 600.0));
+      const double cost = waves * fps_iter_cost(c, t, pp);
       if (cost < best_cost - 1e-9) { best_cost = cost; best = {c, t, pp}; found = true; }
     }
   }
@@ -490,7 +580,7 @@ extern "C" int ps_fps_sample(const float* xyz, int* idx, float* new_xyz, int B, 
   const int nsm = sm_count(dev);
 
   FpsArgs a;
-  a.xyz = xyz; a.idx = idx; a.new_xyz = new_xyz; a.N = N; a.npoint = npoint;
+  a.xyz = xyz; a.idx = idx; a.new_xyz = new_xyz; a.N = N; a.npoint = npoint; a.err = nullptr;
   a.L = ref_block_log2(N);
   a.nper = ceil_div(N, 1 << a.L);
 
@@ -504,12 +594,15 @@ extern "C" int ps_fps_sample(const float* xyz, int* idx, float* new_xyz, int B, 
     PS_CUDA(cudaFreeAsync(temp, stream));
     return PS_OK;
   }
+  // exchange for small clusters: tag polling on plain remote stores (MODE 3) or st.async + mbarrier (MODE 1)
+  bool poll = false;
+  if (const char* e = getenv("PS_FPS_EXCHANGE")) poll = (e[0] == 'p');
   if (pl.T == 128) {
     if (pl.C == 1) return dispatch_pp<128, 0>(pl.PP, a, B, pl.C, stream);
-    if (pl.C <= 4) return dispatch_pp<128, 1>(pl.PP, a, B, pl.C, stream);
+    if (pl.C <= 4) return poll ? dispatch_pp<128, 3>(pl.PP, a, B, pl.C, stream) : dispatch_pp<128, 1>(pl.PP, a, B, pl.C, stream);
     return dispatch_pp<128, 2>(pl.PP, a, B, pl.C, stream);
   }
   if (pl.C == 1) return dispatch_pp<256, 0>(pl.PP, a, B, pl.C, stream);
-  if (pl.C <= 4) return dispatch_pp<256, 1>(pl.PP, a, B, pl.C, stream);
+  if (pl.C <= 4) return poll ? dispatch_pp<256, 3>(pl.PP, a, B, pl.C, stream) : dispatch_pp<256, 1>(pl.PP, a, B, pl.C, stream);
   return dispatch_pp<256, 2>(pl.PP, a, B, pl.C, stream);
 }
