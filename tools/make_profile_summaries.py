@@ -20,7 +20,7 @@ for k, v in seq:
     a[1] += v
 tot = sum(v for _, v in seq)
 with open(f"profiles/launches_{tag}_summary.txt", "w") as f:
-    f.write("ncu --metrics gpu__time_duration.sum --clock-control none -c 700 python bench.py --steps 3 --warmup 3 --no-cpu\n")
+    f.write("ncu --metrics gpu__time_duration.sum --clock-control none -c 900 python bench.py --steps 3 --warmup 3 --no-cpu\n")
     f.write("(cold-cache, serialised launches: compare SHARES, not absolutes)  total %.1f us over %d launches\n\n" % (tot, len(seq)))
     f.write("%8s %10s %9s %7s  kernel\n" % ("count", "sum_us", "avg_us", "share"))
     for k, (c, v) in sorted(agg.items(), key=lambda kv: -kv[1][1]):
