@@ -144,11 +144,13 @@ __global__ void __launch_bounds__(FK_THREADS) knn_feat_kernel(const FkArgs a) {
 
   const int nstage = (C + FK_KC - 1) / FK_KC;
   for (int r0 = 0; r0 < npad; r0 += FK_TR) {
-    float acc[QPT][8];
+    // accumulators as packed pairs of references: one FFMA2 per (query, 2 references, channel); each half rounds
+    // like the scalar FFMA, so the ascending-channel chain is unchanged
+    u64 acc2[QPT][4];
 #pragma unroll
     for (int i = 0; i < QPT; i++)
 #pragma unroll
-      for (int j = 0; j < 8; j++) acc[i][j] = 0.f;
+      for (int j = 0; j < 4; j++) acc2[i][j] = 0ull;
     fetch(r0, 0);
     for (int st = 0; st < nstage; st++) {
       const int c0 = st * FK_KC;
@@ -160,8 +162,8 @@ __global__ void __launch_bounds__(FK_THREADS) knn_feat_kernel(const FkArgs a) {
       // ascending-channel FMA chain per (query, reference) pair; a partial last stage stops at kcn so that
       // no padded product enters the chain
       auto step = [&](int kc) {
-        const float4 r0v = *reinterpret_cast<const float4*>(&rs[kc * FK_TR + lane * 4]);
-        const float4 r1v = *reinterpret_cast<const float4*>(&rs[kc * FK_TR + 128 + lane * 4]);
+        const ulonglong2 r0v = *reinterpret_cast<const ulonglong2*>(&rs[kc * FK_TR + lane * 4]);
+        const ulonglong2 r1v = *reinterpret_cast<const ulonglong2*>(&rs[kc * FK_TR + 128 + lane * 4]);
         float qv[QPT];
         if (QPT == 4) {
           const float4 t = *reinterpret_cast<const float4*>(&qs[kc * TQ + warp * 4]);
@@ -172,14 +174,11 @@ __global__ void __launch_bounds__(FK_THREADS) knn_feat_kernel(const FkArgs a) {
         }
 #pragma unroll
         for (int i = 0; i < QPT; i++) {
-          acc[i][0] = __fmaf_rn(qv[i], r0v.x, acc[i][0]);
-          acc[i][1] = __fmaf_rn(qv[i], r0v.y, acc[i][1]);
-          acc[i][2] = __fmaf_rn(qv[i], r0v.z, acc[i][2]);
-          acc[i][3] = __fmaf_rn(qv[i], r0v.w, acc[i][3]);
-          acc[i][4] = __fmaf_rn(qv[i], r1v.x, acc[i][4]);
-          acc[i][5] = __fmaf_rn(qv[i], r1v.y, acc[i][5]);
-          acc[i][6] = __fmaf_rn(qv[i], r1v.z, acc[i][6]);
-          acc[i][7] = __fmaf_rn(qv[i], r1v.w, acc[i][7]);
+          const u64 qd = pack2(qv[i], qv[i]);
+          acc2[i][0] = fma2(qd, r0v.x, acc2[i][0]);
+          acc2[i][1] = fma2(qd, r0v.y, acc2[i][1]);
+          acc2[i][2] = fma2(qd, r1v.x, acc2[i][2]);
+          acc2[i][3] = fma2(qd, r1v.y, acc2[i][3]);
         }
       };
       if (kcn == FK_KC) {
@@ -189,6 +188,11 @@ __global__ void __launch_bounds__(FK_THREADS) knn_feat_kernel(const FkArgs a) {
         for (int kc = 0; kc < kcn; kc++) step(kc);
       }
     }
+    float acc[QPT][8];
+#pragma unroll
+    for (int i = 0; i < QPT; i++)
+#pragma unroll
+      for (int j = 0; j < 4; j++) { acc[i][2 * j] = lo2(acc2[i][j]); acc[i][2 * j + 1] = hi2(acc2[i][j]); }
     // dist = ((-2 * dot) + |q|^2) + |r|^2 ; padding columns at +inf
 #pragma unroll
     for (int h = 0; h < 2; h++) {
