@@ -153,8 +153,8 @@ def run_ours(args):
         from svdformer_pointsea_b200.dist import bind_to_gpu_numa_node
         numa_cpus = bind_to_gpu_numa_node(local_rank)  # before any pinned allocation (first touch)
     if world > 1:
-        if os.environ.get("NCCL_DEBUG", "VERSION").upper() == "VERSION":
-            os.environ["NCCL_DEBUG"] = "WARN"  # keep NCCL's version banner off stdout: rank 0 prints ONE JSON line
+        # NCCL writes its version banner / warnings to stdout by default; rank 0 must print ONE JSON line there
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
         dist.init_process_group("nccl", device_id=dev)
     ps.load_library()
     peaks, peaks_src = measured_peaks()
@@ -203,11 +203,15 @@ def run_ours(args):
     reducer.flush()
     torch.cuda.synchronize()
     fp32_peak = L.measure_fp32_peak(local_rank, 5)
+    # everything with a variable host cost (NVML initialisation of the clock sampler) happens BEFORE the barrier:
+    # ranks must enter the timed region together, or the early ones spend their first steps waiting for the
+    # collective of the late ones (seen at 8 GPUs: 0.63 instead of 0.38 ms per step over 20 steps)
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    torch.cuda.synchronize()
     if world > 1:
         dist.barrier()
     torch.cuda.synchronize()
-    sampler = ClockSampler(local_rank)
-    sampler.start()
     L.launch_count(reset=True)
     evs = []
     t_host0 = time.perf_counter()

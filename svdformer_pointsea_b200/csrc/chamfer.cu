@@ -339,7 +339,7 @@ extern "C" int ps_chamfer_fwd(const float* xyz1, const float* xyz2, float* dist1
   u64* scratch = nullptr;
   if (need[0] + need[1]) {
     if (int rc = scratch_alloc((void**)&scratch, (need[0] + need[1]) * sizeof(u64), dev, stream)) return rc;
-    PS_CUDA(cudaMemsetAsync(scratch, 0xFF, (need[0] + need[1]) * sizeof(u64), stream));
+    if (int rc = fill32_async(scratch, 0xffffffffu, (need[0] + need[1]) * sizeof(u64), stream)) return rc;
   }
   p.d[0].keys = need[0] ? scratch : nullptr;
   p.d[1].keys = need[1] ? scratch + need[0] : nullptr;

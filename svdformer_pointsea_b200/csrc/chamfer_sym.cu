@@ -516,7 +516,7 @@ int chamfer_fwd_symmetric(const float* xyz1, const float* xyz2, float* dist1, fl
   const size_t nka = (size_t)B * big, nkb = (size_t)B * small;
   u64* scratch = nullptr;
   if (int rc = scratch_alloc((void**)&scratch, (nka + nkb) * sizeof(u64), dev, stream)) return rc;
-  PS_CUDA(cudaMemsetAsync(scratch, 0xFF, (nka + nkb) * sizeof(u64), stream));
+  if (int rc = fill32_async(scratch, 0xffffffffu, (nka + nkb) * sizeof(u64), stream)) return rc;
   p.keys_a = scratch;
   p.keys_b = scratch + nka;
   // tail balancing (see SymParams): cut the units of the last, partially filled wave

@@ -61,6 +61,8 @@ struct DeviceGuard {
 int sm_count(int dev);
 // stream-ordered scratch allocation (pool keeps freed blocks cached); free with cudaFreeAsync
 int scratch_alloc(void** ptr, size_t bytes, int dev, cudaStream_t stream);
+// fills `bytes` (multiple of 4) with the 32-bit pattern `value` by a kernel launch (see runtime.cu for why not memset)
+int fill32_async(void* ptr, unsigned value, size_t bytes, cudaStream_t stream);
 
 // chamfer_sym.cu: PS_OK when handled, 1 when the two-pass kernel should run instead
 int chamfer_fwd_symmetric(const float* xyz1, const float* xyz2, float* dist1, float* dist2, int* idx1,

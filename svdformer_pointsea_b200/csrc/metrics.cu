@@ -128,7 +128,7 @@ extern "C" int ps_chamfer_metrics(const float* dist1, const float* dist2, const 
     } else {
       const size_t bytes = (size_t)B * ((size_t)n1 + n2) * sizeof(int);
       if (int rc = scratch_alloc((void**)&gcount, bytes, dev, stream)) return rc;
-      PS_CUDA(cudaMemsetAsync(gcount, 0, bytes, stream));
+      if (int rc = fill32_async(gcount, 0u, bytes, stream)) return rc;
     }
   }
   PS_CUDA(cudaFuncSetAttribute(chamfer_metrics_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(MT_SMEM_POINTS * sizeof(int))));
