@@ -327,7 +327,7 @@ def run_ours(args):
         if "ops" in result:
             result["ops"]["cpu"] = cpu_ops_baseline()
     if rank == 0:
-        print(json.dumps(result))
+        emit(result)
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
@@ -475,7 +475,7 @@ def run_reference(args):
     pairs = 2.0 * bs * C1["N"] * C1["M"]
     value = pairs * len(ts) / sum(ts) / 1e9
     sample = f"{bs} of the 32 C1 clouds per step, pure-torch direct-form fwd+bwd on {torch.get_num_threads()} threads"
-    print(json.dumps({
+    emit({
         "impl": "reference", "metric": "chamfer_fwd_bwd_gpair_per_s", "value": round(value, 4), "unit": "Gpair/s",
         "n_gpus": int(os.environ.get("WORLD_SIZE", args.gpus)), "steps": args.steps, "warmup": warm,
         "ms_per_step": round(sum(ts) / len(ts) * 1e3, 2), "higher_is_better": True, "scaling": "weak",
@@ -485,10 +485,33 @@ def run_reference(args):
                          "sample": sample},
         "e2e": {"value": round(value, 4), "unit": "Gpair/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
-    }))
+    })
+
+
+_RESULT_FD = None
+
+
+def claim_stdout():
+    """Keep stdout for the ONE JSON line: libraries that print there (NCCL's version banner does, whatever
+    NCCL_DEBUG_FILE says) are pointed at stderr for the whole run; emit() writes to the saved descriptor."""
+    global _RESULT_FD
+    if _RESULT_FD is None:
+        sys.stdout.flush()
+        _RESULT_FD = os.dup(1)
+        os.dup2(2, 1)
+
+
+def emit(obj):
+    line = (json.dumps(obj) + "\n").encode()
+    if _RESULT_FD is None:
+        sys.stdout.write(line.decode())
+        sys.stdout.flush()
+    else:
+        os.write(_RESULT_FD, line)
 
 
 def main():
+    claim_stdout()
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=20)
