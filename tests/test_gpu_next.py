@@ -69,7 +69,9 @@ def test_knn_feat_vs_oracle(B, C, N, S, k, order):
         assert np.array_equal(mo.knn_point_raw(xr.to(DEV), xq.to(DEV), k).cpu().numpy(), want)
 
 
-@pytest.mark.parametrize("B,C,N,k", [(4, 3, 2048, 16), (8, 3, 1024, 16), (4, 64, 512, 8), (2, 256, 512, 4), (2, 64, 1024, 8)])
+@pytest.mark.parametrize("B,C,N,k", [(4, 3, 2048, 16), (8, 3, 1024, 16), (4, 64, 512, 8), (2, 256, 512, 4), (2, 64, 1024, 8),
+                                     (2, 5, 300, 4), (2, 17, 300, 8), (2, 32, 200, 8), (2, 100, 260, 8), (2, 128, 256, 4),
+                                     (2, 132, 256, 4), (1, 512, 128, 4), (1, 7, 9, 3)])
 def test_query_knn_point_vs_torch_cuda_live(B, C, N, k):
     """The reference expression (square_distance + topk) run by torch on this GPU, with duplicated points:
     B*N slices x N elements puts torch.topk on its multi-block radix path for the larger cases."""
