@@ -160,7 +160,7 @@ __global__ void __launch_bounds__(CS_THREADS, 2) chamfer_sym_kernel(const SymPar
     // B point j32 + l) and merged into shared memory with ONE 64-bit atomicMin per lane.
     int step = (ts - t0) / CS_STEP;
     for (int j32 = 0; j32 < cnt_pad; j32 += 32) {
-      unsigned key_m = 0xffffffffu, key_t = 0u;
+      unsigned key_m = 0xffffffffu, key_b = 1u;  // owner lane keeps the ballot MASK; ffs once per 32 B points
       const int jend = min(cnt_pad, j32 + 32);
 #pragma unroll 2
       for (int j = j32; j < jend; j += CS_STEP, step++) {
@@ -193,18 +193,18 @@ __global__ void __launch_bounds__(CS_THREADS, 2) chamfer_sym_kernel(const SymPar
         const unsigned m1 = __reduce_min_sync(0xffffffffu, b1);
         const unsigned m2 = __reduce_min_sync(0xffffffffu, b2);
         const unsigned m3 = __reduce_min_sync(0xffffffffu, b3);
-        const unsigned l0 = __ffs(__ballot_sync(0xffffffffu, b0 == m0)) - 1;
-        const unsigned l1 = __ffs(__ballot_sync(0xffffffffu, b1 == m1)) - 1;
-        const unsigned l2 = __ffs(__ballot_sync(0xffffffffu, b2 == m2)) - 1;
-        const unsigned l3 = __ffs(__ballot_sync(0xffffffffu, b3 == m3)) - 1;
+        const unsigned l0 = __ballot_sync(0xffffffffu, b0 == m0);
+        const unsigned l1 = __ballot_sync(0xffffffffu, b1 == m1);
+        const unsigned l2 = __ballot_sync(0xffffffffu, b2 == m2);
+        const unsigned l3 = __ballot_sync(0xffffffffu, b3 == m3);
         const int o = lane - (j - j32);  // 0..3 for the four owner lanes of this step
-        if (o == 0) { key_m = m0; key_t = l0; }
-        if (o == 1) { key_m = m1; key_t = l1; }
-        if (o == 2) { key_m = m2; key_t = l2; }
-        if (o == 3) { key_m = m3; key_t = l3; }
+        if (o == 0) { key_m = m0; key_b = l0; }
+        if (o == 1) { key_m = m1; key_b = l1; }
+        if (o == 2) { key_m = m2; key_b = l2; }
+        if (o == 3) { key_m = m3; key_b = l3; }
       }
       if (j32 + lane < cnt_pad)
-        atomicMin(&colkey[j32 + lane], ((u64)key_m << 32) | (unsigned)(warp * 32 + key_t));
+        atomicMin(&colkey[j32 + lane], ((u64)key_m << 32) | (unsigned)(warp * 32 + __ffs(key_b) - 1));
     }
     __syncthreads();  // all column keys of this tile are final
 
