@@ -97,3 +97,32 @@ def test_bench_reference_arm_contract():
     line = json.loads(out.stdout.strip().splitlines()[-1])
     assert line["impl"] == "reference" and line["metric"] == "chamfer_fwd_bwd_gpair_per_s" and line["unit"] == "Gpair/s"
     assert line["cpu_baseline"]["cores"] >= 1 and line["e2e"]["h2d_bytes_per_step"] == 0
+
+
+def test_next_row_surface_and_cpu_rejection():
+    """SURVEY 8(f) names exist with the reference's signatures and refuse CPU tensors (no fallback)."""
+    import inspect
+    for name in ("query_knn_point", "index_points", "group_local", "sample_and_group_knn", "EdgeConv", "edge_features",
+                 "calc_cd", "calc_dcd", "fscore", "patch_model_utils", "patch_loss_utils", "chamfer_host_step"):
+        assert hasattr(ps, name), name
+    assert list(inspect.signature(ps.query_knn_point).parameters) == ["k", "xyz", "new_xyz"]
+    assert list(inspect.signature(ps.sample_and_group_knn).parameters) == ["xyz", "points", "npoint", "k", "use_xyz", "idx"]
+    assert list(inspect.signature(ps.group_local).parameters) == ["xyz", "k", "return_idx"]
+    assert list(inspect.signature(ps.calc_cd).parameters) == ["output", "gt", "calc_f1", "return_raw", "normalize", "separate"]
+    assert list(inspect.signature(ps.calc_dcd).parameters) == ["x", "gt", "alpha", "n_lambda", "return_raw", "non_reg"]
+    x = torch.rand(2, 32, 3)
+    f = torch.rand(2, 8, 32)
+    for fn in (lambda: ps.query_knn_point(4, x, x), lambda: ps.query_knn_point(4, torch.rand(2, 32, 8), torch.rand(2, 32, 8)),
+               lambda: ps.edge_features(f, 4), lambda: ps.index_points(x, torch.zeros(2, 5, dtype=torch.long)),
+               lambda: ps.sample_and_group_knn(x.transpose(1, 2).contiguous(), None, 8, 4),
+               lambda: ps.calc_cd(x, x), lambda: ps.calc_dcd(x, x), lambda: ps.fscore(torch.rand(2, 5), torch.rand(2, 6))):
+        with pytest.raises(ps.PointSeaError):
+            fn()
+    # EdgeConv keeps the reference's parameter names (state_dict compatibility: models/model_utils.py:856-866)
+    keys = set(ps.EdgeConv(3, 64, 16).state_dict().keys())
+    assert {"conv.0.weight", "conv.1.running_mean", "conv.3.weight", "conv.6.bias"} <= keys
+
+
+def test_pipelined_sums_and_numa_helper_never_raise_without_a_gpu():
+    from svdformer_pointsea_b200.dist import bind_to_gpu_numa_node
+    assert bind_to_gpu_numa_node(0) is None or isinstance(bind_to_gpu_numa_node(0), set)
