@@ -19,8 +19,12 @@
  *     thread-local message.  Nothing ever calls exit() (the reference's CUDA_CHECK_ERRORS
  *     does: pointnet2_ops/_ext-src/include/cuda_utils.h:30-39) and no error is silently
  *     dropped (the reference's Chamfer returns an int Python ignores: chamfer3D.cu:145-150).
- *   - re-entrant: no global mutable state; safe to call concurrently from several host
- *     threads on different devices (nn.DataParallel replica threads).
+ *   - thread-safe: callable concurrently from several host threads on the same or different
+ *     devices (nn.DataParallel replica threads).  The only process-wide state is per-device
+ *     and internally synchronised: a private scratch memory pool and cached device attributes
+ *     (runtime.cu), and the mutex-guarded staging slots / CUDA-graph caches of the one-launch
+ *     step entry points (step.cu, host_pipeline.cu).  Error text and the launch counter are
+ *     thread-local.
  */
 #ifndef POINTSEA_B200_H
 #define POINTSEA_B200_H
@@ -67,6 +71,50 @@ int ps_chamfer_bwd(const float* xyz1, const float* xyz2, const float* graddist1,
 int ps_chamfer_sums(const float* dist1, const float* dist2, double* out6, long long n1, long long n2,
                     int dev, void* stream);
 
+/* ps_chamfer_fwd with the callers' reductions (utils/loss_utils.py:10-31: mean / mean-of-sqrt per side) fused
+ * into the forward's epilogue launch: sums6 (device, 6 doubles, layout of ps_chamfer_sums) comes out of the pass
+ * that writes dist/idx, without re-reading them.  The sums are accumulated in a fixed order (bit-reproducible). */
+int ps_chamfer_fwd_sums(const float* xyz1, const float* xyz2, float* dist1, float* dist2, int* idx1, int* idx2,
+                        double* sums6, int B, int N, int M, int dev, void* stream);
+
+/* ---- the single collective of the batch-sharded path, over peer memory ---------------------------
+ * The reference has no multi-process path (nn.DataParallel gathers on one GPU); its loss reductions
+ * (utils/loss_utils.py:10-19,50-57) are what has to be summed across ranks.  A ps_comm is a set of per-rank
+ * MAILBOXES in device memory that the peers store into directly over NVLink: the kernel that produces the sums
+ * publishes them, a one-warp kernel adds the world's contributions in rank order (bit-identical on every rank).
+ * No host call per step, so a whole step replays as one CUDA graph.  Setup (once):
+ *   ps_comm_create on every rank -> ps_comm_export (an opaque ps_comm_handle_bytes()-byte handle, CUDA IPC) ->
+ *   exchange the handles by any host channel (torch.distributed.all_gather_object, MPI, a file) ->
+ *   ps_comm_connect(handles of all ranks, rank order).  Ranks living in ONE process (threads, tests) use
+ *   ps_comm_connect_local instead.  Every rank must issue the same sequence of collective calls. */
+typedef struct ps_comm ps_comm;
+int ps_comm_create(int rank, int world, int dev, ps_comm** out);
+int ps_comm_handle_bytes(void);
+int ps_comm_export(ps_comm* comm, void* handle);
+int ps_comm_connect(ps_comm* comm, const void* handles /* world x ps_comm_handle_bytes() */);
+int ps_comm_connect_local(ps_comm* const* comms, int world);
+/* out[0..n) (device) = sum over ranks of in[0..n) (device), n <= 30, one launch on `stream`. */
+int ps_comm_allreduce(ps_comm* comm, const double* in, double* out, int n, void* stream);
+/* Diagnostics (synchronises the device): messages published / consumed, and whether a wait timed out
+ * (a lost peer gives NaN results and this flag after ~4 s instead of hanging the GPU). */
+int ps_comm_status(ps_comm* comm, long long* published, long long* consumed, int* timed_out);
+int ps_comm_destroy(ps_comm* comm);
+
+/* One training-style Chamfer step on DEVICE buffers as ONE launch: forward + loss sums (+ publish to the peers)
+ * + backward (+ wait: world-wide sums).  Equivalent to ps_chamfer_fwd_sums, ps_chamfer_bwd and — with a
+ * communicator — ps_comm_allreduce of the sums, captured into a CUDA graph keyed by the arguments and replayed
+ * with a single cudaGraphLaunch (fresh buffer addresses retarget the cached graph in place).  graddist1 ==
+ * graddist2 == NULL: forward + sums only.  comm == NULL: sums_global6 is not written.  Buffers as in
+ * ps_chamfer_fwd / ps_chamfer_bwd; sums_local6 / sums_global6: device, 6 doubles each. */
+int ps_chamfer_step(const float* xyz1, const float* xyz2, const float* graddist1, const float* graddist2,
+                    float* dist1, float* dist2, int* idx1, int* idx2, float* gradxyz1, float* gradxyz2,
+                    double* sums_local6, double* sums_global6, ps_comm* comm, int B, int N, int M, int dev,
+                    void* stream);
+/* Graph-cache counters of ps_chamfer_step / of the host-buffer entry points on `dev`: exact replays, in-place
+ * retargets (cudaGraphExecUpdate) and instantiations so far. */
+int ps_chamfer_step_stats(int dev, long long* hits, long long* updates, long long* instantiations);
+int ps_chamfer_host_stats(int dev, long long* hits, long long* updates, long long* instantiations);
+
 /* Host-buffer form of one Chamfer step (forward, and backward when graddist1/2 are given): every
  * pointer here is a HOST pointer with the shapes of ps_chamfer_fwd / ps_chamfer_bwd.  This is the
  * call for the reference's CPU-allocating wrapper (dist_chamfer_3D.py:33-42 allocates dist/idx on
@@ -92,6 +140,18 @@ int ps_chamfer_host(const float* xyz1, const float* xyz2, float* dist1, float* d
 int ps_chamfer_host_step(const float* xyz1, const float* xyz2, const float* graddist1, const float* graddist2,
                          float* dev_gradxyz1, float* dev_gradxyz2, double* sums6, int B, int N, int M, int chunk,
                          int dev, void* stream);
+
+/* ps_chamfer_host_step on a batch shard: sums6 receives the WORLD-WIDE sums (the local sums are exchanged
+ * through `comm` by a kernel inside the same graph, after the last chunk). */
+int ps_chamfer_host_step_dist(const float* xyz1, const float* xyz2, const float* graddist1, const float* graddist2,
+                              float* dev_gradxyz1, float* dev_gradxyz2, double* sums6, ps_comm* comm, int B, int N,
+                              int M, int chunk, int dev, void* stream);
+
+/* General host-buffer form: everything ps_chamfer_host downloads (dist, idx, gradients) plus the loss sums
+ * (sums6, HOST, may be NULL), world-wide when `comm` is given (may be NULL).  Same pipeline, same graph. */
+int ps_chamfer_host_full(const float* xyz1, const float* xyz2, float* dist1, float* dist2, int* idx1, int* idx2,
+                         const float* graddist1, const float* graddist2, float* gradxyz1, float* gradxyz2,
+                         double* sums6, ps_comm* comm, int B, int N, int M, int chunk, int dev, void* stream);
 
 /* ---- Furthest point sampling ------------------------------------------------------------
  * Replaces furthest_point_sampling_kernel_wrapper (pointnet2_ops/_ext-src/src/sampling_gpu.cu:175-229,

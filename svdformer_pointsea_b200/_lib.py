@@ -24,7 +24,20 @@ _SIGNATURES = {
     "ps_chamfer_fwd": [_P, _P, _P, _P, _P, _P, _c_int, _c_int, _c_int, _c_int, _P],
     "ps_chamfer_bwd": [_P, _P, _P, _P, _P, _P, _P, _P, _c_int, _c_int, _c_int, _c_int, _P],
     "ps_chamfer_host": [_P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _c_int, _c_int, _c_int, _c_int, _c_int, _P],
+    "ps_chamfer_host_full": [_P] * 12 + [_c_int, _c_int, _c_int, _c_int, _c_int, _P],
     "ps_chamfer_host_step": [_P, _P, _P, _P, _P, _P, _P, _c_int, _c_int, _c_int, _c_int, _c_int, _P],
+    "ps_chamfer_fwd_sums": [_P, _P, _P, _P, _P, _P, _P, _c_int, _c_int, _c_int, _c_int, _P],
+    "ps_chamfer_step": [_P] * 13 + [_c_int, _c_int, _c_int, _c_int, _P],
+    "ps_chamfer_step_stats": [_c_int, ctypes.POINTER(ctypes.c_longlong), ctypes.POINTER(ctypes.c_longlong), ctypes.POINTER(ctypes.c_longlong)],
+    "ps_chamfer_host_stats": [_c_int, ctypes.POINTER(ctypes.c_longlong), ctypes.POINTER(ctypes.c_longlong), ctypes.POINTER(ctypes.c_longlong)],
+    "ps_chamfer_host_step_dist": [_P, _P, _P, _P, _P, _P, _P, _P, _c_int, _c_int, _c_int, _c_int, _c_int, _P],
+    "ps_comm_create": [_c_int, _c_int, _c_int, ctypes.POINTER(_c_void_p)],
+    "ps_comm_export": [_P, _P],
+    "ps_comm_connect": [_P, _P],
+    "ps_comm_connect_local": [ctypes.POINTER(_c_void_p), _c_int],
+    "ps_comm_allreduce": [_P, _P, _P, _c_int, _P],
+    "ps_comm_status": [_P, ctypes.POINTER(ctypes.c_longlong), ctypes.POINTER(ctypes.c_longlong), ctypes.POINTER(_c_int)],
+    "ps_comm_destroy": [_P],
     "ps_chamfer_sums": [_P, _P, _P, ctypes.c_longlong, ctypes.c_longlong, _c_int, _P],
     "ps_fps": [_P, _P, _c_int, _c_int, _c_int, _c_int, _P],
     "ps_fps_sample": [_P, _P, _P, _c_int, _c_int, _c_int, _c_int, _P],
@@ -49,7 +62,7 @@ _SIGNATURES = {
     "ps_device_info": [_c_int, ctypes.POINTER(_c_int), ctypes.POINTER(_c_int), ctypes.POINTER(_c_int)],
     "ps_measure_fp32_peak": [_c_int, _c_int, ctypes.POINTER(ctypes.c_double)],
 }
-EXPORTED_SYMBOLS = sorted(list(_SIGNATURES) + ["ps_version", "ps_last_error", "ps_launch_count"])
+EXPORTED_SYMBOLS = sorted(list(_SIGNATURES) + ["ps_version", "ps_last_error", "ps_launch_count", "ps_comm_handle_bytes"])
 
 _lib = None
 
@@ -76,6 +89,8 @@ def load():
     lib.ps_version.restype = _c_int
     lib.ps_last_error.argtypes = []
     lib.ps_last_error.restype = ctypes.c_char_p
+    lib.ps_comm_handle_bytes.argtypes = []
+    lib.ps_comm_handle_bytes.restype = _c_int
     lib.ps_launch_count.argtypes = [_c_int]
     lib.ps_launch_count.restype = ctypes.c_longlong
     _lib = lib
@@ -148,6 +163,14 @@ def ptr(t):
 
 def launch_count(reset=False):
     return int(load().ps_launch_count(1 if reset else 0))
+
+
+def graph_stats(index=0, which="step"):
+    """(exact replays, in-place retargets, instantiations) of the one-launch entry points' graph cache."""
+    h, u, i = ctypes.c_longlong(), ctypes.c_longlong(), ctypes.c_longlong()
+    fn = load().ps_chamfer_step_stats if which == "step" else load().ps_chamfer_host_stats
+    check(fn(index, ctypes.byref(h), ctypes.byref(u), ctypes.byref(i)), "graph stats")
+    return {"hits": h.value, "updates": u.value, "instantiations": i.value}
 
 
 def measure_fp32_peak(index=0, reps=5):

@@ -20,9 +20,11 @@ def _check_out(t, name, dtype, shape, like):
     return t
 
 
-def chamfer_forward(xyz1, xyz2, out=None):
+def chamfer_forward(xyz1, xyz2, out=None, sums=None):
     """(dist1, dist2, idx1, idx2) for xyz1 (B,N,3), xyz2 (B,M,3); no autograd.  `out` may carry the four
-    preallocated outputs, as the reference's pybind `chamfer_3D.forward` takes them (chamfer_cuda.cpp:17-19)."""
+    preallocated outputs, as the reference's pybind `chamfer_3D.forward` takes them (chamfer_cuda.cpp:17-19).
+    `sums`: a (6,) float64 CUDA tensor that receives the loss sums of `chamfer_sums` from the same launch that
+    writes dist/idx (ps_chamfer_fwd_sums)."""
     L.require(xyz1, "xyz1", torch.float32, 3)
     L.require(xyz2, "xyz2", torch.float32, 3)
     if xyz1.size(2) != 3 or xyz2.size(2) != 3 or xyz1.size(0) != xyz2.size(0):
@@ -41,10 +43,62 @@ def chamfer_forward(xyz1, xyz2, out=None):
         dist2 = torch.empty(B, M, device=xyz1.device, dtype=torch.float32)
         idx1 = torch.empty(B, N, device=xyz1.device, dtype=torch.int32)
         idx2 = torch.empty(B, M, device=xyz1.device, dtype=torch.int32)
+    if sums is not None:
+        _check_out(sums, "sums", torch.float64, (6,), xyz1)
+        rc = L.load().ps_chamfer_fwd_sums(L.ptr(xyz1), L.ptr(xyz2), L.ptr(dist1), L.ptr(dist2), L.ptr(idx1), L.ptr(idx2),
+                                          L.ptr(sums), B, N, M, dev, L.stream_ptr(dev))
+        L.check(rc, "ps_chamfer_fwd_sums")
+        return dist1, dist2, idx1, idx2
     rc = L.load().ps_chamfer_fwd(L.ptr(xyz1), L.ptr(xyz2), L.ptr(dist1), L.ptr(dist2), L.ptr(idx1), L.ptr(idx2),
                                  B, N, M, dev, L.stream_ptr(dev))
     L.check(rc, "ps_chamfer_fwd")
     return dist1, dist2, idx1, idx2
+
+
+class ChamferStep:
+    """One training-style Chamfer step on DEVICE clouds as ONE launch (ps_chamfer_step): forward + loss sums
+    [+ publish to the peers] + backward [+ world-wide sums], replayed from a CUDA graph.
+
+    Buffers are allocated once for a shape; `__call__(xyz1, xyz2, graddist1, graddist2)` returns
+    `(sums_local, sums_global, gradxyz1, gradxyz2)` — device tensors owned by this object (overwritten by the next
+    call); `dist1/dist2/idx1/idx2` are attributes.  `comm`: a `dist.PeerComm` (then `sums_global` holds the sums over
+    all ranks, identical bits on every rank) or None (`sums_global` is `sums_local`)."""
+
+    def __init__(self, B, N, M, device, comm=None):
+        dev = torch.device(device)
+        self.B, self.N, self.M, self.device, self.comm = B, N, M, dev, comm
+        self.dist1 = torch.empty(B, N, device=dev)
+        self.dist2 = torch.empty(B, M, device=dev)
+        self.idx1 = torch.empty(B, N, device=dev, dtype=torch.int32)
+        self.idx2 = torch.empty(B, M, device=dev, dtype=torch.int32)
+        self.gradxyz1 = torch.empty(B, N, 3, device=dev)
+        self.gradxyz2 = torch.empty(B, M, 3, device=dev)
+        self.sums_local = torch.zeros(6, device=dev, dtype=torch.float64)
+        self.sums_global = torch.zeros(6, device=dev, dtype=torch.float64) if comm is not None else self.sums_local
+
+    def __call__(self, xyz1, xyz2, graddist1=None, graddist2=None):
+        B, N, M = self.B, self.N, self.M
+        L.require(xyz1, "xyz1", torch.float32, 3)
+        L.require(xyz2, "xyz2", torch.float32, 3)
+        if tuple(xyz1.shape) != (B, N, 3) or tuple(xyz2.shape) != (B, M, 3):
+            raise L.PointSeaError(f"ChamferStep was built for ({B},{N},3) / ({B},{M},3), got {tuple(xyz1.shape)} {tuple(xyz2.shape)}")
+        with_bwd = graddist1 is not None or graddist2 is not None
+        if with_bwd:
+            if graddist1 is None or graddist2 is None:
+                raise L.PointSeaError("ChamferStep: backward needs both graddist1 and graddist2")
+            L.require(graddist1, "graddist1", torch.float32, 2)
+            L.require(graddist2, "graddist2", torch.float32, 2)
+            dev = L.same_device(xyz1, xyz2, graddist1, graddist2, self.dist1)
+        else:
+            dev = L.same_device(xyz1, xyz2, self.dist1)
+        rc = L.load().ps_chamfer_step(
+            L.ptr(xyz1), L.ptr(xyz2), L.ptr(graddist1) if with_bwd else None, L.ptr(graddist2) if with_bwd else None,
+            L.ptr(self.dist1), L.ptr(self.dist2), L.ptr(self.idx1), L.ptr(self.idx2),
+            L.ptr(self.gradxyz1) if with_bwd else None, L.ptr(self.gradxyz2) if with_bwd else None,
+            L.ptr(self.sums_local), L.ptr(self.sums_global) if self.comm is not None else None,
+            self.comm.handle if self.comm is not None else None, B, N, M, dev, L.stream_ptr(dev))
+        L.check(rc, "ps_chamfer_step")
+        return self.sums_local, self.sums_global, (self.gradxyz1 if with_bwd else None), (self.gradxyz2 if with_bwd else None)
 
 
 def chamfer_backward(xyz1, xyz2, graddist1, graddist2, idx1, idx2, out=None):
@@ -95,7 +149,8 @@ def _require_host(t, name, dtype, shape):
     return t
 
 
-def chamfer_host(xyz1, xyz2, graddist1=None, graddist2=None, out=None, chunk=0, device=None, blocking=True):
+def chamfer_host(xyz1, xyz2, graddist1=None, graddist2=None, out=None, chunk=0, device=None, blocking=True, sums_out=None,
+                 comm=None):
     """Chamfer forward (+ backward when graddist1/2 are given) on HOST tensors, pipelined through the GPU.
 
     The batch is cut into chunks of `chunk` clouds (0: library default); upload, kernels and download
@@ -104,6 +159,8 @@ def chamfer_host(xyz1, xyz2, graddist1=None, graddist2=None, out=None, chunk=0, 
     pinned outputs `(dist1, dist2, idx1, idx2[, gradxyz1, gradxyz2])`, otherwise they are allocated
     pinned here.  With `blocking=False` the outputs are valid once the current CUDA stream of
     `device` has been synchronised.  Results are bit-identical to chamfer_forward / chamfer_backward.
+    `sums_out`: a pinned (6,) float64 CPU tensor that also receives the loss sums of `chamfer_sums`; with `comm` (a
+    `dist.PeerComm`) they are the sums over all ranks' shards, exchanged by a kernel inside the same graph.
     """
     if xyz1.dim() != 3 or xyz2.dim() != 3 or xyz1.size(2) != 3 or xyz2.size(2) != 3 or xyz1.size(0) != xyz2.size(0):
         raise L.PointSeaError(f"chamfer expects (B,N,3) and (B,M,3), got {tuple(xyz1.shape)} {tuple(xyz2.shape)}")
@@ -133,16 +190,25 @@ def chamfer_host(xyz1, xyz2, graddist1=None, graddist2=None, out=None, chunk=0, 
     for t, (shape, dt), nm in zip(out, shapes, ("dist1", "dist2", "idx1", "idx2", "gradxyz1", "gradxyz2")):
         _require_host(t, nm, dt, shape)
     gp = [L.ptr(graddist1), L.ptr(graddist2), L.ptr(out[4]), L.ptr(out[5])] if with_bwd else [None] * 4
-    rc = L.load().ps_chamfer_host(L.ptr(xyz1), L.ptr(xyz2), L.ptr(out[0]), L.ptr(out[1]), L.ptr(out[2]), L.ptr(out[3]),
-                                  gp[0], gp[1], gp[2], gp[3], B, N, M, int(chunk), index, L.stream_ptr(index))
-    L.check(rc, "ps_chamfer_host")
+    if sums_out is not None or comm is not None:
+        if sums_out is None:
+            raise L.PointSeaError("chamfer_host: `comm` needs `sums_out`")
+        _require_host(sums_out, "sums_out", torch.float64, (6,))
+        rc = L.load().ps_chamfer_host_full(L.ptr(xyz1), L.ptr(xyz2), L.ptr(out[0]), L.ptr(out[1]), L.ptr(out[2]), L.ptr(out[3]),
+                                           gp[0], gp[1], gp[2], gp[3], L.ptr(sums_out), comm.handle if comm is not None else None,
+                                           B, N, M, int(chunk), index, L.stream_ptr(index))
+        L.check(rc, "ps_chamfer_host_full")
+    else:
+        rc = L.load().ps_chamfer_host(L.ptr(xyz1), L.ptr(xyz2), L.ptr(out[0]), L.ptr(out[1]), L.ptr(out[2]), L.ptr(out[3]),
+                                      gp[0], gp[1], gp[2], gp[3], B, N, M, int(chunk), index, L.stream_ptr(index))
+        L.check(rc, "ps_chamfer_host")
     if blocking:
         torch.cuda.current_stream(index).synchronize()
     return tuple(out)
 
 
 def chamfer_host_step(xyz1, xyz2, graddist1=None, graddist2=None, grad_out=None, sums_out=None, chunk=0, device=None,
-                      blocking=True):
+                      blocking=True, comm=None):
     """One training-style Chamfer step on HOST clouds: upload in chunks, forward, loss sums, backward — and only
     the six loss sums come back over PCIe.
 
@@ -150,7 +216,8 @@ def chamfer_host_step(xyz1, xyz2, graddist1=None, graddist2=None, grad_out=None,
     `(sums, gradxyz1, gradxyz2)`: `sums` a pinned float64 CPU tensor [sum sqrt d1, sum sqrt d2, sum d1, sum d2, n1, n2]
     (`sums_out` to reuse one), the gradients CUDA tensors on `device` (`grad_out=(g1, g2)` to reuse buffers; None
     without graddist).  With `blocking=False` everything is valid once the current stream of `device` has been
-    synchronised.  Values equal chamfer_forward + chamfer_sums + chamfer_backward on the same clouds."""
+    synchronised.  Values equal chamfer_forward + chamfer_sums + chamfer_backward on the same clouds.  `comm`: a
+    `dist.PeerComm`; `sums` then holds the sums over ALL ranks' shards (exchanged by a kernel inside the same graph)."""
     if xyz1.dim() != 3 or xyz2.dim() != 3 or xyz1.size(2) != 3 or xyz2.size(2) != 3 or xyz1.size(0) != xyz2.size(0):
         raise L.PointSeaError(f"chamfer expects (B,N,3) and (B,M,3), got {tuple(xyz1.shape)} {tuple(xyz2.shape)}")
     B, N, _ = xyz1.shape
@@ -180,10 +247,16 @@ def chamfer_host_step(xyz1, xyz2, graddist1=None, graddist2=None, grad_out=None,
             L.require(t, nm, torch.float32, 3)
             if tuple(t.shape) != shape or t.device != dev:
                 raise L.PointSeaError(f"{nm} must be a {shape} tensor on {dev}")
-    rc = L.load().ps_chamfer_host_step(L.ptr(xyz1), L.ptr(xyz2), L.ptr(graddist1) if with_bwd else None,
-                                       L.ptr(graddist2) if with_bwd else None, L.ptr(g1) if with_bwd else None,
-                                       L.ptr(g2) if with_bwd else None, L.ptr(sums_out), B, N, M, int(chunk), index,
-                                       L.stream_ptr(index))
+    if comm is not None:
+        rc = L.load().ps_chamfer_host_step_dist(L.ptr(xyz1), L.ptr(xyz2), L.ptr(graddist1) if with_bwd else None,
+                                                L.ptr(graddist2) if with_bwd else None, L.ptr(g1) if with_bwd else None,
+                                                L.ptr(g2) if with_bwd else None, L.ptr(sums_out), comm.handle, B, N, M,
+                                                int(chunk), index, L.stream_ptr(index))
+    else:
+        rc = L.load().ps_chamfer_host_step(L.ptr(xyz1), L.ptr(xyz2), L.ptr(graddist1) if with_bwd else None,
+                                           L.ptr(graddist2) if with_bwd else None, L.ptr(g1) if with_bwd else None,
+                                           L.ptr(g2) if with_bwd else None, L.ptr(sums_out), B, N, M, int(chunk), index,
+                                           L.stream_ptr(index))
     L.check(rc, "ps_chamfer_host_step")
     if blocking:
         torch.cuda.current_stream(index).synchronize()

@@ -22,7 +22,7 @@
 //   * when the targets are split across CTAs the partial results are merged with a 64-bit
 //     atomicMin on (dist_bits << 32 | idx): distances are >= 0 so the bit pattern is
 //     monotone, and equal distances resolve to the lower index.
-#include "common.cuh"
+#include "comm.cuh"
 
 #include <cstdlib>
 
@@ -309,20 +309,28 @@ static void plan_units(ChamferParams& p, int B, int Q, int nsm) {
 
 using namespace ps;
 
-extern "C" int ps_chamfer_fwd(const float* xyz1, const float* xyz2, float* dist1, float* dist2,
-                              int* idx1, int* idx2, int B, int N, int M, int dev, void* stream_) {
-  PS_REQUIRE(B >= 0 && N > 0 && M > 0, "ps_chamfer_fwd: bad sizes B=%d N=%d M=%d", B, N, M);
-  if (B == 0) return PS_OK;
-  PS_REQUIRE(xyz1 && xyz2 && dist1 && dist2 && idx1 && idx2, "ps_chamfer_fwd: null pointer");
+namespace ps {
+// Forward (+ optional fused loss sums, + optional publication of those sums to the peers' mailboxes)
+int chamfer_fwd_impl(const float* xyz1, const float* xyz2, float* dist1, float* dist2, int* idx1, int* idx2,
+                     double* sums6, const ps_comm* comm, int B, int N, int M, int dev, void* stream_, const char* who) {
+  PS_REQUIRE(B >= 0 && N > 0 && M > 0, "%s: bad sizes B=%d N=%d M=%d", who, B, N, M);
+  if (B == 0) {
+    if (sums6) {
+      PS_CUDA(cudaMemsetAsync(sums6, 0, 6 * sizeof(double), (cudaStream_t)stream_));
+      if (comm) return comm_publish_launch(comm, sums6, 6, (cudaStream_t)stream_);
+    }
+    return PS_OK;
+  }
+  PS_REQUIRE(xyz1 && xyz2 && dist1 && dist2 && idx1 && idx2, "%s: null pointer", who);
   PS_REQUIRE((long long)B * N < (1ll << 31) / 3 * 3 && (long long)B * M < (1ll << 31) / 3 * 3,
-             "ps_chamfer_fwd: B*N or B*M too large");
+             "%s: B*N or B*M too large", who);
   DeviceGuard guard(dev);
-  if (!guard.ok) return set_error(PS_ERR_CUDA, "ps_chamfer_fwd: cannot select device %d", dev);
+  if (!guard.ok) return set_error(PS_ERR_CUDA, "%s: cannot select device %d", who, dev);
   cudaStream_t stream = (cudaStream_t)stream_;
   const int nsm = sm_count(dev);
 
   {
-    const int rc = chamfer_fwd_symmetric(xyz1, xyz2, dist1, dist2, idx1, idx2, B, N, M, dev, stream);
+    const int rc = chamfer_fwd_symmetric(xyz1, xyz2, dist1, dist2, idx1, idx2, sums6, comm, B, N, M, dev, stream);
     if (rc <= 0) return rc;  // handled (PS_OK) or failed; 1 = shape better served by the two-pass kernel
   }
   const int maxq = N > M ? N : M;
@@ -336,9 +344,11 @@ extern "C" int ps_chamfer_fwd(const float* xyz1, const float* xyz2, float* dist1
   size_t need[2] = {0, 0};
   for (int d = 0; d < 2; d++)
     if (p.d[d].nsplit > 1) need[d] = (size_t)B * p.d[d].nq;
+  ScratchGuard scratch_mem;
   u64* scratch = nullptr;
   if (need[0] + need[1]) {
-    if (int rc = scratch_alloc((void**)&scratch, (need[0] + need[1]) * sizeof(u64), dev, stream)) return rc;
+    if (int rc = scratch_mem.alloc((need[0] + need[1]) * sizeof(u64), dev, stream)) return rc;
+    scratch = static_cast<u64*>(scratch_mem.ptr);
     if (int rc = fill32_async(scratch, 0xffffffffu, (need[0] + need[1]) * sizeof(u64), stream)) return rc;
   }
   p.d[0].keys = need[0] ? scratch : nullptr;
@@ -356,8 +366,24 @@ extern "C" int ps_chamfer_fwd(const float* xyz1, const float* xyz2, float* dist1
     chamfer_unpack_kernel<<<ceil_div(need[d], 256), 256, 0, stream>>>(p.d[d].keys, p.d[d].dist, p.d[d].idx, need[d]);
     PS_LAUNCH_CHECK();
   }
-  if (scratch) PS_CUDA(cudaFreeAsync(scratch, stream));
+  if (int rc = scratch_mem.release()) return rc;
+  if (sums6) {
+    if (int rc = chamfer_sums_launch(dist1, dist2, sums6, (long long)B * N, (long long)B * M, 0, dev, stream)) return rc;
+    if (comm) return comm_publish_launch(comm, sums6, 6, stream);
+  }
   return PS_OK;
+}
+}  // namespace ps
+
+extern "C" int ps_chamfer_fwd(const float* xyz1, const float* xyz2, float* dist1, float* dist2,
+                              int* idx1, int* idx2, int B, int N, int M, int dev, void* stream) {
+  return ps::chamfer_fwd_impl(xyz1, xyz2, dist1, dist2, idx1, idx2, nullptr, nullptr, B, N, M, dev, stream, "ps_chamfer_fwd");
+}
+
+extern "C" int ps_chamfer_fwd_sums(const float* xyz1, const float* xyz2, float* dist1, float* dist2, int* idx1,
+                                   int* idx2, double* sums6, int B, int N, int M, int dev, void* stream) {
+  PS_REQUIRE(sums6 != nullptr, "ps_chamfer_fwd_sums: null sums6");
+  return ps::chamfer_fwd_impl(xyz1, xyz2, dist1, dist2, idx1, idx2, sums6, nullptr, B, N, M, dev, stream, "ps_chamfer_fwd_sums");
 }
 
 extern "C" int ps_chamfer_bwd(const float* xyz1, const float* xyz2, const float* graddist1,

@@ -21,9 +21,10 @@
 //   * partial results of both sides (B splits for rows, A tiles for columns) meet in global
 //     64-bit keys (dist_bits << 32 | idx) merged with atomicMin, then an unpack kernel.
 // Index semantics are the reference's on both sides: lowest index among exact minima.
-#include "common.cuh"
+#include "comm.cuh"
 
 #include <cstdlib>
+#include <cstring>
 
 namespace ps {
 
@@ -69,14 +70,94 @@ __device__ __forceinline__ bool sym_decode_unit(const SymParams& p, int& b, int&
   return t0 < t1;
 }
 
-static __global__ void sym_unpack_kernel(const u64* __restrict__ keys, float* __restrict__ dist,
-                                         int* __restrict__ idx, size_t n) {
-  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i < n) {
-    const u64 k = keys[i];
-    dist[i] = __uint_as_float((unsigned)(k >> 32));
-    idx[i] = (int)(unsigned)k;
+// Epilogue of the forward: ONE launch unpacks both key arrays into (dist, idx), and — when the caller wants
+// them — reduces the distances to the six loss sums of ps_chamfer_sums (utils/loss_utils.py:10-31) without
+// re-reading them from HBM: per-block partials in a fixed order, the last block (ticket) folds them, again
+// in a fixed order, so the sums are bit-reproducible run to run.  With a communicator the same last block
+// PUBLISHES the sums into every peer's mailbox over NVLink (comm.cuh): the step's collective is fused here.
+struct EpiParams {
+  const u64* keys_a; const u64* keys_b;
+  float* da; int* ia; float* db; int* ib;
+  size_t nka, nkb;
+  int a_is_1;        // cloud A is xyz1 (sums are reported in the caller's order)
+  double* partial;   // [gridDim.x][4] scratch, or null: no sums
+  unsigned* ticket;  // all-ones before the launch (the key fill covers it)
+  double* out6;
+  int publish;
+};
+
+__global__ void __launch_bounds__(256) sym_epilogue_kernel(const EpiParams p, const CommDev c) {
+  const size_t stride = (size_t)gridDim.x * blockDim.x;
+  const size_t i0 = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  double sa_sqrt = 0.0, sa = 0.0, sb_sqrt = 0.0, sb = 0.0;
+  for (size_t i = i0; i < p.nka; i += stride) {
+    const u64 k = p.keys_a[i];
+    const float d = __uint_as_float((unsigned)(k >> 32));
+    p.da[i] = d;
+    p.ia[i] = (int)(unsigned)k;
+    sa_sqrt += (double)sqrtf(d);
+    sa += (double)d;
   }
+  for (size_t i = i0; i < p.nkb; i += stride) {
+    const u64 k = p.keys_b[i];
+    const float d = __uint_as_float((unsigned)(k >> 32));
+    p.db[i] = d;
+    p.ib[i] = (int)(unsigned)k;
+    sb_sqrt += (double)sqrtf(d);
+    sb += (double)d;
+  }
+  if (p.partial == nullptr) return;
+  // caller order: [sum sqrt d1, sum sqrt d2, sum d1, sum d2]
+  double s[4];
+  s[0] = p.a_is_1 ? sa_sqrt : sb_sqrt; s[1] = p.a_is_1 ? sb_sqrt : sa_sqrt;
+  s[2] = p.a_is_1 ? sa : sb;           s[3] = p.a_is_1 ? sb : sa;
+  __shared__ double sh[8][4];
+  __shared__ bool last;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+  for (int k = 0; k < 4; k++) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) s[k] += __shfl_xor_sync(0xffffffffu, s[k], o);
+  }
+  if (lane == 0) { sh[warp][0] = s[0]; sh[warp][1] = s[1]; sh[warp][2] = s[2]; sh[warp][3] = s[3]; }
+  __syncthreads();
+  if (threadIdx.x < 4) {
+    double t = 0.0;
+#pragma unroll
+    for (int w = 0; w < 8; w++) t += sh[w][threadIdx.x];
+    p.partial[(size_t)blockIdx.x * 4 + threadIdx.x] = t;
+    __threadfence();
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) last = (atomicAdd(p.ticket, 1u) + 2u == gridDim.x);  // the ticket starts at 0xffffffff
+  __syncthreads();
+  if (!last) return;
+  __threadfence();
+  double t[4] = {0.0, 0.0, 0.0, 0.0};
+  for (unsigned g = threadIdx.x; g < gridDim.x; g += blockDim.x) {
+#pragma unroll
+    for (int k = 0; k < 4; k++) t[k] += __ldcg(p.partial + (size_t)g * 4 + k);
+  }
+#pragma unroll
+  for (int k = 0; k < 4; k++) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) t[k] += __shfl_xor_sync(0xffffffffu, t[k], o);
+  }
+  __syncthreads();
+  if (lane == 0) { sh[warp][0] = t[0]; sh[warp][1] = t[1]; sh[warp][2] = t[2]; sh[warp][3] = t[3]; }
+  __syncthreads();
+  __shared__ double fin[6];
+  if (threadIdx.x < 4) {
+    double v = 0.0;
+#pragma unroll
+    for (int w = 0; w < 8; w++) v += sh[w][threadIdx.x];
+    fin[threadIdx.x] = v;
+  }
+  if (threadIdx.x == 4) fin[4] = (double)(p.a_is_1 ? p.nka : p.nkb);
+  if (threadIdx.x == 5) fin[5] = (double)(p.a_is_1 ? p.nkb : p.nka);
+  __syncthreads();
+  if (threadIdx.x < 6) p.out6[threadIdx.x] = fin[threadIdx.x];
+  if (p.publish && warp == 0) comm_publish(c, fin, 6);
 }
 
 template <int Q>
@@ -476,7 +557,7 @@ static int launch_sym(const SymParams& p, int grid, cudaStream_t stream) {
 
 // Returns PS_OK when it handled the call, 1 when the shape is better served by the two-pass kernel.
 int chamfer_fwd_symmetric(const float* xyz1, const float* xyz2, float* dist1, float* dist2, int* idx1,
-                          int* idx2, int B, int N, int M, int dev, cudaStream_t stream) {
+                          int* idx2, double* sums6, const ps_comm* comm, int B, int N, int M, int dev, cudaStream_t stream) {
   int variant = 1;  // 1: B-packed (chamfer_sym_kernel), 2: A-packed kernel (chamfer_symp_kernel), 0: two-pass
   if (const char* e = getenv("PS_CHAMFER_SYM")) variant = atoi(e);
   if (variant == 0) return 1;
@@ -514,9 +595,14 @@ int chamfer_fwd_symmetric(const float* xyz1, const float* xyz2, float* dist1, fl
   p.nsplit = ceil_div(small, bestL);
 
   const size_t nka = (size_t)B * big, nkb = (size_t)B * small;
-  u64* scratch = nullptr;
-  if (int rc = scratch_alloc((void**)&scratch, (nka + nkb) * sizeof(u64), dev, stream)) return rc;
-  if (int rc = fill32_async(scratch, 0xffffffffu, (nka + nkb) * sizeof(u64), stream)) return rc;
+  // scratch: [keys_a][keys_b][ticket, 16 bytes][epilogue partials]; the fill covers keys + ticket
+  int egrid = ceil_div((long long)(nka + nkb), 256 * 4);
+  if (egrid > nsm * 4) egrid = nsm * 4;
+  const size_t fill_bytes = (nka + nkb) * sizeof(u64) + 16;
+  ScratchGuard scratch_mem;
+  if (int rc = scratch_mem.alloc(fill_bytes + (size_t)egrid * 4 * sizeof(double), dev, stream)) return rc;
+  u64* scratch = static_cast<u64*>(scratch_mem.ptr);
+  if (int rc = fill32_async(scratch, 0xffffffffu, fill_bytes, stream)) return rc;
   p.keys_a = scratch;
   p.keys_b = scratch + nka;
   // tail balancing (see SymParams): cut the units of the last, partially filled wave
@@ -551,16 +637,21 @@ int chamfer_fwd_symmetric(const float* xyz1, const float* xyz2, float* dist1, fl
     else rc = launch_sym<2>(p, grid, stream);
   }
   if (rc) return rc;
-  float* da = a_is_1 ? dist1 : dist2;
-  int* ia = a_is_1 ? idx1 : idx2;
-  float* db = a_is_1 ? dist2 : dist1;
-  int* ib = a_is_1 ? idx2 : idx1;
-  sym_unpack_kernel<<<ceil_div(nka, 256), 256, 0, stream>>>(p.keys_a, da, ia, nka);
+  EpiParams e;
+  e.keys_a = p.keys_a; e.keys_b = p.keys_b;
+  e.da = a_is_1 ? dist1 : dist2; e.ia = a_is_1 ? idx1 : idx2;
+  e.db = a_is_1 ? dist2 : dist1; e.ib = a_is_1 ? idx2 : idx1;
+  e.nka = nka; e.nkb = nkb;
+  e.a_is_1 = a_is_1 ? 1 : 0;
+  e.ticket = reinterpret_cast<unsigned*>(scratch + nka + nkb);
+  e.partial = sums6 ? reinterpret_cast<double*>(scratch + nka + nkb + 2) : nullptr;
+  e.out6 = sums6;
+  e.publish = (sums6 && comm) ? 1 : 0;
+  CommDev cd;
+  if (e.publish) cd = comm->d; else memset(&cd, 0, sizeof(cd));
+  sym_epilogue_kernel<<<egrid, 256, 0, stream>>>(e, cd);
   PS_LAUNCH_CHECK();
-  sym_unpack_kernel<<<ceil_div(nkb, 256), 256, 0, stream>>>(p.keys_b, db, ib, nkb);
-  PS_LAUNCH_CHECK();
-  PS_CUDA(cudaFreeAsync(scratch, stream));
-  return PS_OK;
+  return scratch_mem.release();
 }
 
 }  // namespace ps

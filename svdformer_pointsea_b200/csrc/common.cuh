@@ -11,6 +11,8 @@
 #error "pointsea_b200 kernels are written for sm_100a (B200) only"
 #endif
 
+struct ps_comm;
+
 namespace ps {
 
 typedef unsigned long long u64;
@@ -59,14 +61,56 @@ struct DeviceGuard {
 };
 
 int sm_count(int dev);
-// stream-ordered scratch allocation (pool keeps freed blocks cached); free with cudaFreeAsync
+// stream-ordered scratch allocation from the library's own memory pool (freed blocks stay cached up to a bounded
+// threshold; torch's allocator and the device's default pool are left alone); free with cudaFreeAsync
 int scratch_alloc(void** ptr, size_t bytes, int dev, cudaStream_t stream);
+// A caller-owned arena that replaces the stream-ordered allocations of the launchers running on this host
+// thread while it is installed (the graph-captured step entry points install one: their graphs then hold no
+// memory nodes and stay updatable).  Requests beyond it fall back to the pool and record what was needed.
+struct Workspace {
+  char* base = nullptr;
+  size_t bytes = 0, used = 0, needed = 0;
+};
+Workspace*& tls_workspace();
+// RAII owner of one scratch block: every early return of a launcher gives the block back to the pool
+struct ScratchGuard {
+  void* ptr = nullptr;
+  cudaStream_t stream = nullptr;
+  bool pooled = false;
+  int alloc(size_t bytes, int dev, cudaStream_t s) {
+    stream = s;
+    if (Workspace* w = tls_workspace()) {
+      const size_t need = (bytes + 255) & ~(size_t)255;
+      w->needed += need;
+      if (w->used + need <= w->bytes) {
+        ptr = w->base + w->used;
+        w->used += need;
+        return PS_OK;
+      }
+    }
+    pooled = true;
+    return scratch_alloc(&ptr, bytes, dev, s);
+  }
+  int release() {
+    void* q = ptr;
+    ptr = nullptr;
+    if (q && pooled) PS_CUDA(cudaFreeAsync(q, stream));
+    return PS_OK;
+  }
+  ~ScratchGuard() { if (ptr && pooled) cudaFreeAsync(ptr, stream); }
+  ScratchGuard() = default;
+  ScratchGuard(const ScratchGuard&) = delete;
+  ScratchGuard& operator=(const ScratchGuard&) = delete;
+};
 // fills `bytes` (multiple of 4) with the 32-bit pattern `value` by a kernel launch (see runtime.cu for why not memset)
 int fill32_async(void* ptr, unsigned value, size_t bytes, cudaStream_t stream);
 
 // chamfer_sym.cu: PS_OK when handled, 1 when the two-pass kernel should run instead
+// sums6 != null: the six loss sums of ps_chamfer_sums come out of the same epilogue launch; comm != null (needs sums6):
+// that launch also publishes them to the peers' mailboxes (comm.cuh)
 int chamfer_fwd_symmetric(const float* xyz1, const float* xyz2, float* dist1, float* dist2, int* idx1,
-                          int* idx2, int B, int N, int M, int dev, cudaStream_t stream);
+                          int* idx2, double* sums6, const struct ::ps_comm* comm, int B, int N, int M, int dev,
+                          cudaStream_t stream);
 
 // chamfer.cu: the six loss sums of ps_chamfer_sums; accumulate != 0 adds to out6 instead of overwriting it
 int chamfer_sums_launch(const float* dist1, const float* dist2, double* out6, long long n1, long long n2, int accumulate,

@@ -328,18 +328,19 @@ extern "C" int ps_knn_feat(const float* xr, const float* xq, int* idx, int B, in
   while (TQ > 8 && (long long)B * ceil_div(S, TQ) < 2ll * nsm) TQ /= 2;
 
   const bool self = (xq == xr) && (S == N);
-  float* norms = nullptr;
   const size_t nn = (size_t)B * N + (self ? 0 : (size_t)B * S);
-  if (int rc = scratch_alloc((void**)&norms, nn * sizeof(float), dev, stream)) return rc;
+  ScratchGuard norms_mem;
+  if (int rc = norms_mem.alloc(nn * sizeof(float), dev, stream)) return rc;
+  float* norms = static_cast<float*>(norms_mem.ptr);
   FkArgs a;
   a.xq = xq; a.xr = xr; a.idx = idx; a.C = C; a.N = N; a.S = S; a.k = k; a.order = order; a.npad = npad;
   if (channel_major) { a.sbr = (long long)C * N; a.snr = 1; a.scr = N; a.sbq = (long long)C * S; a.snq = 1; a.scq = S; }
   else { a.sbr = (long long)N * C; a.snr = C; a.scr = 1; a.sbq = (long long)S * C; a.snq = C; a.scq = 1; }
   a.pp = norms;
   a.qq = self ? norms : norms + (size_t)B * N;
-  if (int rc = rowsumsq_launch(xr, norms, B, C, N, a.sbr, a.snr, a.scr, stream, "ps_knn_feat")) { cudaFreeAsync(norms, stream); return rc; }
+  if (int rc = rowsumsq_launch(xr, norms, B, C, N, a.sbr, a.snr, a.scr, stream, "ps_knn_feat")) return rc;
   if (!self)
-    if (int rc = rowsumsq_launch(xq, norms + (size_t)B * N, B, C, S, a.sbq, a.snq, a.scq, stream, "ps_knn_feat")) { cudaFreeAsync(norms, stream); return rc; }
+    if (int rc = rowsumsq_launch(xq, norms + (size_t)B * N, B, C, S, a.sbq, a.snq, a.scq, stream, "ps_knn_feat")) return rc;
   const dim3 grid(ceil_div(S, TQ), B);
 #define PS_FK(TQV)                                                                                  \
   {                                                                                                 \
@@ -351,6 +352,5 @@ extern "C" int ps_knn_feat(const float* xr, const float* xq, int* idx, int B, in
   if (TQ == 32) PS_FK(32) else if (TQ == 16) PS_FK(16) else PS_FK(8)
 #undef PS_FK
   PS_LAUNCH_CHECK();
-  PS_CUDA(cudaFreeAsync(norms, stream));
-  return PS_OK;
+  return norms_mem.release();
 }

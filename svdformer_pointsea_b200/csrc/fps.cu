@@ -587,12 +587,11 @@ extern "C" int ps_fps_sample(const float* xyz, int* idx, float* new_xyz, int B, 
   FpsPlan pl;
   if (!plan_fps(B, N, a.L, a.nper, nsm, dev, pl)) {
     // beyond the register-resident kernels (N > 131072): one CTA per cloud with global scratch
-    float* temp = nullptr;
-    if (int rc = scratch_alloc((void**)&temp, (size_t)B * N * sizeof(float), dev, stream)) return rc;
-    fps_generic_kernel<<<B, FPS_GT, 0, stream>>>(a, temp);
+    ScratchGuard temp_mem;
+    if (int rc = temp_mem.alloc((size_t)B * N * sizeof(float), dev, stream)) return rc;
+    fps_generic_kernel<<<B, FPS_GT, 0, stream>>>(a, static_cast<float*>(temp_mem.ptr));
     PS_LAUNCH_CHECK();
-    PS_CUDA(cudaFreeAsync(temp, stream));
-    return PS_OK;
+    return temp_mem.release();
   }
   // exchange for small clusters: tag polling on plain remote stores (MODE 3) or st.async + mbarrier (MODE 1)
   bool poll = false;

@@ -519,8 +519,9 @@ static int gather_bwd_impl(const float* gout, const int* idx, float* gfeat, int 
     const int nchunks = ceil_div(Mp, CSR_CHUNK);
     const size_t bnd_bytes = ((size_t)B * nchunks * (N + 1) * sizeof(int) + 15) / 16 * 16;
     const size_t list_bytes = (size_t)B * Mp * sizeof(unsigned short);
-    unsigned char* scratch = nullptr;
-    if (int rc = scratch_alloc((void**)&scratch, bnd_bytes + list_bytes, dev, stream)) return rc;
+    ScratchGuard scratch_mem;
+    if (int rc = scratch_mem.alloc(bnd_bytes + list_bytes, dev, stream)) return rc;
+    unsigned char* scratch = static_cast<unsigned char*>(scratch_mem.ptr);
     int* bnd = reinterpret_cast<int*>(scratch);
     unsigned short* list = reinterpret_cast<unsigned short*>(scratch + bnd_bytes);
     const size_t smem_b = (size_t)(2 * N + 1) * sizeof(int) + (size_t)CSR_CHUNK * sizeof(unsigned short);
@@ -540,8 +541,7 @@ static int gather_bwd_impl(const float* gout, const int* idx, float* gfeat, int 
     if (npt <= 1) PS_CSR(1, 12, 8) else if (npt <= 2) PS_CSR(2, 12, 8) else if (npt <= 4) PS_CSR(4, 8, 4) else PS_CSR(8, 4, 2)
 #undef PS_CSR
     PS_LAUNCH_CHECK();
-    PS_CUDA(cudaFreeAsync(scratch, stream));
-    return PS_OK;
+    return scratch_mem.release();
   }
   int ct = 0;
   if (row_bytes * 8 <= GG_SMEM_MAX / 2) ct = 8;

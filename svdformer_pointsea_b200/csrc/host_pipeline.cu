@@ -19,7 +19,8 @@
 // keyed by the buffer addresses and sizes, and replayed with a single cudaGraphLaunch on the
 // caller's stream while the key repeats (steady-state training / evaluation loops with persistent
 // pinned buffers).  PS_HOST_GRAPH=0 disables the graphs.
-#include "common.cuh"
+#include "comm.cuh"
+#include "graph_cache.cuh"
 
 #include <cstdlib>
 #include <cstring>
@@ -31,22 +32,9 @@ constexpr int SLOTS = 3;
 constexpr int MAX_CHUNKS = 64;
 
 
-struct PipeKey {
-  const void* p[13];
-  int B, N, M, nchunks;
-  int sizes[MAX_CHUNKS];
-};
-struct PipeGraph {
-  PipeKey key;
-  cudaGraphExec_t exec = nullptr;
-  unsigned long long stamp = 0;
-};
-constexpr int GRAPH_CACHE = 8;
-
 struct HostPipe {
   std::mutex mu;
-  PipeGraph graphs[GRAPH_CACHE];
-  unsigned long long clock = 0;
+  GraphCache graphs;
   cudaStream_t s_cap = nullptr;   // origin stream of the captures
   cudaEvent_t ev_last = nullptr;  // end of the most recent call on this device (any caller stream)
   bool ready = false;
@@ -54,7 +42,7 @@ struct HostPipe {
   cudaEvent_t ev_in[SLOTS], ev_gin[SLOTS], ev_fwd[SLOTS], ev_run[SLOTS], ev_out[SLOTS], ev_begin = nullptr, ev_end = nullptr;
   void* slot[SLOTS] = {nullptr, nullptr, nullptr};
   size_t slot_bytes = 0;
-  double* d_sums = nullptr;  // 6 doubles: loss partial sums of the current call (ps_chamfer_host_step)
+  double* d_sums = nullptr;  // 12 doubles: loss partial sums of the current call (ps_chamfer_host_step) [+ world-wide sums]
 };
 
 static HostPipe* pipe_for(int dev) {
@@ -79,7 +67,7 @@ static int pipe_init(HostPipe& hp) {
   PS_CUDA(cudaEventCreateWithFlags(&hp.ev_last, cudaEventDisableTiming));
   PS_CUDA(cudaEventCreateWithFlags(&hp.ev_begin, cudaEventDisableTiming));
   PS_CUDA(cudaEventCreateWithFlags(&hp.ev_end, cudaEventDisableTiming));
-  PS_CUDA(cudaMalloc(&hp.d_sums, 6 * sizeof(double)));
+  PS_CUDA(cudaMalloc(&hp.d_sums, 12 * sizeof(double)));
   hp.ready = true;
   return PS_OK;
 }
@@ -143,6 +131,7 @@ struct PipeArgs {
   // loss sums accumulated on the device and downloaded once (48 bytes); dist/idx stay in the staging slots
   float *dev_g1 = nullptr, *dev_g2 = nullptr;
   double* h_sums = nullptr;
+  ps_comm* comm = nullptr;  // with h_sums: the sums are exchanged with the peers and h_sums receives the world-wide ones
   size_t o_x1, o_x2, o_d1, o_d2, o_i1, o_i2, o_gd1, o_gd2, o_g1, o_g2;
 };
 
@@ -201,6 +190,9 @@ static int enqueue_pipeline(HostPipe& hp, const PipeArgs& a, cudaStream_t origin
       float* g2 = a.dev_g2 ? a.dev_g2 + h2 * 3 : d_g2;
       if (int rc = ps_chamfer_bwd(d_x1, d_x2, d_gd1, d_gd2, d_i1, d_i2, g1, g2, nb, a.N, a.M, a.dev, hp.s_bwd)) return rc;
     }
+    // the path's single collective, after the last chunk's kernels: publish + wait over peer memory
+    if (a.h_sums && a.comm && c == a.nchunks - 1)
+      if (int rc = ps_comm_allreduce(a.comm, hp.d_sums, hp.d_sums + 6, 6, hp.s_bwd)) return rc;
     PS_CUDA(cudaEventRecord(hp.ev_run[s], hp.s_bwd));
 
     // download: distances and indices as soon as the forward is done, gradients after the backward
@@ -212,7 +204,7 @@ static int enqueue_pipeline(HostPipe& hp, const PipeArgs& a, cudaStream_t origin
     PS_CUDA(cudaStreamWaitEvent(hp.s_out, hp.ev_run[s], 0));
     if (a.with_bwd && a.gradxyz1) COPY(a.gradxyz1 + h1 * 3, d_g1, c1 * 12, cudaMemcpyDeviceToHost, hp.s_out);
     if (a.with_bwd && a.gradxyz2) COPY(a.gradxyz2 + h2 * 3, d_g2, c2 * 12, cudaMemcpyDeviceToHost, hp.s_out);
-    if (a.h_sums && c == a.nchunks - 1) COPY(a.h_sums, hp.d_sums, 6 * sizeof(double), cudaMemcpyDeviceToHost, hp.s_out);
+    if (a.h_sums && c == a.nchunks - 1) COPY(a.h_sums, hp.d_sums + (a.comm ? 6 : 0), 6 * sizeof(double), cudaMemcpyDeviceToHost, hp.s_out);
     PS_CUDA(cudaEventRecord(hp.ev_out[s], hp.s_out));
   }
   // downloads are in order on s_out: `origin` continues once the last one has landed
@@ -221,13 +213,7 @@ static int enqueue_pipeline(HostPipe& hp, const PipeArgs& a, cudaStream_t origin
   return PS_OK;
 }
 
-static void drop_graphs(HostPipe& hp) {
-  for (auto& g : hp.graphs) {
-    if (g.exec) cudaGraphExecDestroy(g.exec);
-    g.exec = nullptr;
-    g.stamp = 0;
-  }
-}
+static void drop_graphs(HostPipe& hp) { hp.graphs.drop(); }
 
 }  // namespace ps
 
@@ -235,8 +221,8 @@ using namespace ps;
 
 static int host_pipeline_call(const float* xyz1, const float* xyz2, float* dist1, float* dist2, int* idx1,
                               int* idx2, const float* graddist1, const float* graddist2, float* gradxyz1,
-                              float* gradxyz2, float* dev_g1, float* dev_g2, double* h_sums, int B, int N, int M,
-                              int chunk, int dev, void* stream_) {
+                              float* gradxyz2, float* dev_g1, float* dev_g2, double* h_sums, ps_comm* comm, int B, int N,
+                              int M, int chunk, int dev, void* stream_) {
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
   const bool with_bwd = graddist1 != nullptr || graddist2 != nullptr;
   HostPipe* hpp = pipe_for(dev);
@@ -252,7 +238,7 @@ static int host_pipeline_call(const float* xyz1, const float* xyz2, float* dist1
   a.xyz1 = xyz1; a.xyz2 = xyz2; a.graddist1 = graddist1; a.graddist2 = graddist2;
   a.dist1 = dist1; a.dist2 = dist2; a.gradxyz1 = gradxyz1; a.gradxyz2 = gradxyz2;
   a.idx1 = idx1; a.idx2 = idx2;
-  a.dev_g1 = dev_g1; a.dev_g2 = dev_g2; a.h_sums = h_sums;
+  a.dev_g1 = dev_g1; a.dev_g2 = dev_g2; a.h_sums = h_sums; a.comm = comm;
   a.B = B; a.N = N; a.M = M; a.chunk = chunk; a.dev = dev; a.with_bwd = with_bwd;
   // slot layout (all sub-buffers 256-byte aligned so the vectorised kernels see aligned clouds)
   const size_t n1 = (size_t)chunk * N, n2 = (size_t)chunk * M;
@@ -305,43 +291,18 @@ static int host_pipeline_call(const float* xyz1, const float* xyz2, float* dist1
   }
   int rc = PS_OK;
   if (use_graph) {
-    PipeKey key;
-    memset(&key, 0, sizeof(key));
+    GraphKey key;
     const void* ptrs[13] = {xyz1, xyz2, dist1, dist2, idx1, idx2, graddist1, graddist2, gradxyz1, gradxyz2, dev_g1, dev_g2, h_sums};
-    memcpy(key.p, ptrs, sizeof(ptrs));
-    key.B = B; key.N = N; key.M = M; key.nchunks = a.nchunks;
-    memcpy(key.sizes, a.sizes, sizeof(int) * a.nchunks);
-    PipeGraph* hit = nullptr;
-    PipeGraph* victim = &hp.graphs[0];
-    for (auto& g : hp.graphs) {
-      if (g.exec && memcmp(&g.key, &key, sizeof(key)) == 0) hit = &g;
-      if (g.stamp < victim->stamp) victim = &g;
-    }
-    if (!hit) {
-      cudaGraph_t graph = nullptr;
-      if (cudaStreamBeginCapture(hp.s_cap, cudaStreamCaptureModeThreadLocal) == cudaSuccess) {
-        rc = enqueue_pipeline(hp, a, hp.s_cap);
-        const cudaError_t ee = cudaStreamEndCapture(hp.s_cap, &graph);
-        if (rc == PS_OK && ee == cudaSuccess && graph) {
-          if (victim->exec) cudaGraphExecDestroy(victim->exec);
-          victim->exec = nullptr;
-          if (cudaGraphInstantiate(&victim->exec, graph, 0) == cudaSuccess) {
-            victim->key = key;
-            hit = victim;
-          } else {
-            victim->exec = nullptr;
-            victim->stamp = 0;
-          }
-        }
-        if (graph) cudaGraphDestroy(graph);
-        cudaGetLastError();  // a failed capture falls back to the eager pipeline below
-        rc = PS_OK;
-      }
-    }
+    for (const void* q : ptrs) key.ptr(q);
+    key.begin_shape();
+    key.ptr(comm);
+    key.val(B); key.val(N); key.val(M); key.val(a.nchunks);
+    for (int i = 0; i < a.nchunks; i++) key.val(a.sizes[i]);
+    GraphCache::Entry* hit = hp.graphs.get(key, hp.s_cap, [&](cudaStream_t s) { return enqueue_pipeline(hp, a, s); }, &rc);
+    if (rc != PS_OK) return rc;
     if (hit) {
-      hit->stamp = ++hp.clock;
       PS_CUDA(cudaGraphLaunch(hit->exec, stream));
-      launch_counter() += 1;
+      launch_counter() += hit->kernels;
       PS_CUDA(cudaEventRecord(hp.ev_last, stream));
       return PS_OK;
     }
@@ -362,12 +323,28 @@ extern "C" int ps_chamfer_host(const float* xyz1, const float* xyz2, float* dist
   if (graddist1 != nullptr || graddist2 != nullptr)
     PS_REQUIRE(graddist1 && graddist2 && gradxyz1 && gradxyz2, "ps_chamfer_host: backward needs graddist1, graddist2, gradxyz1, gradxyz2");
   return host_pipeline_call(xyz1, xyz2, dist1, dist2, idx1, idx2, graddist1, graddist2, gradxyz1, gradxyz2, nullptr, nullptr,
-                            nullptr, B, N, M, chunk, dev, stream);
+                            nullptr, nullptr, B, N, M, chunk, dev, stream);
 }
 
-extern "C" int ps_chamfer_host_step(const float* xyz1, const float* xyz2, const float* graddist1, const float* graddist2,
-                                    float* dev_gradxyz1, float* dev_gradxyz2, double* sums6, int B, int N, int M,
-                                    int chunk, int dev, void* stream) {
+// General form: every output of the step downloaded (dist, idx, gradients) AND the loss sums, which are world-wide
+// when a communicator is given.  sums6 / comm may be NULL.
+extern "C" int ps_chamfer_host_full(const float* xyz1, const float* xyz2, float* dist1, float* dist2, int* idx1, int* idx2,
+                                    const float* graddist1, const float* graddist2, float* gradxyz1, float* gradxyz2,
+                                    double* sums6, ps_comm* comm, int B, int N, int M, int chunk, int dev, void* stream) {
+  PS_REQUIRE(B >= 0 && N >= 0 && M >= 0, "ps_chamfer_host_full: negative size");
+  if (B == 0 || (N == 0 && M == 0)) return PS_OK;
+  PS_REQUIRE(N > 0 && M > 0, "ps_chamfer_host_full: both clouds need at least one point (N=%d, M=%d)", N, M);
+  PS_REQUIRE(xyz1 && xyz2 && dist1 && dist2 && idx1 && idx2, "ps_chamfer_host_full: null pointer");
+  if (graddist1 != nullptr || graddist2 != nullptr)
+    PS_REQUIRE(graddist1 && graddist2 && gradxyz1 && gradxyz2, "ps_chamfer_host_full: backward needs graddist1, graddist2, gradxyz1, gradxyz2");
+  if (comm) PS_REQUIRE(sums6 && comm->connected && comm->dev == dev, "ps_chamfer_host_full: communicator needs sums6, a connection and device %d", dev);
+  return host_pipeline_call(xyz1, xyz2, dist1, dist2, idx1, idx2, graddist1, graddist2, gradxyz1, gradxyz2, nullptr, nullptr,
+                            sums6, comm, B, N, M, chunk, dev, stream);
+}
+
+static int host_step_call(const float* xyz1, const float* xyz2, const float* graddist1, const float* graddist2,
+                          float* dev_gradxyz1, float* dev_gradxyz2, double* sums6, ps_comm* comm, int B, int N, int M,
+                          int chunk, int dev, void* stream) {
   PS_REQUIRE(B >= 0 && N >= 0 && M >= 0, "ps_chamfer_host_step: negative size");
   if (B == 0 || (N == 0 && M == 0)) return PS_OK;
   PS_REQUIRE(N > 0 && M > 0, "ps_chamfer_host_step: both clouds need at least one point (N=%d, M=%d)", N, M);
@@ -376,6 +353,31 @@ extern "C" int ps_chamfer_host_step(const float* xyz1, const float* xyz2, const 
   if (with_bwd)
     PS_REQUIRE(graddist1 && graddist2 && dev_gradxyz1 && dev_gradxyz2,
                "ps_chamfer_host_step: backward needs graddist1, graddist2 (host) and dev_gradxyz1, dev_gradxyz2 (device)");
+  if (comm) PS_REQUIRE(comm->connected && comm->dev == dev, "ps_chamfer_host_step_dist: communicator not connected or on another device");
   return host_pipeline_call(xyz1, xyz2, nullptr, nullptr, nullptr, nullptr, graddist1, graddist2, nullptr, nullptr,
-                            with_bwd ? dev_gradxyz1 : nullptr, with_bwd ? dev_gradxyz2 : nullptr, sums6, B, N, M, chunk, dev, stream);
+                            with_bwd ? dev_gradxyz1 : nullptr, with_bwd ? dev_gradxyz2 : nullptr, sums6, comm, B, N, M, chunk, dev, stream);
+}
+
+extern "C" int ps_chamfer_host_step(const float* xyz1, const float* xyz2, const float* graddist1, const float* graddist2,
+                                    float* dev_gradxyz1, float* dev_gradxyz2, double* sums6, int B, int N, int M,
+                                    int chunk, int dev, void* stream) {
+  return host_step_call(xyz1, xyz2, graddist1, graddist2, dev_gradxyz1, dev_gradxyz2, sums6, nullptr, B, N, M, chunk, dev, stream);
+}
+
+extern "C" int ps_chamfer_host_step_dist(const float* xyz1, const float* xyz2, const float* graddist1, const float* graddist2,
+                                         float* dev_gradxyz1, float* dev_gradxyz2, double* sums6, ps_comm* comm, int B, int N,
+                                         int M, int chunk, int dev, void* stream) {
+  PS_REQUIRE(comm != nullptr, "ps_chamfer_host_step_dist: null communicator");
+  return host_step_call(xyz1, xyz2, graddist1, graddist2, dev_gradxyz1, dev_gradxyz2, sums6, comm, B, N, M, chunk, dev, stream);
+}
+
+// Graph-cache statistics of the host-buffer entry points on `dev` (see ps_chamfer_step_stats).
+extern "C" int ps_chamfer_host_stats(int dev, long long* hits, long long* updates, long long* instantiations) {
+  HostPipe* hp = pipe_for(dev);
+  PS_REQUIRE(hp != nullptr, "ps_chamfer_host_stats: bad device %d", dev);
+  std::lock_guard<std::mutex> lock(hp->mu);
+  if (hits) *hits = hp->graphs.hits;
+  if (updates) *updates = hp->graphs.updates;
+  if (instantiations) *instantiations = hp->graphs.instantiations;
+  return PS_OK;
 }

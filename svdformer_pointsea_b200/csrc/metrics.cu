@@ -120,6 +120,7 @@ extern "C" int ps_chamfer_metrics(const float* dist1, const float* dist2, const 
   cudaStream_t stream = (cudaStream_t)stream_;
   const bool dcd = idx1 != nullptr;
   const int use_smem = (long long)n1 + n2 <= MT_SMEM_POINTS;
+  ScratchGuard gcount_mem;
   int* gcount = nullptr;
   size_t smem = 0;
   if (dcd) {
@@ -127,7 +128,8 @@ extern "C" int ps_chamfer_metrics(const float* dist1, const float* dist2, const 
       smem = (size_t)(n1 + n2) * sizeof(int);
     } else {
       const size_t bytes = (size_t)B * ((size_t)n1 + n2) * sizeof(int);
-      if (int rc = scratch_alloc((void**)&gcount, bytes, dev, stream)) return rc;
+      if (int rc = gcount_mem.alloc(bytes, dev, stream)) return rc;
+      gcount = static_cast<int*>(gcount_mem.ptr);
       if (int rc = fill32_async(gcount, 0u, bytes, stream)) return rc;
     }
   }
@@ -135,6 +137,5 @@ extern "C" int ps_chamfer_metrics(const float* dist1, const float* dist2, const 
   chamfer_metrics_kernel<<<B, MT_THREADS, smem, stream>>>(dist1, dist2, idx1, idx2, out8, gcount, n1, n2, fscore_threshold,
                                                           dcd_alpha, dcd_n_lambda, dcd_frac1, dcd_frac2, use_smem);
   PS_LAUNCH_CHECK();
-  if (gcount) PS_CUDA(cudaFreeAsync(gcount, stream));
-  return PS_OK;
+  return gcount_mem.release();
 }

@@ -1,7 +1,10 @@
 // Library plumbing: error strings, device queries, launch counter, fp32 peak probe.
 #include "common.cuh"
 
+#include <atomic>
+#include <cstdlib>
 #include <cstring>
+#include <mutex>
 
 namespace ps {
 
@@ -13,6 +16,10 @@ long long& launch_counter() {
   static thread_local long long n = 0;
   return n;
 }
+Workspace*& tls_workspace() {
+  static thread_local Workspace* w = nullptr;
+  return w;
+}
 int set_error(int code, const char* fmt, ...) {
   va_list ap;
   va_start(ap, fmt);
@@ -22,29 +29,55 @@ int set_error(int code, const char* fmt, ...) {
 }
 
 int sm_count(int dev) {
-  // per-device cache; benign race (every writer stores the same value)
-  static int cache[64] = {0};
-  if (dev >= 0 && dev < 64 && cache[dev]) return cache[dev];
+  // per-device cache; relaxed atomics: every writer stores the same value
+  static std::atomic<int> cache[64];
+  if (dev >= 0 && dev < 64) {
+    const int v = cache[dev].load(std::memory_order_relaxed);
+    if (v) return v;
+  }
   int n = 0;
   if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0) n = 148;
-  if (dev >= 0 && dev < 64) cache[dev] = n;
+  if (dev >= 0 && dev < 64) cache[dev].store(n, std::memory_order_relaxed);
   return n;
 }
 
-// Stream-ordered scratch.  The default mempool gives memory back to the driver at every
-// synchronisation unless a release threshold is set, which turns each cudaMallocAsync after a
-// sync into a real (100+ us) allocation; keep freed scratch cached in the pool instead.
-int scratch_alloc(void** ptr, size_t bytes, int dev, cudaStream_t stream) {
-  static bool configured[64] = {false};
-  if (dev >= 0 && dev < 64 && !configured[dev]) {
-    cudaMemPool_t pool;
-    if (cudaDeviceGetDefaultMemPool(&pool, dev) == cudaSuccess) {
-      unsigned long long thr = ~0ull;
-      cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &thr);
+// Stream-ordered scratch from a PRIVATE pool per device.  A pool gives memory back to the driver at every
+// synchronisation unless a release threshold is set, which turns each cudaMallocAsync after a sync into a
+// real (100+ us) allocation; the library's pool keeps up to PS_SCRATCH_KEEP_MB (default 1024) cached and
+// leaves the device's default pool (shared with everything else in the process) untouched.
+static std::mutex g_pool_mu;
+static cudaMemPool_t g_pools[64];
+static bool g_pool_ready[64];
+
+static cudaMemPool_t scratch_pool(int dev) {
+  if (dev < 0 || dev >= 64) return nullptr;
+  std::lock_guard<std::mutex> lock(g_pool_mu);
+  if (!g_pool_ready[dev]) {
+    cudaMemPoolProps props;
+    memset(&props, 0, sizeof(props));
+    props.allocType = cudaMemAllocationTypePinned;
+    props.handleTypes = cudaMemHandleTypeNone;
+    props.location.type = cudaMemLocationTypeDevice;
+    props.location.id = dev;
+    cudaMemPool_t pool = nullptr;
+    if (cudaMemPoolCreate(&pool, &props) == cudaSuccess) {
+      unsigned long long keep = 1024ull << 20;
+      if (const char* e = getenv("PS_SCRATCH_KEEP_MB")) keep = (unsigned long long)atoll(e) << 20;
+      cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
+      g_pools[dev] = pool;
+    } else {
+      cudaGetLastError();
+      g_pools[dev] = nullptr;  // fall back to the default pool, untouched
     }
-    configured[dev] = true;
+    g_pool_ready[dev] = true;
   }
-  PS_CUDA(cudaMallocAsync(ptr, bytes, stream));
+  return g_pools[dev];
+}
+
+int scratch_alloc(void** ptr, size_t bytes, int dev, cudaStream_t stream) {
+  cudaMemPool_t pool = scratch_pool(dev);
+  if (pool) PS_CUDA(cudaMallocFromPoolAsync(ptr, bytes, pool, stream));
+  else PS_CUDA(cudaMallocAsync(ptr, bytes, stream));
   return PS_OK;
 }
 

@@ -5,9 +5,21 @@ clouds [B*r//G, B*(r+1)//G).  The only collective is ONE all-reduce(sum) of a sm
 partial sums and element counts (utils/loss_utils.py:10-19,50-57 define what is summed); the
 division happens after the reduce so uneven shards stay exact.  Backend: NCCL over
 NVLink/NVSwitch on GPUs, gloo in the CPU tests.
+
+Gradients.  The global mean is a function of every rank's shard, and each rank back-propagates only through its
+own shard, so a rank's parameter gradient is its SHARE of the full-batch gradient: the shares must be SUMMED
+across ranks (`grad_reduce="sum"`, the default; e.g. a manual all-reduce(sum) of the gradients).  Stock
+`DistributedDataParallel` AVERAGES gradients instead, which would give 1/world of the reference's
+(`nn.DataParallel`, full batch on one process) gradient; pass `grad_reduce="mean"` to the sharded losses under
+DDP: the backward of the reduction is then scaled by the world size, so the DDP average equals the full-batch
+gradient.  INTEGRATION.md section "Multi-GPU" says the same.
 """
+import ctypes
+
 import torch
 import torch.distributed as dist
+
+from . import _lib as L
 
 
 def bind_to_gpu_numa_node(device_index):
@@ -55,21 +67,108 @@ def shard_batch(t, rank=None, world=None):
     return t[lo:hi].contiguous()
 
 
+class PeerComm:
+    """The path's single collective over PEER MEMORY (csrc/comm.cuh): every rank owns a mailbox in its HBM that the
+    peers store into over NVLink; the kernel that produces the loss sums publishes them, a one-warp kernel adds the
+    world's contributions in rank order (identical bits on every rank).  No host call per step, graph-replayable.
+
+    `PeerComm(group)`: one rank per process; the CUDA IPC handles of the mailboxes are exchanged once through
+    `torch.distributed.all_gather_object` on `group` (any backend).  `PeerComm.local(devices)`: all ranks in this
+    process (threads / tests), one per entry of `devices`."""
+
+    def __init__(self, group=None, device=None, _handle=None, _rank=0, _world=1):
+        lib = L.load()
+        if _handle is not None:
+            self.handle, self.rank, self.world, self.device = _handle, _rank, _world, device
+            return
+        if not torch.cuda.is_available():
+            raise L.PointSeaError("PeerComm needs a CUDA device (the exchange is a CUDA kernel over peer memory)")
+        self.rank = dist.get_rank(group) if dist.is_initialized() else 0
+        self.world = dist.get_world_size(group) if dist.is_initialized() else 1
+        index = torch.cuda.current_device() if device is None else torch.device(device).index
+        L._check_device(index)
+        self.device = torch.device("cuda", index)
+        h = ctypes.c_void_p()
+        L.check(lib.ps_comm_create(self.rank, self.world, index, ctypes.byref(h)), "ps_comm_create")
+        self.handle = h
+        if self.world > 1:
+            nb = lib.ps_comm_handle_bytes()
+            mine = ctypes.create_string_buffer(nb)
+            L.check(lib.ps_comm_export(self.handle, mine), "ps_comm_export")
+            gathered = [None] * self.world
+            dist.all_gather_object(gathered, bytes(mine.raw), group=group)
+            blob = ctypes.create_string_buffer(b"".join(gathered), nb * self.world)
+            L.check(lib.ps_comm_connect(self.handle, blob), "ps_comm_connect")
+            dist.barrier(group=group)  # nobody publishes before every mailbox is mapped everywhere
+
+    @classmethod
+    def local(cls, devices):
+        lib = L.load()
+        world = len(devices)
+        handles = (ctypes.c_void_p * world)()
+        comms = []
+        for r, d in enumerate(devices):
+            index = torch.device(d).index
+            L._check_device(index)
+            h = ctypes.c_void_p()
+            L.check(lib.ps_comm_create(r, world, index, ctypes.byref(h)), "ps_comm_create")
+            handles[r] = h
+            comms.append(cls(device=torch.device("cuda", index), _handle=h, _rank=r, _world=world))
+        L.check(lib.ps_comm_connect_local(handles, world), "ps_comm_connect_local")
+        return comms
+
+    def all_reduce(self, vec, out=None):
+        """Sum of `vec` (float64 CUDA tensor, <= 30 elements) over all ranks, on the current stream."""
+        L.require(vec, "vec", torch.float64, 1)
+        if out is None:
+            out = torch.empty_like(vec)
+        index = L.same_device(vec, out)
+        L.check(L.load().ps_comm_allreduce(self.handle, L.ptr(vec), L.ptr(out), vec.numel(), L.stream_ptr(index)), "ps_comm_allreduce")
+        return out
+
+    def status(self):
+        p, c, t = ctypes.c_longlong(), ctypes.c_longlong(), ctypes.c_int()
+        L.check(L.load().ps_comm_status(self.handle, ctypes.byref(p), ctypes.byref(c), ctypes.byref(t)), "ps_comm_status")
+        return {"published": p.value, "consumed": c.value, "timed_out": bool(t.value)}
+
+    def close(self):
+        if self.handle is not None:
+            L.load().ps_comm_destroy(self.handle)
+            self.handle = None
+
+
+def _world(group, comm):
+    if comm is not None:
+        return comm.world
+    return dist.get_world_size(group) if dist.is_initialized() else 1
+
+
 class _AllReduceSum(torch.autograd.Function):
-    """all-reduce(sum) that autograd can cross.  Backward is the identity: every rank holds the
-    same replicated loss, and we want the gradient of ONE copy of it, so each rank keeps the
-    gradient w.r.t. its own partial sums; parameter gradients are then SUMMED (not averaged)
-    across ranks."""
+    """all-reduce(sum) that autograd can cross.  Every rank holds the same replicated loss and back-propagates
+    through its own shard only, so the backward is the identity times `scale`: 1 when the caller SUMS parameter
+    gradients across ranks, world_size when they are AVERAGED (stock DistributedDataParallel) — see the module
+    docstring."""
 
     @staticmethod
-    def forward(ctx, vec, group):
+    def forward(ctx, vec, group, comm, scale):
+        ctx.scale = scale
+        if comm is not None:
+            return comm.all_reduce(vec.detach().to(torch.float64).contiguous()).to(vec.dtype)
         out = vec.clone()
         dist.all_reduce(out, op=dist.ReduceOp.SUM, group=group)
         return out
 
     @staticmethod
     def backward(ctx, grad):
-        return grad, None
+        return (grad if ctx.scale == 1 else grad * ctx.scale), None, None, None
+
+
+def _grad_scale(grad_reduce, world):
+    if grad_reduce == "sum":
+        return 1
+    if grad_reduce == "mean":
+        return world
+    raise ValueError(f"grad_reduce must be 'sum' or 'mean', got {grad_reduce!r}")
 
 
 class LossSums:
@@ -77,6 +176,7 @@ class LossSums:
 
     add("cd2.d1", values) records sum(values) and values.numel(); reduce() all-reduces the whole
     vector once (enqueued on the current stream, no host sync) and returns {name: global mean}.
+    `comm`: a PeerComm — the exchange then runs over peer memory instead of torch.distributed.
     """
 
     def __init__(self, device, dtype=torch.float32):
@@ -88,22 +188,26 @@ class LossSums:
         self.parts.append(values.sum(dtype=self.dtype).reshape(1))
         self.parts.append(torch.full((1,), float(values.numel()), device=self.device, dtype=self.dtype))
 
-    def reduce(self, group=None):
+    def reduce(self, group=None, comm=None, grad_reduce="sum"):
         vec = torch.cat(self.parts) if self.parts else torch.zeros(0, device=self.device, dtype=self.dtype)
-        if dist.is_initialized() and dist.get_world_size(group) > 1 and vec.numel():
-            vec = _AllReduceSum.apply(vec, group)
+        world = _world(group, comm)
+        scale = _grad_scale(grad_reduce, world)
+        if world > 1 and vec.numel():
+            vec = _AllReduceSum.apply(vec, group, comm, scale)
         out = {}
         for i, name in enumerate(self.names):
             out[name] = vec[2 * i] / vec[2 * i + 1]
         return out
 
 
-def chamfer_metric_means(d1, d2, group=None):
+def chamfer_metric_means(d1, d2, group=None, comm=None):
     """Global means {sqrt_d1, sqrt_d2, d1, d2} of Chamfer outputs over all ranks' shards: one fused
     reduction kernel (ps_chamfer_sums) + ONE all-reduce of 6 doubles.  Metric path (no autograd)."""
     from .chamfer import chamfer_sums
     vec = chamfer_sums(d1, d2)  # [sum sqrt d1, sum sqrt d2, sum d1, sum d2, n1, n2]
-    if dist.is_initialized() and dist.get_world_size(group) > 1:
+    if comm is not None and comm.world > 1:
+        vec = comm.all_reduce(vec)
+    elif dist.is_initialized() and dist.get_world_size(group) > 1:
         dist.all_reduce(vec, op=dist.ReduceOp.SUM, group=group)
     return {"sqrt_d1": vec[0] / vec[4], "sqrt_d2": vec[1] / vec[5], "d1": vec[2] / vec[4], "d2": vec[3] / vec[5]}
 
@@ -159,10 +263,7 @@ def combine_chamfer(means, name, sqrt=True):
     return (m1 + m2) / 2 if sqrt else m1 + m2
 
 
-def get_loss_sharded(pcds_pred, gt, sqrt=True, alpha1=1, alpha2=1, group=None):
-    """utils/loss_utils.get_loss (:33-58) on a batch shard: identical value on every rank, equal
-    to the single-process loss over the concatenated batch.  Gradients flow through the local
-    Chamfer terms (scale by world size is already contained in the global mean)."""
+def _sharded_terms(pcds_pred, gt, sqrt, partial=None):
     from .chamfer import chamfer_3DFunction
     from .pointnet2_utils import fps_subsample
 
@@ -173,6 +274,25 @@ def get_loss_sharded(pcds_pred, gt, sqrt=True, alpha1=1, alpha2=1, group=None):
     for name, (p, q) in {"cdc": (Pc, gt_c), "cd1": (P1, gt_1), "cd2": (P2, gt)}.items():
         d1, d2, _, _ = chamfer_3DFunction.apply(p.contiguous(), q.contiguous())
         chamfer_loss_terms(sums, name, d1, d2, sqrt)
-    means = sums.reduce(group)
+    if partial is not None:  # chamfer_single_side(_sqrt)(partial, P2): the dist1 side only (utils/loss_utils.py:22-31)
+        d1, _, _, _ = chamfer_3DFunction.apply(partial.contiguous(), P2.contiguous())
+        sums.add("pm.d1", torch.sqrt(d1) if sqrt else d1)
+    return sums
+
+
+def get_loss_sharded(pcds_pred, gt, sqrt=True, alpha1=1, alpha2=1, group=None, comm=None, grad_reduce="sum"):
+    """utils/loss_utils.get_loss (:33-58) on a batch shard: identical value on every rank, equal
+    to the single-process loss over the concatenated batch.  `grad_reduce`: how the caller combines parameter
+    gradients across ranks — "sum" (default) or "mean" (stock DistributedDataParallel); see the module docstring.
+    `comm`: a PeerComm to run the one collective over peer memory instead of torch.distributed."""
+    means = _sharded_terms(pcds_pred, gt, sqrt).reduce(group, comm, grad_reduce)
     cdc, cd1, cd2 = (combine_chamfer(means, n, sqrt) for n in ("cdc", "cd1", "cd2"))
     return cdc + alpha1 * cd1 + alpha2 * cd2, [cdc, cd1, cd2]
+
+
+def get_loss_PM_sharded(pcds_pred, partial, gt, sqrt=True, group=None, comm=None, grad_reduce="sum"):
+    """utils/loss_utils.get_loss_PM (:60-85; core/train_55.py:154, core/train_geospec.py:108) on a batch shard: the
+    three Chamfer terms plus the single-sided partial-matching term, still ONE all-reduce (14 numbers)."""
+    means = _sharded_terms(pcds_pred, gt, sqrt, partial=partial).reduce(group, comm, grad_reduce)
+    cdc, cd1, cd2 = (combine_chamfer(means, n, sqrt) for n in ("cdc", "cd1", "cd2"))
+    return cdc + cd1 + cd2 + means["pm.d1"], [cdc, cd1, cd2]
