@@ -249,6 +249,7 @@ def run_ours(args):
     launches_per_step = [0]
     if reduce_mode in ("none (1 GPU)", "peer"):
         stepper = ps.ChamferStep(B, N, M, dev, comm=comm)
+        stepper.prepare(x1, x2, gd1, gd2)  # capture + instantiate outside any loop
 
         def step():
             stepper(x1, x2, gd1, gd2)  # ONE cudaGraphLaunch

@@ -110,6 +110,11 @@ int ps_chamfer_step(const float* xyz1, const float* xyz2, const float* graddist1
                     float* dist1, float* dist2, int* idx1, int* idx2, float* gradxyz1, float* gradxyz2,
                     double* sums_local6, double* sums_global6, ps_comm* comm, int B, int N, int M, int dev,
                     void* stream);
+/* Same arguments, nothing launched: captures and instantiates the graph of this exact call ahead of time, so the
+ * first real step costs a replay (ranks that share a device, or a timed loop, call this first). */
+int ps_chamfer_step_prepare(const float* xyz1, const float* xyz2, const float* graddist1, const float* graddist2,
+                            float* dist1, float* dist2, int* idx1, int* idx2, float* gradxyz1, float* gradxyz2,
+                            double* sums_local6, double* sums_global6, ps_comm* comm, int B, int N, int M, int dev);
 /* Graph-cache counters of ps_chamfer_step / of the host-buffer entry points on `dev`: exact replays, in-place
  * retargets (cudaGraphExecUpdate) and instantiations so far. */
 int ps_chamfer_step_stats(int dev, long long* hits, long long* updates, long long* instantiations);

@@ -76,7 +76,7 @@ class ChamferStep:
         self.sums_local = torch.zeros(6, device=dev, dtype=torch.float64)
         self.sums_global = torch.zeros(6, device=dev, dtype=torch.float64) if comm is not None else self.sums_local
 
-    def __call__(self, xyz1, xyz2, graddist1=None, graddist2=None):
+    def _args(self, xyz1, xyz2, graddist1, graddist2):
         B, N, M = self.B, self.N, self.M
         L.require(xyz1, "xyz1", torch.float32, 3)
         L.require(xyz2, "xyz2", torch.float32, 3)
@@ -91,13 +91,21 @@ class ChamferStep:
             dev = L.same_device(xyz1, xyz2, graddist1, graddist2, self.dist1)
         else:
             dev = L.same_device(xyz1, xyz2, self.dist1)
-        rc = L.load().ps_chamfer_step(
-            L.ptr(xyz1), L.ptr(xyz2), L.ptr(graddist1) if with_bwd else None, L.ptr(graddist2) if with_bwd else None,
-            L.ptr(self.dist1), L.ptr(self.dist2), L.ptr(self.idx1), L.ptr(self.idx2),
-            L.ptr(self.gradxyz1) if with_bwd else None, L.ptr(self.gradxyz2) if with_bwd else None,
-            L.ptr(self.sums_local), L.ptr(self.sums_global) if self.comm is not None else None,
-            self.comm.handle if self.comm is not None else None, B, N, M, dev, L.stream_ptr(dev))
-        L.check(rc, "ps_chamfer_step")
+        args = (L.ptr(xyz1), L.ptr(xyz2), L.ptr(graddist1) if with_bwd else None, L.ptr(graddist2) if with_bwd else None,
+                L.ptr(self.dist1), L.ptr(self.dist2), L.ptr(self.idx1), L.ptr(self.idx2),
+                L.ptr(self.gradxyz1) if with_bwd else None, L.ptr(self.gradxyz2) if with_bwd else None,
+                L.ptr(self.sums_local), L.ptr(self.sums_global) if self.comm is not None else None,
+                self.comm.handle if self.comm is not None else None, B, N, M, dev)
+        return args, dev, with_bwd
+
+    def prepare(self, xyz1, xyz2, graddist1=None, graddist2=None):
+        """Capture + instantiate the graph for these exact buffers without launching anything (ps_chamfer_step_prepare)."""
+        args, _, _ = self._args(xyz1, xyz2, graddist1, graddist2)
+        L.check(L.load().ps_chamfer_step_prepare(*args), "ps_chamfer_step_prepare")
+
+    def __call__(self, xyz1, xyz2, graddist1=None, graddist2=None):
+        args, dev, with_bwd = self._args(xyz1, xyz2, graddist1, graddist2)
+        L.check(L.load().ps_chamfer_step(*args, L.stream_ptr(dev)), "ps_chamfer_step")
         return self.sums_local, self.sums_global, (self.gradxyz1 if with_bwd else None), (self.gradxyz2 if with_bwd else None)
 
 

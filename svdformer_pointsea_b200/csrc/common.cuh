@@ -64,6 +64,9 @@ int sm_count(int dev);
 // stream-ordered scratch allocation from the library's own memory pool (freed blocks stay cached up to a bounded
 // threshold; torch's allocator and the device's default pool are left alone); free with cudaFreeAsync
 int scratch_alloc(void** ptr, size_t bytes, int dev, cudaStream_t stream);
+// creates the device's scratch pool now (entry points that capture call this BEFORE cudaStreamBeginCapture:
+// creating a pool is not allowed while the thread is capturing)
+void scratch_pool_init(int dev);
 // A caller-owned arena that replaces the stream-ordered allocations of the launchers running on this host
 // thread while it is installed (the graph-captured step entry points install one: their graphs then hold no
 // memory nodes and stay updatable).  Requests beyond it fall back to the pool and record what was needed.

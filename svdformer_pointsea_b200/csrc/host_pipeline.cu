@@ -50,7 +50,7 @@ static HostPipe* pipe_for(int dev) {
   return (dev >= 0 && dev < 64) ? &pipes[dev] : nullptr;
 }
 
-static int pipe_init(HostPipe& hp) {
+static int pipe_init(HostPipe& hp, int hp_dev) {
   if (hp.ready) return PS_OK;
   PS_CUDA(cudaStreamCreateWithFlags(&hp.s_in, cudaStreamNonBlocking));
   PS_CUDA(cudaStreamCreateWithFlags(&hp.s_run, cudaStreamNonBlocking));
@@ -68,6 +68,7 @@ static int pipe_init(HostPipe& hp) {
   PS_CUDA(cudaEventCreateWithFlags(&hp.ev_begin, cudaEventDisableTiming));
   PS_CUDA(cudaEventCreateWithFlags(&hp.ev_end, cudaEventDisableTiming));
   PS_CUDA(cudaMalloc(&hp.d_sums, 12 * sizeof(double)));
+  scratch_pool_init(hp_dev);
   hp.ready = true;
   return PS_OK;
 }
@@ -231,7 +232,7 @@ static int host_pipeline_call(const float* xyz1, const float* xyz2, float* dist1
   if (!guard.ok) return set_error(PS_ERR_CUDA, "ps_chamfer_host: cannot select device %d", dev);
   HostPipe& hp = *hpp;
   std::lock_guard<std::mutex> lock(hp.mu);
-  if (int rc = pipe_init(hp)) return rc;
+  if (int rc = pipe_init(hp, dev)) return rc;
 
   PipeArgs a;
   make_plan(B, chunk, a.sizes, &a.nchunks, &chunk);

@@ -74,6 +74,8 @@ static cudaMemPool_t scratch_pool(int dev) {
   return g_pools[dev];
 }
 
+void scratch_pool_init(int dev) { (void)scratch_pool(dev); }
+
 int scratch_alloc(void** ptr, size_t bytes, int dev, cudaStream_t stream) {
   cudaMemPool_t pool = scratch_pool(dev);
   if (pool) PS_CUDA(cudaMallocFromPoolAsync(ptr, bytes, pool, stream));

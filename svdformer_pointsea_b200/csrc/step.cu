@@ -51,10 +51,10 @@ static int enqueue_step(const StepArgs& a, cudaStream_t s) {
 
 using namespace ps;
 
-extern "C" int ps_chamfer_step(const float* xyz1, const float* xyz2, const float* graddist1, const float* graddist2,
-                               float* dist1, float* dist2, int* idx1, int* idx2, float* gradxyz1, float* gradxyz2,
-                               double* sums_local6, double* sums_global6, ps_comm* comm, int B, int N, int M, int dev,
-                               void* stream_) {
+static int chamfer_step_impl(const float* xyz1, const float* xyz2, const float* graddist1, const float* graddist2,
+                             float* dist1, float* dist2, int* idx1, int* idx2, float* gradxyz1, float* gradxyz2,
+                             double* sums_local6, double* sums_global6, ps_comm* comm, int B, int N, int M, int dev,
+                             void* stream_, bool launch) {
   PS_REQUIRE(B >= 0 && N > 0 && M > 0, "ps_chamfer_step: bad sizes B=%d N=%d M=%d", B, N, M);
   PS_REQUIRE(sums_local6 != nullptr, "ps_chamfer_step: null sums_local6");
   PS_REQUIRE(B == 0 || (xyz1 && xyz2 && dist1 && dist2 && idx1 && idx2), "ps_chamfer_step: null pointer");
@@ -73,6 +73,7 @@ extern "C" int ps_chamfer_step(const float* xyz1, const float* xyz2, const float
   std::lock_guard<std::mutex> lock(cx.mu);
   if (!cx.ready) {
     PS_CUDA(cudaStreamCreateWithFlags(&cx.s_cap, cudaStreamNonBlocking));
+    scratch_pool_init(dev);
     cx.ready = true;
   }
   StepArgs a{xyz1, xyz2, with_bwd ? graddist1 : nullptr, with_bwd ? graddist2 : nullptr, dist1, dist2,
@@ -82,11 +83,11 @@ extern "C" int ps_chamfer_step(const float* xyz1, const float* xyz2, const float
   bool use_graph = true;
   if (const char* e = getenv("PS_STEP_GRAPH")) use_graph = atoi(e) != 0;
   cudaStreamCaptureStatus cs = cudaStreamCaptureStatusNone;
-  if (cudaStreamIsCapturing(stream, &cs) != cudaSuccess || cs != cudaStreamCaptureStatusNone) {
+  if (launch && (cudaStreamIsCapturing(stream, &cs) != cudaSuccess || cs != cudaStreamCaptureStatusNone)) {
     cudaGetLastError();
     return enqueue_step(a, stream);  // become part of the caller's own graph (stream-ordered scratch)
   }
-  if (!use_graph) return enqueue_step(a, stream);
+  if (!use_graph) return launch ? enqueue_step(a, stream) : PS_OK;
 
   GraphKey key;
   key.ptr(xyz1); key.ptr(xyz2); key.ptr(a.gd1); key.ptr(a.gd2); key.ptr(dist1); key.ptr(dist2); key.ptr(idx1); key.ptr(idx2);
@@ -98,12 +99,29 @@ extern "C" int ps_chamfer_step(const float* xyz1, const float* xyz2, const float
   int rc = PS_OK;
   GraphCache::Entry* exec = cx.graphs.get(key, cx.s_cap, [&](cudaStream_t s) { return enqueue_step(a, s); }, &rc);
   if (rc != PS_OK) return rc;
+  if (!launch) return PS_OK;
   if (exec) {
     PS_CUDA(cudaGraphLaunch(exec->exec, stream));
     launch_counter() += exec->kernels;
     return PS_OK;
   }
   return enqueue_step(a, stream);
+}
+
+extern "C" int ps_chamfer_step(const float* xyz1, const float* xyz2, const float* graddist1, const float* graddist2,
+                               float* dist1, float* dist2, int* idx1, int* idx2, float* gradxyz1, float* gradxyz2,
+                               double* sums_local6, double* sums_global6, ps_comm* comm, int B, int N, int M, int dev,
+                               void* stream) {
+  return chamfer_step_impl(xyz1, xyz2, graddist1, graddist2, dist1, dist2, idx1, idx2, gradxyz1, gradxyz2, sums_local6,
+                           sums_global6, comm, B, N, M, dev, stream, true);
+}
+
+// Captures and instantiates the graph of this exact call without launching anything (no stream work at all).
+extern "C" int ps_chamfer_step_prepare(const float* xyz1, const float* xyz2, const float* graddist1, const float* graddist2,
+                                       float* dist1, float* dist2, int* idx1, int* idx2, float* gradxyz1, float* gradxyz2,
+                                       double* sums_local6, double* sums_global6, ps_comm* comm, int B, int N, int M, int dev) {
+  return chamfer_step_impl(xyz1, xyz2, graddist1, graddist2, dist1, dist2, idx1, idx2, gradxyz1, gradxyz2, sums_local6,
+                           sums_global6, comm, B, N, M, dev, nullptr, false);
 }
 
 // Cache statistics of ps_chamfer_step on `dev`: exact replays, in-place retargets (cudaGraphExecUpdate), instantiations.

@@ -164,6 +164,8 @@ def test_step_with_comm_two_ranks_on_one_device():
     for r in range(2):
         d1, d2, _, _ = ps.chamfer_forward(data[r][0], data[r][1])
         want_local.append(ps.chamfer_sums(d1, d2))
+    for r in range(2):
+        steps[r].prepare(*data[r])  # graph instantiation may synchronise the device: not while a peer's wait kernel spins
     torch.cuda.synchronize()
     for it in range(6):
         for r in range(2):
