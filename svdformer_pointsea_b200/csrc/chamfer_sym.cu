@@ -339,6 +339,215 @@ __global__ void __launch_bounds__(CS_THREADS, 2) chamfer_sym_kernel(const SymPar
 }
 
 // ------------------------------------------------------------------------------------------------
+// Software-pipelined variant of chamfer_sym_kernel<8> (same algorithm, same results).
+//
+// The scan has two kinds of work per 4-target step: ~96 packed FP32-pipe instructions (the distances, 192 pipe
+// cycles) and ~70 ALU-pipe instructions (FMNMX3 row / column minima, the argmin bookkeeping, REDUX / VOTE of the
+// column fold; the ALU pipe is half rate).  ptxas schedules a step as "all distances, then all minima", the four
+// warps of a scheduler run the same code in near lockstep, and so the two pipes are used in ALTERNATION: ncu on
+// chamfer_sym_kernel shows fma 61 % / alu 49 % / issue 61 % with math_pipe_throttle as the first stall reason —
+// both pipes idle half of the time although neither is saturated.  Here the step is cut into two halves of four
+// A points (A: q 0-3, B: q 4-7) and pipelined by hand: the distances of one half are computed WHILE the minima
+// of the previous half are folded, in source order interleaved instruction group by instruction group, so every
+// single warp feeds both pipes at once.  Live distance registers stay at 32 (16 produced + 16 consumed).
+// GRAN: argmin bookkeeping once per GRAN steps (1 or 2): the final re-evaluation then looks at 4*GRAN candidates
+template <int Q, int UNROLL, int GRAN>
+__global__ void __launch_bounds__(CS_THREADS, 2) chamfer_sym2_kernel(const SymParams p) {
+  static_assert(Q == 8, "the pipelined variant is written for 8 A points per thread");
+  constexpr int TA = CS_THREADS * Q;
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  float* sx = reinterpret_cast<float*>(smem_raw);
+  float* sy = sx + CS_TILE;
+  float* sz = sy + CS_TILE;
+  u64* colkey = reinterpret_cast<u64*>(sz + CS_TILE);
+  float* ax = reinterpret_cast<float*>(colkey + CS_TILE);
+  float* ay = ax + TA;
+  float* az = ay + TA;
+
+  int b, at, t0, t1;
+  if (!sym_decode_unit(p, b, at, t0, t1)) return;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int na = p.na, nb = p.nb;
+  const float INF = __int_as_float(0x7f800000);
+
+  u64 nqx[Q], nqy[Q], nqz[Q];
+  float best[Q];
+  int cstep[Q];
+  const float* abase = p.a + (size_t)b * na * 3;
+#pragma unroll
+  for (int q = 0; q < Q; q++) {
+    const int i = at * TA + tid * Q + q;
+    const bool valid = i < na;
+    const float x = valid ? __ldg(abase + (size_t)i * 3 + 0) : INF;  // see chamfer_sym_kernel: +inf slots never win
+    const float y = valid ? __ldg(abase + (size_t)i * 3 + 1) : 0.f;
+    const float z = valid ? __ldg(abase + (size_t)i * 3 + 2) : 0.f;
+    ax[tid * Q + q] = x; ay[tid * Q + q] = y; az[tid * Q + q] = z;
+    nqx[q] = pack2(-x, -x); nqy[q] = pack2(-y, -y); nqz[q] = pack2(-z, -z);
+    best[q] = INF;
+    cstep[q] = 0;
+  }
+  const float* bcloud = p.b + (size_t)b * nb * 3;
+
+  for (int ts = t0; ts < t1; ts += CS_TILE) {
+    const int cnt = min(CS_TILE, t1 - ts);
+    const int cnt_pad = (cnt + 31) / 32 * 32;  // whole 32-point blocks: the padding sits at +inf and never wins
+    const float* tb = bcloud + (size_t)ts * 3;
+    const bool vec = (reinterpret_cast<uintptr_t>(tb) & 15) == 0;
+    __syncthreads();  // previous tile (and its column pass) fully consumed
+    for (int g = tid; g < cnt_pad / 4; g += CS_THREADS) {
+      float4 X, Y, Z;
+      if (vec && g * 4 + 4 <= cnt) {
+        const float4 a = __ldg(reinterpret_cast<const float4*>(tb + g * 12));
+        const float4 bb = __ldg(reinterpret_cast<const float4*>(tb + g * 12 + 4));
+        const float4 c = __ldg(reinterpret_cast<const float4*>(tb + g * 12 + 8));
+        X = make_float4(a.x, a.w, bb.z, c.y);
+        Y = make_float4(a.y, bb.x, bb.w, c.z);
+        Z = make_float4(a.z, bb.y, c.x, c.w);
+      } else {
+        float xs[4], ys[4], zs[4];
+#pragma unroll
+        for (int e = 0; e < 4; e++) {
+          const int pi = g * 4 + e;
+          const bool in = pi < cnt;
+          xs[e] = in ? __ldg(tb + pi * 3 + 0) : INF;
+          ys[e] = in ? __ldg(tb + pi * 3 + 1) : 0.f;
+          zs[e] = in ? __ldg(tb + pi * 3 + 2) : 0.f;
+        }
+        X = make_float4(xs[0], xs[1], xs[2], xs[3]);
+        Y = make_float4(ys[0], ys[1], ys[2], ys[3]);
+        Z = make_float4(zs[0], zs[1], zs[2], zs[3]);
+      }
+      *reinterpret_cast<float4*>(&sx[g * 4]) = X;
+      *reinterpret_cast<float4*>(&sy[g * 4]) = Y;
+      *reinterpret_cast<float4*>(&sz[g * 4]) = Z;
+    }
+    for (int j = tid; j < cnt_pad; j += CS_THREADS) colkey[j] = ~0ull;
+    __syncthreads();
+
+    const int step0 = (ts - t0) / CS_STEP;
+    // pipeline prologue: distances of half A (q 0-3) for step 0
+    ulonglong2 X = *reinterpret_cast<const ulonglong2*>(&sx[0]);
+    ulonglong2 Y = *reinterpret_cast<const ulonglong2*>(&sy[0]);
+    ulonglong2 Z = *reinterpret_cast<const ulonglong2*>(&sz[0]);
+    u64 dA01[4], dA23[4], dB01[4], dB23[4];
+#pragma unroll
+    for (int i = 0; i < 4; i++) {
+      dA01[i] = dist2x2(X.x, Y.x, Z.x, nqx[i], nqy[i], nqz[i]);
+      dA23[i] = dist2x2(X.y, Y.y, Z.y, nqx[i], nqy[i], nqz[i]);
+    }
+    float old[Q];  // GRAN == 2: the running minima before the current pair of steps
+#pragma unroll
+    for (int q = 0; q < Q; q++) old[q] = INF;
+    for (int j32 = 0; j32 < cnt_pad; j32 += 32) {
+      unsigned key_m = 0xffffffffu, key_b = 1u;  // owner lane keeps the ballot MASK; ffs once per 32 B points
+#pragma unroll UNROLL
+      for (int s8 = 0; s8 < 8; s8++) {
+        const int step = step0 + j32 / CS_STEP + s8;
+        float c0 = INF, c1 = INF, c2 = INF, c3 = INF;
+        // ---- half 1: distances of q 4-7 at this step  ||  minima of q 0-3 at this step ----------------
+#pragma unroll
+        for (int i = 0; i < 4; i++) {
+          dB01[i] = dist2x2(X.x, Y.x, Z.x, nqx[4 + i], nqy[4 + i], nqz[4 + i]);
+          dB23[i] = dist2x2(X.y, Y.y, Z.y, nqx[4 + i], nqy[4 + i], nqz[4 + i]);
+          float nbv = min3(best[i], lo2(dA01[i]), hi2(dA01[i]));
+          nbv = min3(nbv, lo2(dA23[i]), hi2(dA23[i]));
+          if (GRAN == 1) { if (nbv < best[i]) cstep[i] = step; }
+          else if (s8 & 1) { if (nbv < old[i]) cstep[i] = step >> 1; }
+          else old[i] = best[i];
+          best[i] = nbv;
+          if (i & 1) {
+            c0 = min3(c0, lo2(dA01[i - 1]), lo2(dA01[i]));
+            c1 = min3(c1, hi2(dA01[i - 1]), hi2(dA01[i]));
+            c2 = min3(c2, lo2(dA23[i - 1]), lo2(dA23[i]));
+            c3 = min3(c3, hi2(dA23[i - 1]), hi2(dA23[i]));
+          }
+        }
+        // B points of the next step.  Past the tile's last step this reads the bytes behind the arrays (still
+        // inside this CTA's shared memory): those distances are computed and never consumed.
+        const int jn = j32 + (s8 + 1) * CS_STEP;
+        X = *reinterpret_cast<const ulonglong2*>(&sx[jn]);
+        Y = *reinterpret_cast<const ulonglong2*>(&sy[jn]);
+        Z = *reinterpret_cast<const ulonglong2*>(&sz[jn]);
+        // ---- half 2: distances of q 0-3 at the next step  ||  minima of q 4-7 at this step -------------
+#pragma unroll
+        for (int i = 0; i < 4; i++) {
+          dA01[i] = dist2x2(X.x, Y.x, Z.x, nqx[i], nqy[i], nqz[i]);
+          dA23[i] = dist2x2(X.y, Y.y, Z.y, nqx[i], nqy[i], nqz[i]);
+          float nbv = min3(best[4 + i], lo2(dB01[i]), hi2(dB01[i]));
+          nbv = min3(nbv, lo2(dB23[i]), hi2(dB23[i]));
+          if (GRAN == 1) { if (nbv < best[4 + i]) cstep[4 + i] = step; }
+          else if (s8 & 1) { if (nbv < old[4 + i]) cstep[4 + i] = step >> 1; }
+          else old[4 + i] = best[4 + i];
+          best[4 + i] = nbv;
+          if (i & 1) {
+            c0 = min3(c0, lo2(dB01[i - 1]), lo2(dB01[i]));
+            c1 = min3(c1, hi2(dB01[i - 1]), hi2(dB01[i]));
+            c2 = min3(c2, lo2(dB23[i - 1]), lo2(dB23[i]));
+            c3 = min3(c3, hi2(dB23[i - 1]), hi2(dB23[i]));
+          }
+        }
+        // ---- column fold of this step: warp minimum per B point + the lanes holding it -----------------
+        const unsigned b0 = __float_as_uint(c0), b1 = __float_as_uint(c1), b2 = __float_as_uint(c2), b3 = __float_as_uint(c3);
+        const unsigned m0 = __reduce_min_sync(0xffffffffu, b0);
+        const unsigned m1 = __reduce_min_sync(0xffffffffu, b1);
+        const unsigned m2 = __reduce_min_sync(0xffffffffu, b2);
+        const unsigned m3 = __reduce_min_sync(0xffffffffu, b3);
+        const unsigned l0 = __ballot_sync(0xffffffffu, b0 == m0);
+        const unsigned l1 = __ballot_sync(0xffffffffu, b1 == m1);
+        const unsigned l2 = __ballot_sync(0xffffffffu, b2 == m2);
+        const unsigned l3 = __ballot_sync(0xffffffffu, b3 == m3);
+        const int o = lane - s8 * CS_STEP;  // 0..3 for the four owner lanes of this step
+        if (o == 0) { key_m = m0; key_b = l0; }
+        if (o == 1) { key_m = m1; key_b = l1; }
+        if (o == 2) { key_m = m2; key_b = l2; }
+        if (o == 3) { key_m = m3; key_b = l3; }
+      }
+      atomicMin(&colkey[j32 + lane], ((u64)key_m << 32) | (unsigned)(warp * 32 + __ffs(key_b) - 1));
+    }
+    __syncthreads();  // all column keys of this tile are final
+
+    for (int jj = tid; jj < cnt; jj += CS_THREADS) {
+      const u64 key = colkey[jj];
+      const unsigned mbits = (unsigned)(key >> 32);
+      const int tcand = (int)(unsigned)key;
+      const float bx = sx[jj], by = sy[jj], bz = sz[jj];
+      int found = 0;
+#pragma unroll
+      for (int q = Q - 1; q >= 0; q--) {
+        const float d = dist2_ref(bx - ax[tcand * Q + q], by - ay[tcand * Q + q], bz - az[tcand * Q + q]);
+        if (__float_as_uint(d) == mbits) found = q;
+      }
+      const int ia = at * TA + tcand * Q + found;
+      atomicMin(&p.keys_b[(size_t)b * nb + ts + jj], ((u64)mbits << 32) | (unsigned)ia);
+    }
+  }
+
+  // ---- row side: first B point of the remembered group of GRAN steps that reproduces `best` -----------------
+  const int last_ts = t0 + ((t1 - t0 - 1) / CS_TILE) * CS_TILE;
+  constexpr int NC = CS_STEP * GRAN;
+#pragma unroll
+  for (int q = 0; q < Q; q++) {
+    const int i = at * TA + tid * Q + q;
+    const int base = t0 + cstep[q] * NC;
+    const float qx = -lo2(nqx[q]), qy = -lo2(nqy[q]), qz = -lo2(nqz[q]);
+    int found = 0;
+    if (base >= last_ts) {
+      const int off = base - last_ts;  // inside the staged tile (its padding sits at +inf)
+#pragma unroll
+      for (int e = NC - 1; e >= 0; e--)
+        if (dist2_ref(sx[off + e] - qx, sy[off + e] - qy, sz[off + e] - qz) == best[q]) found = e;
+    } else {
+      const float* tp = bcloud + (size_t)base * 3;
+#pragma unroll
+      for (int e = NC - 1; e >= 0; e--)
+        if (dist2_ref(__ldg(tp + e * 3 + 0) - qx, __ldg(tp + e * 3 + 1) - qy, __ldg(tp + e * 3 + 2) - qz) == best[q]) found = e;
+    }
+    if (i >= na) continue;
+    atomicMin(&p.keys_a[(size_t)b * na + i], ((u64)__float_as_uint(best[q]) << 32) | (unsigned)(base + found));
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
 // A-packed variant.  Same algorithm, other register layout: the two halves of every packed
 // operand are two DIFFERENT A points of the thread (a_2p, a_2p+1) and the streamed B point is
 // duplicated in shared memory ((x_j, x_j) pairs, read as broadcast LDS.128).  An A point then
@@ -555,10 +764,23 @@ static int launch_sym(const SymParams& p, int grid, cudaStream_t stream) {
   return PS_OK;
 }
 
+template <int UNROLL, int GRAN>
+static int launch_sym2(const SymParams& p, int grid, cudaStream_t stream) {
+  const size_t smem = (size_t)3 * CS_TILE * 4 + (size_t)CS_TILE * 8 + (size_t)3 * CS_THREADS * 8 * 4;
+  auto kern = chamfer_sym2_kernel<8, UNROLL, GRAN>;
+  PS_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  kern<<<grid, CS_THREADS, smem, stream>>>(p);
+  PS_LAUNCH_CHECK();
+  return PS_OK;
+}
+
 // Returns PS_OK when it handled the call, 1 when the shape is better served by the two-pass kernel.
 int chamfer_fwd_symmetric(const float* xyz1, const float* xyz2, float* dist1, float* dist2, int* idx1,
                           int* idx2, double* sums6, const ps_comm* comm, int B, int N, int M, int dev, cudaStream_t stream) {
-  int variant = 1;  // 1: B-packed (chamfer_sym_kernel), 2: A-packed kernel (chamfer_symp_kernel), 0: two-pass
+  // 0: two-pass kernel (chamfer.cu); 1: chamfer_sym_kernel; 2: A-packed chamfer_symp_kernel; 3-7: software-pipelined
+  // chamfer_sym2_kernel<8, UNROLL, GRAN> (3: 8,1  4: 4,1  5: 2,1  6: 4,2  7: 2,2); default -1 = 6 where it applies
+  // (measured on B200, tools/chamfer_lab.py: C1 305 -> 291 us, 32 x 16384^2 2181 -> 2044 us), else 1
+  int variant = -1;
   if (const char* e = getenv("PS_CHAMFER_SYM")) variant = atoi(e);
   if (variant == 0) return 1;
   const int big = N > M ? N : M, small = N > M ? M : N;
@@ -626,13 +848,23 @@ int chamfer_fwd_symmetric(const float* xyz1, const float* xyz2, float* dist1, fl
     }
   }
   const int grid = (int)(p.ubig + (units - p.ubig) * p.fsub);
+  if (variant < 0) {
+    // the pipelined kernel scans whole 32-point blocks: ragged splits pay for their padding (8 x 1000 x 5000: +5 %)
+    const bool blocks = Q == 8 && (small % 32) == 0 && (p.split_len % 32) == 0 && (p.sub_len % 32) == 0;
+    variant = blocks ? 6 : 1;
+  }
   int rc;
   if (variant == 2) {
     if (Q == 16) rc = launch_symp<8>(p, grid, stream);
     else if (Q == 8) rc = launch_symp<4>(p, grid, stream);
     else rc = launch_symp<2>(p, grid, stream);
   } else {
-    if (Q == 8) rc = launch_sym<8>(p, grid, stream);
+    if (Q == 8 && variant == 3) rc = launch_sym2<8, 1>(p, grid, stream);
+    else if (Q == 8 && variant == 4) rc = launch_sym2<4, 1>(p, grid, stream);
+    else if (Q == 8 && variant == 5) rc = launch_sym2<2, 1>(p, grid, stream);
+    else if (Q == 8 && variant == 6) rc = launch_sym2<4, 2>(p, grid, stream);
+    else if (Q == 8 && variant == 7) rc = launch_sym2<2, 2>(p, grid, stream);
+    else if (Q == 8) rc = launch_sym<8>(p, grid, stream);
     else if (Q == 4) rc = launch_sym<4>(p, grid, stream);
     else rc = launch_sym<2>(p, grid, stream);
   }

@@ -62,7 +62,27 @@ def ev_time(fn, iters, warm=2):
 
 
 # ------------------------------------------------------------------------------------------- C4
-def c4_arm(arm, iters, knn):
+def install_torch_scatter_stub():
+    """torch_scatter is a third-party package absent from this image; models_PointSea/mv_utils_zs.py:1,130 uses one
+    call, scatter(src, index, dim, out=..., reduce="max").  A torch stand-in (test harness only)."""
+    if "torch_scatter" in sys.modules:
+        return
+    m = types.ModuleType("torch_scatter")
+
+    def scatter(src, index, dim=-1, out=None, dim_size=None, reduce="sum"):
+        red = {"max": "amax", "min": "amin", "sum": "sum", "add": "sum", "mean": "mean", "mul": "prod"}[reduce]
+        if out is None:
+            shape = list(src.shape)
+            shape[dim] = int(dim_size if dim_size is not None else index.max().item() + 1)
+            out = torch.zeros(shape, device=src.device, dtype=src.dtype)
+            return out.scatter_reduce_(dim, index, src, reduce=red, include_self=False)
+        return out.scatter_reduce_(dim, index, src, reduce=red, include_self=True)
+
+    m.scatter = scatter
+    sys.modules["torch_scatter"] = m
+
+
+def c4_arm(arm, iters, knn, batch=32, model_name="svdformer", loss_name="get_loss"):
     rank, world, dev = dist_setup()
     if not osp.isdir(REF_TREE):
         print(json.dumps({"config": "C4", "arm": arm, "unavailable": f"{REF_TREE} not staged"}))
@@ -93,37 +113,66 @@ def c4_arm(arm, iters, knn):
         import pointnet2_ops  # noqa: F401  (binds the reference wrappers to the reference kernels)
         pointnet2_ops._ext = ref_pn
     from types import SimpleNamespace as NS
-    import models.model_utils as mu
+    install_torch_scatter_stub()
+    # no network on the box: PointSea asks torchvision for ImageNet weights (PointSea.py:40); random init instead
+    import torchvision.models as tvm
+    _resnet18 = tvm.resnet18
+    tvm.resnet18 = lambda *a, weights=None, **k: _resnet18(*a, weights=None, **k)
+    if model_name == "pointsea":
+        import models_PointSea.model_utils as mu
+    else:
+        import models.model_utils as mu
     if knn == "ours" and arm == "ours":
         import svdformer_pointsea_b200 as ps
         mu.query_knn = ps.query_knn  # the optional one-line swap of INTEGRATION.md
     if knn == "all" and arm == "ours":
         import svdformer_pointsea_b200 as ps
         ps.patch_model_utils(mu)     # every call-site function (kNN, sample_and_group_knn, EdgeConv front, ...)
-    from models.SVDFormer import Model  # after the patch: it does `from models.model_utils import *`
-    from utils.loss_utils import get_loss
+    if model_name == "pointsea":
+        from models_PointSea.PointSea import Model
+    else:
+        from models.SVDFormer import Model  # after the patch: it does `from models.model_utils import *`
+    import utils.loss_utils as lu
+    if loss_name == "get_loss_PM":
+        def get_loss(preds, gt, sqrt=True):
+            return lu.get_loss_PM(preds, partial, gt, sqrt=sqrt)
+    else:
+        get_loss = lu.get_loss
     cfg = NS(NETWORK=NS(step1=4, step2=8, merge_points=512, local_points=512, view_distance=0.7),
              DATASET=NS(TEST_DATASET="ShapeNet"))
     torch.manual_seed(1)
     model = Model(cfg).to(dev)
     model.train()
-    B = 32 // world
+    B = batch // world
     g = torch.Generator().manual_seed(1234 + 4)
-    partial_all = (torch.rand(32, 2048, 3, generator=g) - 0.5)
-    gt_all = (torch.rand(32, 16384, 3, generator=g) - 0.5)
+    partial_all = (torch.rand(batch, 2048, 3, generator=g) - 0.5)
+    gt_all = (torch.rand(batch, 16384, 3, generator=g) - 0.5)
     partial = partial_all[rank * B:(rank + 1) * B].contiguous().to(dev)
     gt = gt_all[rank * B:(rank + 1) * B].contiguous().to(dev)
-    render = mu.PCViews(TRANS=-cfg.NETWORK.view_distance, RESOLUTION=224)
+    if model_name == "pointsea":
+        import models_PointSea.mv_utils_zs as mv
+        render = mv.PCViews_Real(TRANS=-cfg.NETWORK.view_distance)
+    else:
+        render = mu.PCViews(TRANS=-cfg.NETWORK.view_distance, RESOLUTION=224)
     out = {}
 
-    if world > 1 and arm == "ours":
+    if world > 1 and arm == "ours" and loss_name == "get_loss_PM":
+        from svdformer_pointsea_b200.dist import get_loss_PM_sharded
+
+        def get_loss(preds, gt, sqrt=True):  # noqa: F811
+            return get_loss_PM_sharded(preds, partial, gt, sqrt=sqrt)
+    elif world > 1 and arm == "ours":
         # batch-sharded loss: the reference's get_loss over the GLOBAL batch = local Chamfer terms + ONE all-reduce
         # of their partial sums (svdformer_pointsea_b200.dist.get_loss_sharded), identical on every rank
         from svdformer_pointsea_b200.dist import get_loss_sharded as get_loss  # noqa: F811
 
+    def make_depth():
+        img = render.get_img(partial)
+        return img if model_name == "pointsea" else torch.unsqueeze(img, 1)
+
     def step():
         with torch.no_grad():
-            depth = torch.unsqueeze(render.get_img(partial), 1)
+            depth = make_depth()
             preds = model(partial, depth)
             loss, losses = get_loss(preds, gt, sqrt=True)
         out["loss"], out["losses"] = loss, losses
@@ -131,12 +180,14 @@ def c4_arm(arm, iters, knn):
     ts = ev_time(step, iters)
     # time only the loss (FPS x2 + Chamfer x3), the part the reference runs un-parallelised
     with torch.no_grad():
-        depth = torch.unsqueeze(render.get_img(partial), 1)
+        depth = make_depth()
         preds = model(partial, depth)
     tl = ev_time(lambda: get_loss(preds, gt, sqrt=True), iters)
     res = {"config": "C4 SVDFormer PCN fwd + Chamfer loss", "arm": arm, "knn": knn if arm == "ours" else "torch",
            "world": world, "B_per_gpu": B, "ms_step_min": round(min(ts), 3), "ms_step_median": round(sorted(ts)[len(ts) // 2], 3),
-           "ms_loss_min": round(min(tl), 3), "loss": float(out["loss"]), "losses": [float(x) for x in out["losses"]]}
+           "ms_loss_min": round(min(tl), 3), "loss": float(out["loss"]), "losses": [float(x) for x in out["losses"]],
+           "loss_hex": float(out["loss"]).hex(), "losses_hex": [float(x).hex() for x in out["losses"]],
+           "model": model_name, "loss_fn": loss_name, "batch": batch}
     if rank == 0:
         print(json.dumps(res))
     if world > 1:
@@ -148,10 +199,11 @@ def c4_arm(arm, iters, knn):
 def c4(args):
     arms = ["ours", "ref"] if args.arm == "both" else [args.arm]
     if args.arm != "both":
-        return c4_arm(args.arm, args.iters, args.knn)
+        return c4_arm(args.arm, args.iters, args.knn, args.batch, args.model, args.loss)
     lines = []
     for arm, knn in (("ours", "torch"), ("ours", "ours"), ("ours", "all"), ("ref", "torch")):
-        p = subprocess.run([sys.executable, __file__, "c4", "--arm", arm, "--iters", str(args.iters), "--knn", knn],
+        p = subprocess.run([sys.executable, __file__, "c4", "--arm", arm, "--iters", str(args.iters), "--knn", knn, "--batch", str(args.batch),
+                            "--model", args.model, "--loss", args.loss],
                            capture_output=True, text=True)
         last = [ln for ln in p.stdout.strip().splitlines() if ln.startswith("{")]
         if not last:
@@ -222,5 +274,8 @@ if __name__ == "__main__":
     ap.add_argument("--knn", default="torch", choices=["torch", "ours", "all"])
     ap.add_argument("--iters", type=int, default=5)
     ap.add_argument("--no-check", action="store_true")
+    ap.add_argument("--batch", type=int, default=32, help="c4: total clouds")
+    ap.add_argument("--model", default="svdformer", choices=["svdformer", "pointsea"])
+    ap.add_argument("--loss", default="get_loss", choices=["get_loss", "get_loss_PM"])
     a = ap.parse_args()
     {"c4": c4, "c5": c5}[a.config](a)
