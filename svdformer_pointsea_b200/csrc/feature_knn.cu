@@ -90,6 +90,59 @@ __device__ __forceinline__ float fk_sort_values(float v, int lane) {
   return v;
 }
 
+// One warp reduces one row of npad distances (shared memory, padding at +inf) to its k smallest and writes them
+// in the requested order.
+__device__ __forceinline__ void fk_select_row(const FkArgs& a, const float* row, int b, int q, int npad, float* bufd, int* bufi) {
+  const int lane = threadIdx.x & 31;
+  const float INF = __int_as_float(0x7f800000);
+  const int k = a.k, N = a.N;
+  const int nsteps = npad / 32;
+  float lmin = INF;
+  for (int u = 0; u < nsteps; u++) lmin = fminf(lmin, row[u * 32 + lane]);
+  const float T = __shfl_sync(0xffffffffu, fk_sort_values(lmin, lane), k - 1);
+  int cnt = 0;
+  for (int u = 0; u < nsteps; u++) {
+    const float dj = row[u * 32 + lane];
+    const bool pass = dj <= T;
+    const unsigned mask = __ballot_sync(0xffffffffu, pass);
+    if (mask) {
+      const int pos = cnt + __popc(mask & ((1u << lane) - 1u));
+      if (pass && pos < 32) { bufd[pos] = dj; bufi[pos] = u * 32 + lane; }
+      cnt += __popc(mask);
+    }
+  }
+  __syncwarp();
+  float d = INF;
+  int ci = 0x7fffffff;
+  if (cnt <= 32) {
+    if (lane < cnt) { d = bufd[lane]; ci = bufi[lane]; }
+    warp_sort_pairs(d, ci, lane);
+  } else {
+    // many equal distances: streaming insertion into a sorted warp list, candidates in index order
+    float thr = INF;
+    for (int j0 = 0; j0 < N; j0 += 32) {
+      const float dj = (j0 + lane < N) ? row[j0 + lane] : INF;
+      unsigned mask = __ballot_sync(0xffffffffu, dj < thr);
+      while (mask) {
+        const int src = __ffs(mask) - 1;
+        mask &= mask - 1;
+        const float cd = __shfl_sync(0xffffffffu, dj, src);
+        const bool ok = cd < thr;
+        const float ud = __shfl_up_sync(0xffffffffu, d, 1);
+        const int ui = __shfl_up_sync(0xffffffffu, ci, 1);
+        const bool shift = ok && (lane > 0) && (ud > cd);
+        const bool ins = ok && (d > cd);
+        d = shift ? ud : (ins ? cd : d);
+        ci = shift ? ui : (ins ? j0 + src : ci);
+        thr = __shfl_sync(0xffffffffu, d, k - 1);
+      }
+    }
+  }
+  if (a.order == PS_ORDER_TOPK) warp_torch_topk_order(d, ci, lane, k);
+  if (lane < k) a.idx[((size_t)b * a.S + q) * k + lane] = ci;
+  __syncwarp();
+}
+
 template <int TQ>
 __global__ void __launch_bounds__(FK_THREADS) knn_feat_kernel(const FkArgs a) {
   constexpr int QPT = TQ / FK_WARPS;  // queries per thread in the tile loop = rows per warp in the selection
@@ -215,57 +268,149 @@ __global__ void __launch_bounds__(FK_THREADS) knn_feat_kernel(const FkArgs a) {
   __syncwarp();  // each warp selects from the rows it wrote itself
 
   // ---- per-row selection of the k smallest (one warp per row, rows live in shared memory) ----------
-  const int k = a.k;
-  const int nsteps = npad / 32;
 #pragma unroll 1
   for (int i = 0; i < QPT; i++) {
     const int q = q0 + warp * QPT + i;
     if (q >= S) break;  // warp-uniform
-    const float* row = dist + (size_t)(warp * QPT + i) * npad;
-    float lmin = INF;
-    for (int u = 0; u < nsteps; u++) lmin = fminf(lmin, row[u * 32 + lane]);
-    const float T = __shfl_sync(0xffffffffu, fk_sort_values(lmin, lane), k - 1);
-    int cnt = 0;
-    for (int u = 0; u < nsteps; u++) {
-      const float dj = row[u * 32 + lane];
-      const bool pass = dj <= T;
-      const unsigned mask = __ballot_sync(0xffffffffu, pass);
-      if (mask) {
-        const int pos = cnt + __popc(mask & ((1u << lane) - 1u));
-        if (pass && pos < 32) { bufd[warp][pos] = dj; bufi[warp][pos] = u * 32 + lane; }
-        cnt += __popc(mask);
+    fk_select_row(a, dist + (size_t)(warp * QPT + i) * npad, b, q, npad, bufd[warp], bufi[warp]);
+  }
+}
+
+// ---- 8 x 8 register tiles, cp.async double buffering (TQ = 32, N <= 1024) ---------------------------------------
+// knn_feat_kernel<32> above is bound by SHARED-MEMORY BANDWIDTH, not by the FP32 pipe (ncu, B=32 C=256 N=512:
+// lsu wavefronts 57 %, fma 52 %, short_scoreboard the first stall): its 4 x 8 tile reads 12 floats per 32 FMAs, and
+// the SM moves one 128-byte wavefront per cycle for all four schedulers.  Here a warp owns 8 queries x 256
+// references of a 512-reference pass (8 x 8 per lane): 16 floats per 64 FMAs, 10 wavefronts per 64 FP32-pipe
+// cycles, so the LSU stays below the FMA time.  Stages of 8 channels arrive by cp.async into two shared-memory
+// buffers (no prefetch registers), ONE barrier per stage.  Same ascending-channel FMA chain, same results.
+constexpr int F8_KC = 8;
+constexpr int F8_TR = 512;
+constexpr int F8_TQ = 32;
+
+__device__ __forceinline__ void cp_async4(unsigned dst, const float* src, bool valid) {
+  const int n = valid ? 4 : 0;  // src-size 0: zero fill
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 4, %2;" ::"r"(dst), "l"(src), "r"(n) : "memory");
+}
+__device__ __forceinline__ void cp_async16(unsigned dst, const float* src, bool valid) {
+  const int n = valid ? 16 : 0;
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(n) : "memory");
+}
+
+template <int VEC>
+__global__ void __launch_bounds__(FK_THREADS, 2) knn_feat8_kernel(const FkArgs a) {
+  extern __shared__ __align__(16) float smem[];
+  float* dist = smem;                                 // 32 x npad
+  float* qs = dist + (size_t)F8_TQ * a.npad;          // 2 x F8_KC x 32
+  float* rs = qs + 2 * F8_KC * F8_TQ;                 // 2 x F8_KC x F8_TR
+  __shared__ float bufd[FK_WARPS][32];
+  __shared__ int bufi[FK_WARPS][32];
+  const int b = blockIdx.y, q0 = blockIdx.x * F8_TQ, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int qg = warp & 3, rh = warp >> 2;  // this warp: queries qg*8..+8, reference half rh of the pass
+  const float INF = __int_as_float(0x7f800000);
+  const float* xq = a.xq + (size_t)b * a.sbq;
+  const float* xr = a.xr + (size_t)b * a.sbr;
+  const int C = a.C, N = a.N, S = a.S, npad = a.npad;
+
+  float qn[8];
+#pragma unroll
+  for (int i = 0; i < 8; i++) {
+    const int q = q0 + qg * 8 + i;
+    qn[i] = q < S ? __ldg(a.qq + (size_t)b * S + q) : 0.f;
+  }
+  auto load = [&](int r0, int c0, int buf) {
+    float* rb = rs + buf * F8_KC * F8_TR;
+    float* qb = qs + buf * F8_KC * F8_TQ;
+    if (VEC) {  // references contiguous along r (channel-major tensors, N % 4 == 0, 16-byte aligned rows)
+#pragma unroll
+      for (int j = 0; j < F8_KC * F8_TR / 4 / FK_THREADS; j++) {
+        const int i = tid + j * FK_THREADS;
+        const int kc = i / (F8_TR / 4), r = (i % (F8_TR / 4)) * 4;
+        const bool ok = c0 + kc < C && r0 + r < N;
+        cp_async16(smem_u32(rb + kc * F8_TR + r), xr + (ok ? (size_t)(r0 + r) + (size_t)(c0 + kc) * a.scr : 0), ok);
       }
-    }
-    __syncwarp();
-    float d = INF;
-    int ci = 0x7fffffff;
-    if (cnt <= 32) {
-      if (lane < cnt) { d = bufd[warp][lane]; ci = bufi[warp][lane]; }
-      warp_sort_pairs(d, ci, lane);
     } else {
-      // many equal distances: streaming insertion into a sorted warp list, candidates in index order
-      float thr = INF;
-      for (int j0 = 0; j0 < N; j0 += 32) {
-        const float dj = (j0 + lane < N) ? row[j0 + lane] : INF;
-        unsigned mask = __ballot_sync(0xffffffffu, dj < thr);
-        while (mask) {
-          const int src = __ffs(mask) - 1;
-          mask &= mask - 1;
-          const float cd = __shfl_sync(0xffffffffu, dj, src);
-          const bool ok = cd < thr;
-          const float ud = __shfl_up_sync(0xffffffffu, d, 1);
-          const int ui = __shfl_up_sync(0xffffffffu, ci, 1);
-          const bool shift = ok && (lane > 0) && (ud > cd);
-          const bool ins = ok && (d > cd);
-          d = shift ? ud : (ins ? cd : d);
-          ci = shift ? ui : (ins ? j0 + src : ci);
-          thr = __shfl_sync(0xffffffffu, d, k - 1);
-        }
+#pragma unroll
+      for (int j = 0; j < F8_KC * F8_TR / FK_THREADS; j++) {
+        const int i = tid + j * FK_THREADS;
+        const int kc = i / F8_TR, r = i % F8_TR;
+        const bool ok = c0 + kc < C && r0 + r < N;
+        cp_async4(smem_u32(rb + kc * F8_TR + r), xr + (ok ? (size_t)(r0 + r) * a.snr + (size_t)(c0 + kc) * a.scr : 0), ok);
       }
     }
-    if (a.order == PS_ORDER_TOPK) warp_torch_topk_order(d, ci, lane, k);
-    if (lane < k) a.idx[((size_t)b * S + q) * k + lane] = ci;
-    __syncwarp();
+    {
+      const int kc = tid / F8_TQ, q = tid % F8_TQ;  // F8_KC * F8_TQ == FK_THREADS
+      const bool ok = c0 + kc < C && q0 + q < S;
+      cp_async4(smem_u32(qb + kc * F8_TQ + q), xq + (ok ? (size_t)(q0 + q) * a.snq + (size_t)(c0 + kc) * a.scq : 0), ok);
+    }
+    asm volatile("cp.async.commit_group;" ::: "memory");
+  };
+
+  const int nstage = (C + F8_KC - 1) / F8_KC;
+  for (int r0 = 0; r0 < npad; r0 += F8_TR) {
+    u64 acc2[8][4];
+#pragma unroll
+    for (int i = 0; i < 8; i++)
+#pragma unroll
+      for (int j = 0; j < 4; j++) acc2[i][j] = 0ull;
+    load(r0, 0, 0);
+    for (int st = 0; st < nstage; st++) {
+      const int c0 = st * F8_KC;
+      const int kcn = min(F8_KC, C - c0);
+      asm volatile("cp.async.wait_group 0;" ::: "memory");
+      __syncthreads();  // stage st has landed for everyone; everyone is done with stage st-1 (the other buffer)
+      if (st + 1 < nstage) load(r0, c0 + F8_KC, (st + 1) & 1);
+      const float* rb = rs + (st & 1) * F8_KC * F8_TR + rh * 256 + lane * 4;
+      const float* qb = qs + (st & 1) * F8_KC * F8_TQ + qg * 8;
+      auto step = [&](int kc) {
+        const ulonglong2 r0v = *reinterpret_cast<const ulonglong2*>(rb + kc * F8_TR);
+        const ulonglong2 r1v = *reinterpret_cast<const ulonglong2*>(rb + kc * F8_TR + 128);
+        const float4 qa = *reinterpret_cast<const float4*>(qb + kc * F8_TQ);
+        const float4 qc = *reinterpret_cast<const float4*>(qb + kc * F8_TQ + 4);
+        const float qv[8] = {qa.x, qa.y, qa.z, qa.w, qc.x, qc.y, qc.z, qc.w};
+#pragma unroll
+        for (int i = 0; i < 8; i++) {
+          const u64 qd = pack2(qv[i], qv[i]);
+          acc2[i][0] = fma2(qd, r0v.x, acc2[i][0]);
+          acc2[i][1] = fma2(qd, r0v.y, acc2[i][1]);
+          acc2[i][2] = fma2(qd, r1v.x, acc2[i][2]);
+          acc2[i][3] = fma2(qd, r1v.y, acc2[i][3]);
+        }
+      };
+      if (kcn == F8_KC) {
+#pragma unroll
+        for (int kc = 0; kc < F8_KC; kc++) step(kc);
+      } else {
+        for (int kc = 0; kc < kcn; kc++) step(kc);  // no padded product enters the chain
+      }
+    }
+    // dist = ((-2 * dot) + |q|^2) + |r|^2 ; padding columns at +inf
+#pragma unroll
+    for (int h = 0; h < 2; h++) {
+      const int rbase = r0 + rh * 256 + h * 128 + lane * 4;
+      float pn[4];
+#pragma unroll
+      for (int j = 0; j < 4; j++) pn[j] = rbase + j < N ? __ldg(a.pp + (size_t)b * N + rbase + j) : INF;
+#pragma unroll
+      for (int i = 0; i < 8; i++) {
+        const float d0 = lo2(acc2[i][2 * h]), d1 = hi2(acc2[i][2 * h]), d2 = lo2(acc2[i][2 * h + 1]), d3 = hi2(acc2[i][2 * h + 1]);
+        float o[4] = {d0, d1, d2, d3};
+#pragma unroll
+        for (int j = 0; j < 4; j++) {
+          o[j] = __fadd_rn(__fadd_rn(__fmul_rn(-2.0f, o[j]), qn[i]), pn[j]);
+          if (rbase + j >= N) o[j] = INF;
+        }
+        *reinterpret_cast<float4*>(&dist[(size_t)(qg * 8 + i) * npad + rbase]) = make_float4(o[0], o[1], o[2], o[3]);
+      }
+    }
+    __syncthreads();  // the next pass refills buffer 0
+  }
+  // rows were written by two warps each (the two reference halves): the barrier above makes them complete
+#pragma unroll 1
+  for (int i = 0; i < F8_TQ / FK_WARPS; i++) {
+    const int row = warp * (F8_TQ / FK_WARPS) + i;
+    const int q = q0 + row;
+    if (q >= S) break;  // warp-uniform
+    fk_select_row(a, dist + (size_t)row * npad, b, q, npad, bufd[warp], bufi[warp]);
   }
 }
 
@@ -341,6 +486,24 @@ extern "C" int ps_knn_feat(const float* xr, const float* xq, int* idx, int B, in
   if (int rc = rowsumsq_launch(xr, norms, B, C, N, a.sbr, a.snr, a.scr, stream, "ps_knn_feat")) return rc;
   if (!self)
     if (int rc = rowsumsq_launch(xq, norms + (size_t)B * N, B, C, S, a.sbq, a.snq, a.scq, stream, "ps_knn_feat")) return rc;
+  // 8 x 8 register tiles for the models' EdgeConv shapes (full query tiles, N <= 1024): see knn_feat8_kernel
+  bool use8 = TQ == 32 && N <= 1024;
+  if (const char* e = getenv("PS_KNN_FEAT8")) use8 = use8 && atoi(e) != 0;
+  if (use8) {
+    a.npad = (N + F8_TR - 1) / F8_TR * F8_TR;
+    const size_t smem = (size_t)F8_TQ * a.npad * 4 + (size_t)2 * F8_KC * F8_TQ * 4 + (size_t)2 * F8_KC * F8_TR * 4;
+    const bool vec = a.snr == 1 && (N & 3) == 0 && (a.scr & 3) == 0 && (a.sbr & 3) == 0 && (reinterpret_cast<uintptr_t>(xr) & 15) == 0;
+    const dim3 grid8(ceil_div(S, F8_TQ), B);
+    if (vec) {
+      PS_CUDA(cudaFuncSetAttribute(knn_feat8_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      knn_feat8_kernel<1><<<grid8, FK_THREADS, smem, stream>>>(a);
+    } else {
+      PS_CUDA(cudaFuncSetAttribute(knn_feat8_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      knn_feat8_kernel<0><<<grid8, FK_THREADS, smem, stream>>>(a);
+    }
+    PS_LAUNCH_CHECK();
+    return norms_mem.release();
+  }
   const dim3 grid(ceil_div(S, TQ), B);
 #define PS_FK(TQV)                                                                                  \
   {                                                                                                 \
