@@ -69,7 +69,12 @@ _lib = None
 
 
 class PointSeaError(RuntimeError):
-    """Raised for every non-zero return code of the native library."""
+    """Raised for every non-zero return code of the native library (`code`: the PS_ERR_* value, None for errors
+    raised by the Python layer itself)."""
+    code = None
+
+
+PS_ERR_UNSUPPORTED = -3
 
 
 def load():
@@ -101,7 +106,9 @@ def load():
 def check(rc, what):
     if rc != 0:
         msg = load().ps_last_error().decode("utf-8", "replace")
-        raise PointSeaError(f"{what} failed (code {rc}): {msg}")
+        err = PointSeaError(f"{what} failed (code {rc}): {msg}")
+        err.code = rc
+        raise err
 
 
 _checked_devices = set()

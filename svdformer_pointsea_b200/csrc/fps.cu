@@ -28,7 +28,7 @@
 //     ~520 cycles even inside one CTA (profiles/microbench_r1.jsonl); a remote store is visible after ~1/2 of
 //     the 215-cycle DSMEM round trip and a local poll costs ~40.  With 4 fat warps per CTA the polling load on
 //     the LSU is small (the first attempt polled with 16 warps and lost to the barrier).  The spin is bounded:
-//     a protocol failure raises the error flag instead of hanging the GPU.
+//     a protocol failure traps (the launch fails with an error) instead of hanging the GPU or returning garbage.
 //   The message carries the winner's coordinates, so the next iteration never touches global
 //   memory.  Two slot buffers suffice: a writer can only be at iteration j+2 after consuming all
 //   candidates of j+1, and a reader sends its j+1 candidate only after reading the slots of j.
@@ -66,7 +66,6 @@ struct FpsArgs {
   const float* xyz;
   int* idx;
   float* new_xyz;  // optional (B, npoint, 3): coordinates of the sampled points (fused fps_subsample)
-  int* err;        // optional device flag raised when a bounded spin gives up (MODE 3)
   int N, npoint;
   int L;     // log2(bs) of the reference launch
   int nper;  // ceil(N / bs)
@@ -342,7 +341,7 @@ __global__ void __launch_bounds__(T, 1) fps_kernel(const FpsArgs a) {
           ok = ok && va[u].w == j && vb[u].w == j;
         }
       } while (!__all_sync(0xffffffffu, ok) && ++spins < FPS_SPIN_LIMIT);
-      if (spins >= FPS_SPIN_LIMIT) { if (lane == 0 && a.err) atomicExch(a.err, 1); break; }  // bounded: never hang
+      if (spins >= FPS_SPIN_LIMIT) __trap();  // bounded: a protocol failure aborts the launch (an error on the stream), never wrong samples or a hang
     } else {
 #pragma unroll
       for (int u = 0; u < MAXE; u++) {
@@ -580,7 +579,7 @@ extern "C" int ps_fps_sample(const float* xyz, int* idx, float* new_xyz, int B, 
   const int nsm = sm_count(dev);
 
   FpsArgs a;
-  a.xyz = xyz; a.idx = idx; a.new_xyz = new_xyz; a.N = N; a.npoint = npoint; a.err = nullptr;
+  a.xyz = xyz; a.idx = idx; a.new_xyz = new_xyz; a.N = N; a.npoint = npoint;
   a.L = ref_block_log2(N);
   a.nper = ceil_div(N, 1 << a.L);
 

@@ -260,16 +260,39 @@ def sample_and_group_knn(xyz, points, npoint, k, use_xyz=True, idx=None):
     return new_xyz, new_points, idx, grouped_xyz
 
 
+def _with_reference_fallback(ours, reference):
+    """`ours`, and the reference module's ORIGINAL torch expression when the C ABI answers PS_ERR_UNSUPPORTED (a
+    shape outside what the kernels cover: k > 32, feature kNN beyond the shared-memory distance block, ...).  The
+    reference's models accept those shapes, so a patched model must not crash on them; every other error, and a
+    missing library, still raises."""
+    if reference is None:
+        return ours
+
+    def call(*args, **kwargs):
+        try:
+            return ours(*args, **kwargs)
+        except L.PointSeaError as e:
+            if e.code != L.PS_ERR_UNSUPPORTED:
+                raise
+            return reference(*args, **kwargs)
+
+    call.__name__ = getattr(ours, "__name__", "call")
+    call.__doc__ = ours.__doc__
+    call.pointsea_kernel, call.reference = ours, reference
+    return call
+
+
 def patch_model_utils(module):
     """Rebind the call-site functions inside an imported reference `models.model_utils` (or
     `models_PointSea.model_utils`).  Classes defined there (PointNet_SA_Module_KNN, EdgeConv users) look the
-    names up in the module globals at call time, so no reference source changes."""
-    module.query_knn = pu.query_knn
-    module.fps_subsample = pu.fps_subsample
-    module.query_knn_point = query_knn_point
-    module.index_points = index_points
-    module.group_local = group_local
-    module.sample_and_group_knn = sample_and_group_knn
+    names up in the module globals at call time, so no reference source changes.  Shapes the kernels do not cover
+    (PS_ERR_UNSUPPORTED) are answered by the module's own original functions."""
+    if getattr(module, "_pointsea_patched", False):
+        return module
+    for name, ours in (("query_knn", pu.query_knn), ("fps_subsample", pu.fps_subsample), ("query_knn_point", query_knn_point),
+                       ("index_points", index_points), ("group_local", group_local), ("sample_and_group_knn", sample_and_group_knn)):
+        setattr(module, name, _with_reference_fallback(ours, getattr(module, name, None)))
     if hasattr(module, "EdgeConv"):
-        module.EdgeConv.forward = EdgeConv.forward
+        module.EdgeConv.forward = _with_reference_fallback(EdgeConv.forward, module.EdgeConv.forward)
+    module._pointsea_patched = True
     return module

@@ -261,8 +261,32 @@ def test_patch_model_utils_rebinds_names():
     m = types.ModuleType("fake_model_utils")
     m.EdgeConv = type("EdgeConv", (torch.nn.Module,), {})
     ps.patch_model_utils(m)
+    # names absent from the module are bound to the kernels directly; present ones keep the original as a fallback
     assert m.query_knn is pu.query_knn and m.sample_and_group_knn is ps.sample_and_group_knn
-    assert m.EdgeConv.forward is ps.EdgeConv.forward
+
+
+def test_patched_call_sites_fall_back_to_the_reference_expression_when_unsupported():
+    """a patched model must not crash on shapes the reference accepts but the kernels do not cover
+    (here k = 40 > 32).  PS_ERR_UNSUPPORTED routes the call to the module's own original function; other errors raise."""
+    import types
+    from oracle import oracle as O
+    m = types.ModuleType("fake_model_utils")
+    calls = []
+
+    def ref_query_knn_point(k, xyz, new_xyz):
+        calls.append(k)
+        return O.torch_query_knn_point(k, xyz, new_xyz)
+
+    m.query_knn_point = ref_query_knn_point
+    ps.patch_model_utils(m)
+    g = torch.Generator().manual_seed(3)
+    x = make_cloud(g, 2, 300).cuda()
+    got = m.query_knn_point(8, x, x)             # covered: our kernel, the reference function is not called
+    assert calls == [] and torch.equal(got.long(), O.torch_query_knn_point(8, x, x).long())
+    got = m.query_knn_point(40, x, x)            # k > 32: the reference's torch expression answers
+    assert calls == [40] and got.shape == (2, 300, 40)
+    with pytest.raises(ps.PointSeaError):        # anything else still fails loudly
+        m.query_knn_point(8, x.cpu(), x.cpu())
 
 
 # ---------------------------------------------------------------- hub sources in the grouping backward

@@ -523,6 +523,29 @@ def test_repeatability_as_a_race_guard():
                 assert torch.equal(o, r), f"output {k} changed on repetition {it}"
 
 
+@pytest.mark.parametrize("cluster,threads,exchange", [(c, t, e) for c in (1, 2, 4, 8, 16) for t in (128, 256)
+                                                     for e in (("async", "poll") if 1 < c <= 4 else ("async",))])
+def test_fps_exchange_race_guard_over_the_forced_plan_matrix(monkeypatch, cluster, threads, exchange):
+    """Every exchange protocol of the FPS kernel (single CTA, st.async + mbarrier all-to-all, the two-level variant for
+    8 / 16 CTAs, and the polling variant on plain remote stores), at both thread counts: 12 back-to-back runs on two
+    streams with duplicates (ties on every iteration) must equal the oracle bit for bit, every time."""
+    monkeypatch.setenv("PS_FPS_CLUSTER", str(cluster))
+    monkeypatch.setenv("PS_FPS_THREADS", str(threads))
+    if exchange == "poll":
+        monkeypatch.setenv("PS_FPS_EXCHANGE", "poll")
+    N = {1: 2048, 2: 4096, 4: 8192, 8: 16384, 16: 16384}[cluster]
+    g = torch.Generator().manual_seed(100 + cluster + threads)
+    x = make_cloud(g, 3, N, dup=N // 4, near_origin=5)
+    want = O.fps(x.numpy(), 200)
+    xc = x.to(DEV)
+    streams = [torch.cuda.Stream(), torch.cuda.Stream()]
+    for it in range(12):
+        with torch.cuda.stream(streams[it & 1]):
+            got = ps.furthest_point_sample(xc, 200)
+        streams[it & 1].synchronize()
+        assert np.array_equal(got.cpu().numpy(), want), f"cluster={cluster} threads={threads} {exchange}: run {it} differs"
+
+
 def test_fused_fps_subsample_matches_unfused_call_site():
     """fps_subsample (models/model_utils.py:489-499): one kernel vs FPS + gather + transposes,
     forward values and the gather gradient."""

@@ -20,7 +20,8 @@ for k, v in seq:
     a[1] += v
 tot = sum(v for _, v in seq)
 with open(f"profiles/launches_{tag}_summary.txt", "w") as f:
-    f.write("ncu --metrics gpu__time_duration.sum --clock-control none -c 900 python bench.py --steps 3 --warmup 3 --no-cpu\n")
+    f.write("ncu --metrics gpu__time_duration.sum --clock-control none -c 2000 python bench.py --steps 3 --warmup 3 --no-cpu --no-ref-cuda --repeats 1\n"
+            if tag != "r1" else "ncu --metrics gpu__time_duration.sum --clock-control none -c 900 python bench.py --steps 3 --warmup 3 --no-cpu\n")
     f.write("(cold-cache, serialised launches: compare SHARES, not absolutes)  total %.1f us over %d launches\n\n" % (tot, len(seq)))
     f.write("%8s %10s %9s %7s  kernel\n" % ("count", "sum_us", "avg_us", "share"))
     for k, (c, v) in sorted(agg.items(), key=lambda kv: -kv[1][1]):
@@ -58,6 +59,6 @@ for r in rows[2:]:
         line.append(f"{n}={v}")
     out.append("  ".join(line))
 open(f"profiles/ncu_full_{tag}_table.txt", "w").write(
-    "ncu --set full --clock-control none --import-source on -k regex:... -c 16 python tools/prof_target.py all 2\n"
+    "ncu --set full --clock-control none --import-source on -k regex:... -c 20 python tools/prof_target.py all 2\n"
     "one line per captured launch (B200; C1 Chamfer, C2 FPS, C3 kNN / group fwd / group bwd shapes; cold-cache replays)\n" + "\n".join(out) + "\n")
 print("\n".join(out))
