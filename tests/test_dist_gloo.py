@@ -154,11 +154,16 @@ def _toy_loss(fn_name, w, partial, gt, **kw):
     return D.get_loss_PM_sharded((Pc, P1, P2), partial, gt, sqrt=False, **kw)[0]
 
 
-def _patch_cpu_ops():
+def _patch_cpu_ops(monkeypatch=None):
+    """In a worker process: plain assignment.  In the pytest process: through `monkeypatch`, so later tests see the real ops."""
     import svdformer_pointsea_b200.chamfer as C
     import svdformer_pointsea_b200.pointnet2_utils as P
-    C.chamfer_3DFunction = _TorchChamfer
-    P.fps_subsample = _cpu_fps_subsample
+    if monkeypatch is None:
+        C.chamfer_3DFunction = _TorchChamfer
+        P.fps_subsample = _cpu_fps_subsample
+    else:
+        monkeypatch.setattr(C, "chamfer_3DFunction", _TorchChamfer)
+        monkeypatch.setattr(P, "fps_subsample", _cpu_fps_subsample)
 
 
 def _grad_worker(rank, world, port, B, q):
@@ -183,7 +188,7 @@ def _grad_worker(rank, world, port, B, q):
     dist.destroy_process_group()
 
 
-def test_two_rank_gradients_match_the_single_process_gradient():
+def test_two_rank_gradients_match_the_single_process_gradient(monkeypatch):
     B, world = 5, 2
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
@@ -192,7 +197,7 @@ def test_two_rank_gradients_match_the_single_process_gradient():
     [p.start() for p in procs]
     res = sorted((q.get(timeout=180) for _ in range(world)), key=lambda t: t[0])
     [p.join(timeout=60) for p in procs]
-    _patch_cpu_ops()
+    _patch_cpu_ops(monkeypatch)
     for fn in ("get_loss", "get_loss_PM"):
         partial, gt, w = _toy_batch(B)
         w = w.double().requires_grad_(True)
@@ -206,9 +211,9 @@ def test_two_rank_gradients_match_the_single_process_gradient():
                 assert np.allclose(got_grad, w.grad.numpy(), rtol=1e-5, atol=1e-8), (fn, mode)
 
 
-def test_get_loss_pm_matches_the_reference_expression():
+def test_get_loss_pm_matches_the_reference_expression(monkeypatch):
     """get_loss_PM_sharded without a process group == utils/loss_utils.get_loss_PM (:60-85) written out in torch."""
-    _patch_cpu_ops()
+    _patch_cpu_ops(monkeypatch)
     import svdformer_pointsea_b200.dist as D
     partial, gt, w = _toy_batch(3)
     Pc, P1, P2 = gt[:, :16] @ w, gt[:, :32] @ w, gt @ w
