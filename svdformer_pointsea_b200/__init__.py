@@ -12,7 +12,7 @@ Public surface = the reference's op boundary:
 losses run unchanged.
 """
 from ._lib import PointSeaError, LIB_PATH, load as load_library  # noqa: F401
-from .chamfer import chamfer_3DDist, chamfer_3DFunction, chamfer_forward, chamfer_backward, chamfer_sums, chamfer_host, chamfer_host_step, ChamferStep  # noqa: F401
+from .chamfer import chamfer_3DDist, chamfer_3DFunction, chamfer_forward, chamfer_backward, chamfer_sums, chamfer_host, chamfer_host_async, HostStep, chamfer_host_step, ChamferStep  # noqa: F401
 from .pointnet2_utils import (  # noqa: F401
     furthest_point_sample, gather_operation, grouping_operation, ball_query, three_nn, three_interpolate,
     FurthestPointSampling, GatherOperation, GroupingOperation, BallQuery, ThreeNN, ThreeInterpolate,

@@ -25,6 +25,8 @@ _SIGNATURES = {
     "ps_chamfer_bwd": [_P, _P, _P, _P, _P, _P, _P, _P, _c_int, _c_int, _c_int, _c_int, _P],
     "ps_chamfer_host": [_P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _c_int, _c_int, _c_int, _c_int, _c_int, _P],
     "ps_chamfer_host_full": [_P] * 12 + [_c_int, _c_int, _c_int, _c_int, _c_int, _P],
+    "ps_chamfer_host_submit": [_P] * 12 + [_c_int, _c_int, _c_int, _c_int, _c_int, _P, ctypes.POINTER(ctypes.c_longlong)],
+    "ps_chamfer_host_wait": [ctypes.c_longlong, _c_int, _P, _c_int, _c_int],
     "ps_chamfer_host_step": [_P, _P, _P, _P, _P, _P, _P, _c_int, _c_int, _c_int, _c_int, _c_int, _P],
     "ps_chamfer_fwd_sums": [_P, _P, _P, _P, _P, _P, _P, _c_int, _c_int, _c_int, _c_int, _P],
     "ps_chamfer_step": [_P] * 13 + [_c_int, _c_int, _c_int, _c_int, _P],

@@ -6,6 +6,8 @@ Differences that are deliberate: outputs are allocated on the device
 (the reference allocates on the CPU and copies, :33-42), work is enqueued on the caller's
 current stream (the reference uses the legacy default stream), errors raise.
 """
+import ctypes
+
 import torch
 from torch import nn
 from torch.autograd import Function
@@ -157,6 +159,43 @@ def _require_host(t, name, dtype, shape):
     return t
 
 
+def _host_args(who, xyz1, xyz2, graddist1, graddist2, out, device, sums_out, comm):
+    """Shared validation of the host-buffer calls: returns (B, N, M, device index, out list, gradient pointers)."""
+    if xyz1.dim() != 3 or xyz2.dim() != 3 or xyz1.size(2) != 3 or xyz2.size(2) != 3 or xyz1.size(0) != xyz2.size(0):
+        raise L.PointSeaError(f"chamfer expects (B,N,3) and (B,M,3), got {tuple(xyz1.shape)} {tuple(xyz2.shape)}")
+    B, N, _ = xyz1.shape
+    M = xyz2.size(1)
+    _require_host(xyz1, "xyz1", torch.float32, (B, N, 3))
+    _require_host(xyz2, "xyz2", torch.float32, (B, M, 3))
+    with_bwd = graddist1 is not None or graddist2 is not None
+    if with_bwd:
+        if graddist1 is None or graddist2 is None:
+            raise L.PointSeaError(f"{who}: backward needs both graddist1 and graddist2")
+        _require_host(graddist1, "graddist1", torch.float32, (B, N))
+        _require_host(graddist2, "graddist2", torch.float32, (B, M))
+    if not torch.cuda.is_available():
+        raise L.PointSeaError(f"{who} needs a CUDA device (there is no CPU implementation)")
+    index = torch.cuda.current_device() if device is None else torch.device(device).index
+    L._check_device(index)
+    if out is None:
+        out = [torch.empty(B, N, dtype=torch.float32).pin_memory(), torch.empty(B, M, dtype=torch.float32).pin_memory(),
+               torch.empty(B, N, dtype=torch.int32).pin_memory(), torch.empty(B, M, dtype=torch.int32).pin_memory()]
+        if with_bwd:
+            out += [torch.empty(B, N, 3, dtype=torch.float32).pin_memory(), torch.empty(B, M, 3, dtype=torch.float32).pin_memory()]
+    shapes = [((B, N), torch.float32), ((B, M), torch.float32), ((B, N), torch.int32), ((B, M), torch.int32),
+              ((B, N, 3), torch.float32), ((B, M, 3), torch.float32)]
+    if len(out) != (6 if with_bwd else 4):
+        raise L.PointSeaError(f"{who}: `out` must hold {6 if with_bwd else 4} tensors")
+    for t, (shape, dt), nm in zip(out, shapes, ("dist1", "dist2", "idx1", "idx2", "gradxyz1", "gradxyz2")):
+        _require_host(t, nm, dt, shape)
+    gp = [L.ptr(graddist1), L.ptr(graddist2), L.ptr(out[4]), L.ptr(out[5])] if with_bwd else [None] * 4
+    if sums_out is not None or comm is not None:
+        if sums_out is None:
+            raise L.PointSeaError(f"{who}: `comm` needs `sums_out`")
+        _require_host(sums_out, "sums_out", torch.float64, (6,))
+    return B, N, M, index, out, gp
+
+
 def chamfer_host(xyz1, xyz2, graddist1=None, graddist2=None, out=None, chunk=0, device=None, blocking=True, sums_out=None,
                  comm=None):
     """Chamfer forward (+ backward when graddist1/2 are given) on HOST tensors, pipelined through the GPU.
@@ -170,38 +209,8 @@ def chamfer_host(xyz1, xyz2, graddist1=None, graddist2=None, out=None, chunk=0, 
     `sums_out`: a pinned (6,) float64 CPU tensor that also receives the loss sums of `chamfer_sums`; with `comm` (a
     `dist.PeerComm`) they are the sums over all ranks' shards, exchanged by a kernel inside the same graph.
     """
-    if xyz1.dim() != 3 or xyz2.dim() != 3 or xyz1.size(2) != 3 or xyz2.size(2) != 3 or xyz1.size(0) != xyz2.size(0):
-        raise L.PointSeaError(f"chamfer expects (B,N,3) and (B,M,3), got {tuple(xyz1.shape)} {tuple(xyz2.shape)}")
-    B, N, _ = xyz1.shape
-    M = xyz2.size(1)
-    _require_host(xyz1, "xyz1", torch.float32, (B, N, 3))
-    _require_host(xyz2, "xyz2", torch.float32, (B, M, 3))
-    with_bwd = graddist1 is not None or graddist2 is not None
-    if with_bwd:
-        if graddist1 is None or graddist2 is None:
-            raise L.PointSeaError("chamfer_host: backward needs both graddist1 and graddist2")
-        _require_host(graddist1, "graddist1", torch.float32, (B, N))
-        _require_host(graddist2, "graddist2", torch.float32, (B, M))
-    if not torch.cuda.is_available():
-        raise L.PointSeaError("chamfer_host needs a CUDA device (there is no CPU implementation)")
-    index = torch.cuda.current_device() if device is None else torch.device(device).index
-    L._check_device(index)
-    if out is None:
-        out = [torch.empty(B, N, dtype=torch.float32).pin_memory(), torch.empty(B, M, dtype=torch.float32).pin_memory(),
-               torch.empty(B, N, dtype=torch.int32).pin_memory(), torch.empty(B, M, dtype=torch.int32).pin_memory()]
-        if with_bwd:
-            out += [torch.empty(B, N, 3, dtype=torch.float32).pin_memory(), torch.empty(B, M, 3, dtype=torch.float32).pin_memory()]
-    shapes = [((B, N), torch.float32), ((B, M), torch.float32), ((B, N), torch.int32), ((B, M), torch.int32),
-              ((B, N, 3), torch.float32), ((B, M, 3), torch.float32)]
-    if len(out) != (6 if with_bwd else 4):
-        raise L.PointSeaError(f"chamfer_host: `out` must hold {6 if with_bwd else 4} tensors")
-    for t, (shape, dt), nm in zip(out, shapes, ("dist1", "dist2", "idx1", "idx2", "gradxyz1", "gradxyz2")):
-        _require_host(t, nm, dt, shape)
-    gp = [L.ptr(graddist1), L.ptr(graddist2), L.ptr(out[4]), L.ptr(out[5])] if with_bwd else [None] * 4
-    if sums_out is not None or comm is not None:
-        if sums_out is None:
-            raise L.PointSeaError("chamfer_host: `comm` needs `sums_out`")
-        _require_host(sums_out, "sums_out", torch.float64, (6,))
+    B, N, M, index, out, gp = _host_args("chamfer_host", xyz1, xyz2, graddist1, graddist2, out, device, sums_out, comm)
+    if sums_out is not None:
         rc = L.load().ps_chamfer_host_full(L.ptr(xyz1), L.ptr(xyz2), L.ptr(out[0]), L.ptr(out[1]), L.ptr(out[2]), L.ptr(out[3]),
                                            gp[0], gp[1], gp[2], gp[3], L.ptr(sums_out), comm.handle if comm is not None else None,
                                            B, N, M, int(chunk), index, L.stream_ptr(index))
@@ -213,6 +222,52 @@ def chamfer_host(xyz1, xyz2, graddist1=None, graddist2=None, out=None, chunk=0, 
     if blocking:
         torch.cuda.current_stream(index).synchronize()
     return tuple(out)
+
+
+class HostStep(object):
+    """A step submitted by `chamfer_host_async`: `out` (and `sums`) are valid after `synchronize()` (host) or, for
+    work queued on a CUDA stream, after `wait()`.  Keeps its buffers alive until then."""
+
+    def __init__(self, ticket, index, out, sums, keep):
+        self.ticket, self.index, self.out, self.sums, self._keep = ticket, index, out, sums, keep
+
+    def wait(self, stream=None):
+        """Makes `stream` (default: the current stream of the step's device) wait for the step's last output byte."""
+        sp = L.stream_ptr(self.index) if stream is None else stream.cuda_stream
+        L.check(L.load().ps_chamfer_host_wait(self.ticket, self.index, sp, 1, 0), "ps_chamfer_host_wait")
+        return self
+
+    def synchronize(self):
+        """Blocks the calling thread until the step has written its last output byte; returns `out`."""
+        L.check(L.load().ps_chamfer_host_wait(self.ticket, self.index, None, 0, 1), "ps_chamfer_host_wait")
+        self._keep = None
+        return self.out
+
+
+def chamfer_host_async(xyz1, xyz2, graddist1=None, graddist2=None, out=None, chunk=0, device=None, sums_out=None, comm=None):
+    """`chamfer_host` for loops that keep more than one step in flight: returns a `HostStep` at once.
+
+    The step is ordered behind the current stream of `device` but runs on one of the library's two lanes, so the
+    upload and the kernels of the next submission overlap the download of this one (a loader that prefetches batch
+    i+1 while the results of batch i are read back):
+
+        pending = None
+        for batch in loader:                       # pinned host tensors, at least three buffer sets in rotation
+            step = chamfer_host_async(*batch, out=outs[i % 3], sums_out=sums[i % 3])
+            if pending is not None:
+                consume(pending.synchronize())     # results of the previous step, while this one runs
+            pending = step
+
+    Same arguments and results as `chamfer_host` (bit-identical); the buffers of a step must not be reused before
+    its `synchronize()` / `wait()`.  With `comm` the steps run one after the other."""
+    B, N, M, index, out, gp = _host_args("chamfer_host_async", xyz1, xyz2, graddist1, graddist2, out, device, sums_out, comm)
+    ticket = ctypes.c_longlong(0)
+    rc = L.load().ps_chamfer_host_submit(L.ptr(xyz1), L.ptr(xyz2), L.ptr(out[0]), L.ptr(out[1]), L.ptr(out[2]), L.ptr(out[3]),
+                                         gp[0], gp[1], gp[2], gp[3], L.ptr(sums_out) if sums_out is not None else None,
+                                         comm.handle if comm is not None else None, B, N, M, int(chunk), index,
+                                         L.stream_ptr(index), ctypes.byref(ticket))
+    L.check(rc, "ps_chamfer_host_submit")
+    return HostStep(ticket.value, index, tuple(out), sums_out, (xyz1, xyz2, graddist1, graddist2, out, sums_out))
 
 
 def chamfer_host_step(xyz1, xyz2, graddist1=None, graddist2=None, grad_out=None, sums_out=None, chunk=0, device=None,

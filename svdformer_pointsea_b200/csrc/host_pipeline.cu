@@ -19,6 +19,14 @@
 // keyed by the buffer addresses and sizes, and replayed with a single cudaGraphLaunch on the
 // caller's stream while the key repeats (steady-state training / evaluation loops with persistent
 // pinned buffers).  PS_HOST_GRAPH=0 disables the graphs.
+//
+// LANES: a call occupies the staging slots of its lane from its first upload to its last download, so calls on
+// one lane run back to back.  The asynchronous entry points (ps_chamfer_host_submit / ps_chamfer_host_wait)
+// alternate between LANES independent lanes, each with its own streams, slots, events and graph cache and its
+// own launch stream: step i+1 uploads and computes while step i still downloads (PCIe is full duplex, the two
+// copy engines and the SMs are three separate resources), which is what a loader that prefetches the next batch
+// does.  The stream-ordered entry points keep their contract ("complete when `stream` reaches the call") and
+// always use lane 0.
 #include "comm.cuh"
 #include "graph_cache.cuh"
 
@@ -30,13 +38,15 @@ namespace ps {
 
 constexpr int SLOTS = 3;
 constexpr int MAX_CHUNKS = 64;
+constexpr int LANES = 2;
 
-
-struct HostPipe {
-  std::mutex mu;
+struct Lane {
   GraphCache graphs;
-  cudaStream_t s_cap = nullptr;   // origin stream of the captures
-  cudaEvent_t ev_last = nullptr;  // end of the most recent call on this device (any caller stream)
+  cudaStream_t s_cap = nullptr;     // origin stream of the captures
+  cudaStream_t s_launch = nullptr;  // launch stream of the asynchronous entry points
+  cudaEvent_t ev_last = nullptr;    // end of the most recent call on this lane (any caller stream)
+  cudaEvent_t ev_sub = nullptr;     // the submitting stream's position at ps_chamfer_host_submit
+  unsigned long long calls = 0;
   bool ready = false;
   cudaStream_t s_in = nullptr, s_run = nullptr, s_bwd = nullptr, s_out = nullptr;
   cudaEvent_t ev_in[SLOTS], ev_gin[SLOTS], ev_fwd[SLOTS], ev_run[SLOTS], ev_out[SLOTS], ev_begin = nullptr, ev_end = nullptr;
@@ -45,12 +55,18 @@ struct HostPipe {
   double* d_sums = nullptr;  // 12 doubles: loss partial sums of the current call (ps_chamfer_host_step) [+ world-wide sums]
 };
 
+struct HostPipe {
+  std::mutex mu;
+  Lane lane[LANES];
+  unsigned long long submits = 0;
+};
+
 static HostPipe* pipe_for(int dev) {
   static HostPipe pipes[64];
   return (dev >= 0 && dev < 64) ? &pipes[dev] : nullptr;
 }
 
-static int pipe_init(HostPipe& hp, int hp_dev) {
+static int pipe_init(Lane& hp, int hp_dev) {
   if (hp.ready) return PS_OK;
   PS_CUDA(cudaStreamCreateWithFlags(&hp.s_in, cudaStreamNonBlocking));
   PS_CUDA(cudaStreamCreateWithFlags(&hp.s_run, cudaStreamNonBlocking));
@@ -64,7 +80,9 @@ static int pipe_init(HostPipe& hp, int hp_dev) {
     PS_CUDA(cudaEventCreateWithFlags(&hp.ev_out[i], cudaEventDisableTiming));
   }
   PS_CUDA(cudaStreamCreateWithFlags(&hp.s_cap, cudaStreamNonBlocking));
+  PS_CUDA(cudaStreamCreateWithFlags(&hp.s_launch, cudaStreamNonBlocking));
   PS_CUDA(cudaEventCreateWithFlags(&hp.ev_last, cudaEventDisableTiming));
+  PS_CUDA(cudaEventCreateWithFlags(&hp.ev_sub, cudaEventDisableTiming));
   PS_CUDA(cudaEventCreateWithFlags(&hp.ev_begin, cudaEventDisableTiming));
   PS_CUDA(cudaEventCreateWithFlags(&hp.ev_end, cudaEventDisableTiming));
   PS_CUDA(cudaMalloc(&hp.d_sums, 12 * sizeof(double)));
@@ -139,7 +157,7 @@ struct PipeArgs {
 // Enqueues the chunked three-stream pipeline behind `origin` and joins it back into `origin`.
 // Works both eagerly and under stream capture of `origin` (the side streams join the capture
 // through the event waits; every branch ends in s_out, which is joined back at the end).
-static int enqueue_pipeline(HostPipe& hp, const PipeArgs& a, cudaStream_t origin) {
+static int enqueue_pipeline(Lane& hp, const PipeArgs& a, cudaStream_t origin) {
 #define COPY(...) PS_CUDA(cudaMemcpyAsync(__VA_ARGS__))
   PS_CUDA(cudaEventRecord(hp.ev_begin, origin));
   PS_CUDA(cudaStreamWaitEvent(hp.s_in, hp.ev_begin, 0));
@@ -214,7 +232,7 @@ static int enqueue_pipeline(HostPipe& hp, const PipeArgs& a, cudaStream_t origin
   return PS_OK;
 }
 
-static void drop_graphs(HostPipe& hp) { hp.graphs.drop(); }
+static void drop_graphs(Lane& hp) { hp.graphs.drop(); }
 
 }  // namespace ps
 
@@ -223,16 +241,30 @@ using namespace ps;
 static int host_pipeline_call(const float* xyz1, const float* xyz2, float* dist1, float* dist2, int* idx1,
                               int* idx2, const float* graddist1, const float* graddist2, float* gradxyz1,
                               float* gradxyz2, float* dev_g1, float* dev_g2, double* h_sums, ps_comm* comm, int B, int N,
-                              int M, int chunk, int dev, void* stream_) {
+                              int M, int chunk, int dev, void* stream_, long long* ticket = nullptr) {
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
   const bool with_bwd = graddist1 != nullptr || graddist2 != nullptr;
   HostPipe* hpp = pipe_for(dev);
   PS_REQUIRE(hpp != nullptr, "ps_chamfer_host: bad device %d", dev);
   DeviceGuard guard(dev);
   if (!guard.ok) return set_error(PS_ERR_CUDA, "ps_chamfer_host: cannot select device %d", dev);
-  HostPipe& hp = *hpp;
-  std::lock_guard<std::mutex> lock(hp.mu);
+  std::lock_guard<std::mutex> lock(hpp->mu);
+  // stream-ordered call: lane 0 on the caller's stream.  Submission (ticket != null): the next lane in turn, on
+  // the lane's own launch stream, behind the submitting stream's current position.
+  const int li = ticket ? (int)(hpp->submits++ % LANES) : 0;
+  Lane& hp = hpp->lane[li];
   if (int rc = pipe_init(hp, dev)) return rc;
+  if (ticket) {
+    PS_CUDA(cudaEventRecord(hp.ev_sub, stream));
+    stream = hp.s_launch;
+    PS_CUDA(cudaStreamWaitEvent(stream, hp.ev_sub, 0));
+    // the exchange kernels of consecutive steps must run in the same order on every rank: with a communicator the
+    // lanes take turns (no overlap between steps)
+    if (comm)
+      for (int o = 0; o < LANES; o++)
+        if (o != li && hpp->lane[o].ready) PS_CUDA(cudaStreamWaitEvent(stream, hpp->lane[o].ev_last, 0));
+    *ticket = (long long)(((++hp.calls) << 8) | (unsigned)(li + 1));
+  }
 
   PipeArgs a;
   make_plan(B, chunk, a.sizes, &a.nchunks, &chunk);
@@ -377,8 +409,57 @@ extern "C" int ps_chamfer_host_stats(int dev, long long* hits, long long* update
   HostPipe* hp = pipe_for(dev);
   PS_REQUIRE(hp != nullptr, "ps_chamfer_host_stats: bad device %d", dev);
   std::lock_guard<std::mutex> lock(hp->mu);
-  if (hits) *hits = hp->graphs.hits;
-  if (updates) *updates = hp->graphs.updates;
-  if (instantiations) *instantiations = hp->graphs.instantiations;
+  long long h = 0, u = 0, n = 0;
+  for (const Lane& l : hp->lane) { h += l.graphs.hits; u += l.graphs.updates; n += l.graphs.instantiations; }
+  if (hits) *hits = h;
+  if (updates) *updates = u;
+  if (instantiations) *instantiations = n;
+  return PS_OK;
+}
+
+// Asynchronous form of ps_chamfer_host_full for loops that keep more than one step in flight (a loader that
+// prefetches the next batch while the previous results are read): the call is ordered behind the current position
+// of `stream`, runs on one of the library's lanes (in turn) and does NOT join `stream` again.  *ticket identifies
+// it for ps_chamfer_host_wait.  Consecutive submissions overlap: upload and kernels of step i+1 with the download of
+// step i.  With a communicator the steps run one after the other (the peers must see the exchanges in one order).
+extern "C" int ps_chamfer_host_submit(const float* xyz1, const float* xyz2, float* dist1, float* dist2, int* idx1, int* idx2,
+                                      const float* graddist1, const float* graddist2, float* gradxyz1, float* gradxyz2,
+                                      double* sums6, ps_comm* comm, int B, int N, int M, int chunk, int dev, void* stream,
+                                      long long* ticket) {
+  PS_REQUIRE(ticket != nullptr, "ps_chamfer_host_submit: null ticket");
+  *ticket = 0;
+  PS_REQUIRE(B >= 0 && N >= 0 && M >= 0, "ps_chamfer_host_submit: negative size");
+  if (B == 0 || (N == 0 && M == 0)) return PS_OK;
+  PS_REQUIRE(N > 0 && M > 0, "ps_chamfer_host_submit: both clouds need at least one point (N=%d, M=%d)", N, M);
+  PS_REQUIRE(xyz1 && xyz2 && dist1 && dist2 && idx1 && idx2, "ps_chamfer_host_submit: null pointer");
+  if (graddist1 != nullptr || graddist2 != nullptr)
+    PS_REQUIRE(graddist1 && graddist2 && gradxyz1 && gradxyz2, "ps_chamfer_host_submit: backward needs graddist1, graddist2, gradxyz1, gradxyz2");
+  if (comm) PS_REQUIRE(sums6 && comm->connected && comm->dev == dev, "ps_chamfer_host_submit: communicator needs sums6, a connection and device %d", dev);
+  cudaStreamCaptureStatus cs = cudaStreamCaptureStatusNone;
+  PS_REQUIRE(cudaStreamIsCapturing(static_cast<cudaStream_t>(stream), &cs) == cudaSuccess && cs == cudaStreamCaptureStatusNone,
+             "ps_chamfer_host_submit: `stream` is capturing (use ps_chamfer_host_full inside a capture)");
+  return host_pipeline_call(xyz1, xyz2, dist1, dist2, idx1, idx2, graddist1, graddist2, gradxyz1, gradxyz2, nullptr, nullptr,
+                            sums6, comm, B, N, M, chunk, dev, stream, ticket);
+}
+
+// Joins a submission: `stream` (when wait_stream != 0) continues only after the submitted step has written its last
+// output byte; block != 0 also blocks the calling host thread until then.  ticket 0 (an empty submission) is a no-op.
+// A lane is reused every LANES submissions: waiting for an old ticket waits for the lane's latest step, which is
+// later in the same stream order and therefore still sufficient.
+extern "C" int ps_chamfer_host_wait(long long ticket, int dev, void* stream, int wait_stream, int block) {
+  if (ticket == 0) return PS_OK;
+  const int li = (int)(ticket & 0xff) - 1;
+  HostPipe* hpp = pipe_for(dev);
+  PS_REQUIRE(hpp != nullptr && li >= 0 && li < LANES, "ps_chamfer_host_wait: bad ticket or device %d", dev);
+  DeviceGuard guard(dev);
+  if (!guard.ok) return set_error(PS_ERR_CUDA, "ps_chamfer_host_wait: cannot select device %d", dev);
+  cudaEvent_t ev;
+  {
+    std::lock_guard<std::mutex> lock(hpp->mu);
+    PS_REQUIRE(hpp->lane[li].ready, "ps_chamfer_host_wait: nothing was submitted on device %d", dev);
+    ev = hpp->lane[li].ev_last;
+  }
+  if (wait_stream) PS_CUDA(cudaStreamWaitEvent(static_cast<cudaStream_t>(stream), ev, 0));
+  if (block) PS_CUDA(cudaEventSynchronize(ev));
   return PS_OK;
 }

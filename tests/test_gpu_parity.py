@@ -94,6 +94,55 @@ def test_chamfer_host_pipeline_matches_device_entry_points_bitwise(B, N, M, chun
     assert torch.equal(out2[0], out[0]) and torch.equal(out2[3], out[3])
 
 
+def test_chamfer_host_async_keeps_several_steps_in_flight_bitwise():
+    """ps_chamfer_host_submit / ps_chamfer_host_wait: steps submitted back to back on the library's two lanes (step
+    i+1 uploads and computes while step i downloads) return exactly what the stream-ordered call returns, for
+    different clouds per step, rotating buffer sets, with and without the backward, and through both ways of
+    joining a step (host synchronize, stream wait)."""
+    g = torch.Generator().manual_seed(4242)
+    B, N, M, NSTEPS, NSETS = 6, 700, 1500, 9, 3
+    clouds = [(make_cloud(g, B, N).pin_memory(), make_cloud(g, B, M).pin_memory(),
+               torch.randn(B, N, generator=g).pin_memory(), torch.randn(B, M, generator=g).pin_memory()) for _ in range(NSTEPS)]
+    want, want_sums = [], []
+    for a, b, ga, gb in clouds:
+        ws = torch.empty(6, dtype=torch.float64).pin_memory()
+        want.append(tuple(x.clone() for x in ps.chamfer_host(a, b, ga, gb, sums_out=ws)))
+        want_sums.append(ws.clone())
+    outs = [[torch.empty(B, N).pin_memory(), torch.empty(B, M).pin_memory(), torch.empty(B, N, dtype=torch.int32).pin_memory(),
+             torch.empty(B, M, dtype=torch.int32).pin_memory(), torch.empty(B, N, 3).pin_memory(), torch.empty(B, M, 3).pin_memory()]
+            for _ in range(NSETS)]
+    sums = [torch.empty(6, dtype=torch.float64).pin_memory() for _ in range(NSETS)]
+    pending, done = None, 0
+    for i, (a, b, ga, gb) in enumerate(clouds):
+        step = ps.chamfer_host_async(a, b, ga, gb, out=outs[i % NSETS], sums_out=sums[i % NSETS])
+        assert step.ticket != 0
+        if pending is not None:
+            got = pending.synchronize()
+            for h, w in zip(got, want[i - 1]):
+                assert torch.equal(h, w)
+            assert torch.equal(pending.sums, want_sums[i - 1])
+            done += 1
+        pending = step
+    # the last one through a stream wait: a kernel queued behind it sees the finished host buffer
+    pending.wait()
+    torch.cuda.current_stream().synchronize()
+    for h, w in zip(pending.out, want[-1]):
+        assert torch.equal(h, w)
+    assert done == NSTEPS - 1
+    # forward only, library-allocated outputs, two in flight at once
+    s1 = ps.chamfer_host_async(clouds[0][0], clouds[0][1])
+    s2 = ps.chamfer_host_async(clouds[1][0], clouds[1][1])
+    for h, w in zip(s2.synchronize(), want[1][:4]):
+        assert torch.equal(h, w)
+    for h, w in zip(s1.synchronize(), want[0][:4]):
+        assert torch.equal(h, w)
+    # the stream-ordered call still works in between (lane 0) and empty batches are no-ops
+    again = ps.chamfer_host(clouds[2][0], clouds[2][1])
+    assert torch.equal(again[0], want[2][0])
+    e = ps.chamfer_host_async(torch.zeros(0, 8, 3), torch.zeros(0, 9, 3))
+    assert e.ticket == 0 and e.synchronize()[0].numel() == 0
+
+
 def test_chamfer_host_rejects_device_tensors_and_bad_shapes():
     a = torch.zeros(2, 8, 3, device=DEV)
     with pytest.raises(ps.PointSeaError):
