@@ -15,13 +15,13 @@ partial 2048 points vs ground truth 16384 points, fp32, synthetic `rand - 0.5` c
            `--repeats` times (each bracketed by barrier + synchronize, ranks brought into lockstep by 3 untimed
            replayed steps first); the MEDIAN block is reported, all blocks are listed.
   e2e    = the same step through the host-buffer API (chamfer_host_async -> ps_chamfer_host_submit / _wait): clouds
-           and upstream gradients come from PINNED HOST buffers (three sets in rotation, as a prefetching loader
-           would hand them out), and EVERY output goes back to the host — dist, idx, gradients and the loss sums
-           (world-wide at N > 1: the peer exchange is a kernel inside the same graph).  Two steps are in flight:
-           step i is submitted, then the host joins step i-1 and reads its loss.  `e2e.per_call` is one call at a
-           time (the latency of a single chamfer_host call); `e2e.loss_readback` leaves the gradients on the
-           device and reads back only the loss sums; `e2e.fresh_buffers` hands out a NEW address set every step
-           (the cached graph is retargeted in place).
+           and upstream gradients come from PINNED HOST buffers (depth + 1 sets in rotation, as a prefetching
+           loader would hand them out), and EVERY output goes back to the host — dist, idx, gradients and the loss
+           sums (world-wide at N > 1: the peer exchange is a kernel inside the same graph).  Three steps are in
+           flight (--e2e-depth): step i is submitted, then the host joins step i-2 and reads its loss.
+           `e2e.per_call` is one call at a time (the latency of a single chamfer_host call); `e2e.loss_readback`
+           leaves the gradients on the device and reads back only the loss sums; `e2e.fresh_buffers` hands out a
+           NEW address set every step (the cached graph is retargeted in place).
   ops    = the other hot-path ops at their BASELINE configs (C2 FPS+gather, C3 kNN+group, ball query, 3-NN),
            each device-timed, each next to the REFERENCE'S OWN CUDA KERNEL (oracle/_ref, compiled unmodified
            for sm_100a; baseline leg only, never on the product path) timed in the same run: `ref_cuda_ms`,
@@ -240,7 +240,7 @@ def run_ours(args):
     g = torch.Generator().manual_seed(1234 + 1 + rank)
     NSETS = 3  # host-buffer sets handed out in rotation by the e2e loops
     h_sets = [tuple(t.pin_memory() for t in (make_cloud(g, B, N), make_cloud(g, B, M), torch.randn(B, N, generator=g),
-                                             torch.randn(B, M, generator=g))) for _ in range(NSETS)]
+                                             torch.randn(B, M, generator=g))) for _ in range(NSETS + 1)]
     h_x1, h_x2, h_gd1, h_gd2 = h_sets[0]
     x1, x2, gd1, gd2 = (t.to(dev) for t in (h_x1, h_x2, h_gd1, h_gd2))
     flush_buf = torch.empty(256 << 20, dtype=torch.uint8, device=dev)  # 256 MB > 126 MB L2
@@ -377,41 +377,54 @@ def run_ours(args):
         for dst, src in zip(h_outs[i % NSETS], (d1, d2, i1, i2, g1, g2)):
             dst.copy_(src, non_blocking=True)
 
+    DEPTH = max(1, min(4, args.e2e_depth))  # steps in flight in the e2e loop
+    OSETS = DEPTH + 1                       # buffer sets: DEPTH in flight + the one the host is reading
+    while len(h_sets) < OSETS:
+        h_sets.append(tuple(t.clone().pin_memory() for t in h_sets[len(h_sets) % NSETS]))
+    while len(h_outs) < OSETS:
+        h_outs.append(host_outs())
+        h_sums.append(torch.empty(6, dtype=torch.float64).pin_memory())
+
     def e2e_overlapped(nsteps, warm):
-        """Depth-2 loop over chamfer_host_async: step i is submitted, then the host joins step i-1 (blocks until its
-        last output byte is in host memory) and reads its loss — the upload and kernels of step i overlap the
-        download of step i-1.  Device time of the whole block (CUDA events on the submitting stream: the first is
-        recorded before the first submission, the last after a stream-side join of the last step) and the host's
-        wall clock around the same block, in ms."""
+        """Loop over chamfer_host_async with DEPTH steps in flight: step i is submitted, then the host joins step
+        i-DEPTH+1 (blocks until its last output byte is in host memory) and reads its loss — upload and kernels of
+        the younger steps overlap the download of the older ones.  Returns the device time of the whole block (CUDA
+        events on the submitting stream: the first recorded before the first submission, the last after a
+        stream-side join of the last step), the host's wall clock around the same block (ms) and a checksum."""
+        import collections
         cur = torch.cuda.current_stream()
-        pending, seen = None, 0.0
-        for i in range(warm):
-            s = i % NSETS
+
+        def submit(i):
+            s = i % OSETS
             a, b, ga, gb = h_sets[s]
-            st = ps.chamfer_host_async(a, b, ga, gb, out=h_outs[s], chunk=args.e2e_chunk, sums_out=h_sums[s], comm=comm)
-            if pending is not None:
-                pending.synchronize()
-            pending = st
-        pending.synchronize()
+            return ps.chamfer_host_async(a, b, ga, gb, out=h_outs[s], chunk=args.e2e_chunk, sums_out=h_sums[s], comm=comm)
+
+        pending, seen = collections.deque(), 0.0
+        for i in range(warm):
+            pending.append(submit(i))
+            if len(pending) == DEPTH:
+                pending.popleft().synchronize()
+        while pending:
+            pending.popleft().synchronize()
         torch.cuda.synchronize()
         if world > 1:
             dist.barrier()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         t0 = time.perf_counter()
         e0.record(cur)
-        pending = None
         for i in range(warm, warm + nsteps):
-            s = i % NSETS
-            a, b, ga, gb = h_sets[s]
-            st = ps.chamfer_host_async(a, b, ga, gb, out=h_outs[s], chunk=args.e2e_chunk, sums_out=h_sums[s], comm=comm)
-            if pending is not None:
-                pending.synchronize()
-                seen += float(pending.sums[2])  # the step's result, read on the host
-            pending = st
-        pending.wait(cur)
+            pending.append(submit(i))
+            if len(pending) == DEPTH:
+                st = pending.popleft()
+                st.synchronize()
+                seen += float(st.sums[2])  # the step's result, read on the host
+        for st in pending:
+            st.wait(cur)
         e1.record(cur)
-        pending.synchronize()
-        seen += float(pending.sums[2])
+        while pending:
+            st = pending.popleft()
+            st.synchronize()
+            seen += float(st.sums[2])
         wall = (time.perf_counter() - t0) * 1e3
         e1.synchronize()
         return e0.elapsed_time(e1), wall, seen
@@ -422,7 +435,7 @@ def run_ours(args):
     call_ms = max_over_ranks(sum(full_ms), dev, world, dist) / args.steps
     ov_blocks, ov_wall = [], []
     for _ in range(3):
-        dms, wms, _seen = e2e_overlapped(args.steps, max(args.warmup, 3))
+        dms, wms, _seen = e2e_overlapped(args.steps, max(args.warmup, 3, 4 * OSETS))  # every (buffer set, lane) pair captured before the timed block
         ov_blocks.append(max_over_ranks(dms, dev, world, dist) / args.steps)
         ov_wall.append(max_over_ranks(wms, dev, world, dist) / args.steps)
     e2e_ms = statistics.median(ov_blocks)
@@ -433,16 +446,17 @@ def run_ours(args):
            "api": "svdformer_pointsea_b200.chamfer_host_async(..., sums_out, comm) -> ps_chamfer_host_submit / ps_chamfer_host_wait: pinned "
                   "host clouds + upstream gradients in; dist, idx, gradients AND the loss sums out (world-wide sums at N > 1: the "
                   "peer-memory exchange is a kernel inside the same graph); per step one CUDA graph launch (chunked H2D / kernels / "
-                  "D2H on four streams); TWO steps in flight: step i is submitted, then the host joins step i-1 and reads its loss, "
-                  "so upload + kernels of step i overlap the download of step i-1 (with a communicator the steps do not overlap)",
+                  "D2H on four streams); %d steps in flight: step i is submitted, then the host joins step i-%d and reads its loss, "
+                  "so upload + kernels of the younger steps overlap the download of the older ones (with a communicator the steps "
+                  "do not overlap)" % (DEPTH, DEPTH - 1),
            "timing": f"median of 3 blocks of {args.steps} steps; a block = CUDA events around all of its steps on the submitting stream "
-                     "(max over ranks); every input byte crosses PCIe inside its own step, three rotating pinned buffer sets, nothing "
+                     f"(max over ranks); every input byte crosses PCIe inside its own step, {OSETS} rotating pinned buffer sets, nothing "
                      "is reused across steps (no L2 flush needed)",
            "blocks_ms_per_step": [round(b, 4) for b in ov_blocks], "host_wall_ms_per_step": round(statistics.median(ov_wall), 4),
            "per_call": {"value": round(pairs_per_step * world / (call_ms * 1e-3) / 1e9, 2), "ms_per_step": round(call_ms, 4),
                         "note": "one step at a time through chamfer_host(..., blocking=False): CUDA events around each call, L2 flushed "
                                 "between calls; the latency of a single call (round-2 headline before the asynchronous pair existed)"},
-           "host_buffer_sets": NSETS, "chunk": args.e2e_chunk, "numa_bound_cpus": (len(numa_cpus) if numa_cpus else None),
+           "steps_in_flight": DEPTH, "host_buffer_sets": OSETS, "chunk": args.e2e_chunk, "numa_bound_cpus": (len(numa_cpus) if numa_cpus else None),
            "loss_readback": {"value": round(pairs_per_step * world / (loss_ms * 1e-3) / 1e9, 2), "ms_per_step": round(loss_ms, 4),
                              "d2h_bytes_per_step": 48,
                              "note": "chamfer_host_step: gradients stay in device buffers for the optimizer, only the six loss sums are read back"}}
@@ -889,6 +903,7 @@ def main():
     ap.add_argument("--repeats", type=int, default=7, help="how many times the K-step block is timed (median reported)")
     ap.add_argument("--scaling", default="weak", choices=["weak", "strong"])
     ap.add_argument("--workload", default="c5", choices=["c1", "c5", "c4loss"], help="--scaling strong: which fixed-size workload to split")
+    ap.add_argument("--e2e-depth", type=int, default=3, help="steps in flight in the e2e loop (1-4; 1 = one call at a time)")
     ap.add_argument("--e2e-chunk", type=int, default=0, help="clouds per pipeline chunk of the host-buffer call (0: library default)")
     ap.add_argument("--reduce", default="peer", choices=["peer", "nccl_graph", "pipelined", "inline"],
                     help="how the per-step reduction of the loss sums runs when N > 1 (A/B); default: peer-memory exchange inside the step's graph")

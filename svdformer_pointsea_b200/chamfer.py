@@ -247,16 +247,15 @@ class HostStep(object):
 def chamfer_host_async(xyz1, xyz2, graddist1=None, graddist2=None, out=None, chunk=0, device=None, sums_out=None, comm=None):
     """`chamfer_host` for loops that keep more than one step in flight: returns a `HostStep` at once.
 
-    The step is ordered behind the current stream of `device` but runs on one of the library's two lanes, so the
-    upload and the kernels of the next submission overlap the download of this one (a loader that prefetches batch
-    i+1 while the results of batch i are read back):
+    The step is ordered behind the current stream of `device` but runs on one of the library's four lanes, so the
+    upload and the kernels of the next submissions overlap the download of this one (a loader that prefetches the
+    next batches while the results of an earlier one are read back; up to four steps in flight):
 
-        pending = None
-        for batch in loader:                       # pinned host tensors, at least three buffer sets in rotation
-            step = chamfer_host_async(*batch, out=outs[i % 3], sums_out=sums[i % 3])
-            if pending is not None:
-                consume(pending.synchronize())     # results of the previous step, while this one runs
-            pending = step
+        pending = collections.deque()
+        for i, batch in enumerate(loader):         # pinned host tensors, DEPTH + 1 buffer sets in rotation
+            pending.append(chamfer_host_async(*batch, out=outs[i % (DEPTH + 1)], sums_out=sums[i % (DEPTH + 1)]))
+            if len(pending) == DEPTH:              # DEPTH = 3: the loop runs at the speed of the busiest resource
+                consume(pending.popleft().synchronize())
 
     Same arguments and results as `chamfer_host` (bit-identical); the buffers of a step must not be reused before
     its `synchronize()` / `wait()`.  With `comm` the steps run one after the other."""

@@ -548,248 +548,14 @@ __global__ void __launch_bounds__(CS_THREADS, 2) chamfer_sym2_kernel(const SymPa
 }
 
 // ------------------------------------------------------------------------------------------------
-// chamfer_sym2_kernel with the column fold's routing and merge taken off the ALU pipe ("column store" variant).
-//
-// SASS of chamfer_sym2_kernel<8,4,2>, one 4-target step: 96 FP32-pipe instructions (192 pipe cycles) against 68
-// ALU-pipe instructions (half rate: 136 cycles) — 32 FMNMX3 that cannot go away, 12 for the argmin bookkeeping,
-// and 24 for the column fold: per target REDUX + MOV + ISETP + VOTE, then compare/select pairs that route the warp
-// minimum and the ballot to the lane that owns the target, and every 32 targets a 64-bit shared-memory atomicMin
-// (an ATOMS.CAST.SPIN loop) that merges the eight warps.  Here the routing and the merge are gone: the lanes that
-// HOLD the warp minimum store it themselves (the ISETP that feeds the ballot predicates the store; equal values, so
-// the race is benign) and lane 0 stores the four ballots with one 128-bit store, into per-warp rows
-// cmin[warp][target] / cbal[warp][target].  The column pass after the tile folds the eight rows per target (lowest
-// warp among equal minima, lowest lane of its ballot: the same thread the atomicMin key selected).  The 4 MOVs per
-// step that materialised +inf for the fold's first FMNMX3 are gone as well (2-input minimum first).
-// B tiles are 1024 targets (the two 32 KB row arrays replace the 16 KB key array; 100 KB per CTA, two CTAs per SM).
-// GRAN = steps per argmin bookkeeping group (2, 4 or 8): the final re-evaluation looks at 4*GRAN candidates per A
-// point — the larger groups pay off when a unit scans many targets.
-constexpr int C3_TILE = 1024;
-constexpr int C3_PAD = 8;  // the pipelined scan reads one step past the last staged target
-
-// p = (b == m); returns ballot(p); the holders of the minimum store it
-__device__ __forceinline__ unsigned col_vote_store(unsigned b, unsigned m, unsigned addr) {
-  unsigned l;
-  // no "memory" clobber on purpose (see st_shared_if_less below): the rows are only read after a __syncthreads()
-  asm volatile("{\n\t.reg .pred p;\n\tsetp.eq.u32 p, %1, %2;\n\tvote.sync.ballot.b32 %0, p, 0xffffffff;\n\t@p st.shared.u32 [%3], %1;\n\t}"
-               : "=r"(l) : "r"(b), "r"(m), "r"(addr));
-  return l;
-}
-__device__ __forceinline__ void st_shared_v4_if(unsigned flag, unsigned addr, unsigned a, unsigned b, unsigned c, unsigned d) {
-  asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.u32 p, %0, 0;\n\t@p st.shared.v4.u32 [%1], {%2, %3, %4, %5};\n\t}" ::"r"(flag), "r"(addr), "r"(a), "r"(b), "r"(c), "r"(d));
-}
-
-template <int UNROLL, int GRAN>
-__global__ void __launch_bounds__(CS_THREADS, 2) chamfer_sym3_kernel(const SymParams p) {
-  static_assert((GRAN == 2 || GRAN == 4 || GRAN == 8) && UNROLL % GRAN == 0 && 8 % UNROLL == 0, "bookkeeping groups must be whole inside the unrolled body");
-  constexpr int Q = 8;
-  constexpr int TA = CS_THREADS * Q;
-  constexpr int NW = CS_THREADS / 32;
-  extern __shared__ __align__(16) unsigned char smem_raw[];
-  float* sx = reinterpret_cast<float*>(smem_raw);
-  float* sy = sx + C3_TILE + C3_PAD;
-  float* sz = sy + C3_TILE + C3_PAD;
-  unsigned* cmin = reinterpret_cast<unsigned*>(sz + C3_TILE + C3_PAD);  // [NW][C3_TILE] warp minimum (fp32 bits) per target
-  unsigned* cbal = cmin + NW * C3_TILE;                                  // [NW][C3_TILE] lanes holding it
-  float* ax = reinterpret_cast<float*>(cbal + NW * C3_TILE);
-  float* ay = ax + TA;
-  float* az = ay + TA;
-
-  int b, at, t0, t1;
-  if (!sym_decode_unit(p, b, at, t0, t1)) return;
-  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const int na = p.na, nb = p.nb;
-  const float INF = __int_as_float(0x7f800000);
-  const unsigned cmin_w = smem_u32(cmin + warp * C3_TILE), cbal_w = smem_u32(cbal + warp * C3_TILE);
-  const unsigned lane0 = lane == 0 ? 1u : 0u;
-
-  u64 nqx[Q], nqy[Q], nqz[Q];
-  float best[Q];
-  int cstep[Q];
-  const float* abase = p.a + (size_t)b * na * 3;
-#pragma unroll
-  for (int q = 0; q < Q; q++) {
-    const int i = at * TA + tid * Q + q;
-    const bool valid = i < na;
-    const float x = valid ? __ldg(abase + (size_t)i * 3 + 0) : INF;  // see chamfer_sym_kernel: +inf slots never win
-    const float y = valid ? __ldg(abase + (size_t)i * 3 + 1) : 0.f;
-    const float z = valid ? __ldg(abase + (size_t)i * 3 + 2) : 0.f;
-    ax[tid * Q + q] = x; ay[tid * Q + q] = y; az[tid * Q + q] = z;
-    nqx[q] = pack2(-x, -x); nqy[q] = pack2(-y, -y); nqz[q] = pack2(-z, -z);
-    best[q] = INF;
-    cstep[q] = 0;
-  }
-  const float* bcloud = p.b + (size_t)b * nb * 3;
-
-  for (int ts = t0; ts < t1; ts += C3_TILE) {
-    const int cnt = min(C3_TILE, t1 - ts);
-    const int cnt_pad = (cnt + 31) / 32 * 32;  // whole 32-point blocks: the padding sits at +inf and never wins
-    const float* tb = bcloud + (size_t)ts * 3;
-    const bool vec = (reinterpret_cast<uintptr_t>(tb) & 15) == 0;
-    __syncthreads();  // previous tile (and its column pass) fully consumed
-    for (int g = tid; g < cnt_pad / 4; g += CS_THREADS) {
-      float4 X, Y, Z;
-      if (vec && g * 4 + 4 <= cnt) {
-        const float4 a = __ldg(reinterpret_cast<const float4*>(tb + g * 12));
-        const float4 bb = __ldg(reinterpret_cast<const float4*>(tb + g * 12 + 4));
-        const float4 c = __ldg(reinterpret_cast<const float4*>(tb + g * 12 + 8));
-        X = make_float4(a.x, a.w, bb.z, c.y);
-        Y = make_float4(a.y, bb.x, bb.w, c.z);
-        Z = make_float4(a.z, bb.y, c.x, c.w);
-      } else {
-        float xs[4], ys[4], zs[4];
-#pragma unroll
-        for (int e = 0; e < 4; e++) {
-          const int pi = g * 4 + e;
-          const bool in = pi < cnt;
-          xs[e] = in ? __ldg(tb + pi * 3 + 0) : INF;
-          ys[e] = in ? __ldg(tb + pi * 3 + 1) : 0.f;
-          zs[e] = in ? __ldg(tb + pi * 3 + 2) : 0.f;
-        }
-        X = make_float4(xs[0], xs[1], xs[2], xs[3]);
-        Y = make_float4(ys[0], ys[1], ys[2], ys[3]);
-        Z = make_float4(zs[0], zs[1], zs[2], zs[3]);
-      }
-      *reinterpret_cast<float4*>(&sx[g * 4]) = X;
-      *reinterpret_cast<float4*>(&sy[g * 4]) = Y;
-      *reinterpret_cast<float4*>(&sz[g * 4]) = Z;
-    }
-    __syncthreads();
-
-    const int step0 = (ts - t0) / CS_STEP;
-    // pipeline prologue: distances of half A (q 0-3) for step 0
-    ulonglong2 X = *reinterpret_cast<const ulonglong2*>(&sx[0]);
-    ulonglong2 Y = *reinterpret_cast<const ulonglong2*>(&sy[0]);
-    ulonglong2 Z = *reinterpret_cast<const ulonglong2*>(&sz[0]);
-    u64 dA01[4], dA23[4], dB01[4], dB23[4];
-#pragma unroll
-    for (int i = 0; i < 4; i++) {
-      dA01[i] = dist2x2(X.x, Y.x, Z.x, nqx[i], nqy[i], nqz[i]);
-      dA23[i] = dist2x2(X.y, Y.y, Z.y, nqx[i], nqy[i], nqz[i]);
-    }
-    float old[Q];  // the running minima before the current group of GRAN steps
-#pragma unroll
-    for (int q = 0; q < Q; q++) old[q] = INF;
-    for (int j32 = 0; j32 < cnt_pad; j32 += 32) {
-#pragma unroll UNROLL
-      for (int s8 = 0; s8 < 8; s8++) {
-        const int step = step0 + j32 / CS_STEP + s8;
-        float c0, c1, c2, c3;
-        // ---- half 1: distances of q 4-7 at this step  ||  minima of q 0-3 at this step ----------------
-#pragma unroll
-        for (int i = 0; i < 4; i++) {
-          dB01[i] = dist2x2(X.x, Y.x, Z.x, nqx[4 + i], nqy[4 + i], nqz[4 + i]);
-          dB23[i] = dist2x2(X.y, Y.y, Z.y, nqx[4 + i], nqy[4 + i], nqz[4 + i]);
-          float nbv = min3(best[i], lo2(dA01[i]), hi2(dA01[i]));
-          nbv = min3(nbv, lo2(dA23[i]), hi2(dA23[i]));
-          if ((s8 % GRAN) == GRAN - 1) { if (nbv < old[i]) cstep[i] = step / GRAN; }
-          else if ((s8 % GRAN) == 0) old[i] = best[i];
-          best[i] = nbv;
-          if (i == 1) {
-            c0 = fminf(lo2(dA01[0]), lo2(dA01[1]));
-            c1 = fminf(hi2(dA01[0]), hi2(dA01[1]));
-            c2 = fminf(lo2(dA23[0]), lo2(dA23[1]));
-            c3 = fminf(hi2(dA23[0]), hi2(dA23[1]));
-          }
-          if (i == 3) {
-            c0 = min3(c0, lo2(dA01[2]), lo2(dA01[3]));
-            c1 = min3(c1, hi2(dA01[2]), hi2(dA01[3]));
-            c2 = min3(c2, lo2(dA23[2]), lo2(dA23[3]));
-            c3 = min3(c3, hi2(dA23[2]), hi2(dA23[3]));
-          }
-        }
-        // B points of the next step (past the tile's last step: the padding behind the arrays, never consumed)
-        const int jn = j32 + (s8 + 1) * CS_STEP;
-        X = *reinterpret_cast<const ulonglong2*>(&sx[jn]);
-        Y = *reinterpret_cast<const ulonglong2*>(&sy[jn]);
-        Z = *reinterpret_cast<const ulonglong2*>(&sz[jn]);
-        // ---- half 2: distances of q 0-3 at the next step  ||  minima of q 4-7 at this step -------------
-#pragma unroll
-        for (int i = 0; i < 4; i++) {
-          dA01[i] = dist2x2(X.x, Y.x, Z.x, nqx[i], nqy[i], nqz[i]);
-          dA23[i] = dist2x2(X.y, Y.y, Z.y, nqx[i], nqy[i], nqz[i]);
-          float nbv = min3(best[4 + i], lo2(dB01[i]), hi2(dB01[i]));
-          nbv = min3(nbv, lo2(dB23[i]), hi2(dB23[i]));
-          if ((s8 % GRAN) == GRAN - 1) { if (nbv < old[4 + i]) cstep[4 + i] = step / GRAN; }
-          else if ((s8 % GRAN) == 0) old[4 + i] = best[4 + i];
-          best[4 + i] = nbv;
-          if (i & 1) {
-            c0 = min3(c0, lo2(dB01[i - 1]), lo2(dB01[i]));
-            c1 = min3(c1, hi2(dB01[i - 1]), hi2(dB01[i]));
-            c2 = min3(c2, lo2(dB23[i - 1]), lo2(dB23[i]));
-            c3 = min3(c3, hi2(dB23[i - 1]), hi2(dB23[i]));
-          }
-        }
-        // ---- column fold of this step: warp minimum per B point, stored by its holders; ballots by lane 0 ----
-        const unsigned b0 = __float_as_uint(c0), b1 = __float_as_uint(c1), b2 = __float_as_uint(c2), b3 = __float_as_uint(c3);
-        const unsigned m0 = __reduce_min_sync(0xffffffffu, b0);
-        const unsigned m1 = __reduce_min_sync(0xffffffffu, b1);
-        const unsigned m2 = __reduce_min_sync(0xffffffffu, b2);
-        const unsigned m3 = __reduce_min_sync(0xffffffffu, b3);
-        const unsigned joff = (unsigned)(j32 + s8 * CS_STEP) * 4u;
-        const unsigned l0 = col_vote_store(b0, m0, cmin_w + joff);
-        const unsigned l1 = col_vote_store(b1, m1, cmin_w + joff + 4);
-        const unsigned l2 = col_vote_store(b2, m2, cmin_w + joff + 8);
-        const unsigned l3 = col_vote_store(b3, m3, cmin_w + joff + 12);
-        st_shared_v4_if(lane0, cbal_w + joff, l0, l1, l2, l3);
-      }
-    }
-    __syncthreads();  // the rows of all eight warps are complete
-
-    // ---- column side: fold the warps, exact index inside the recorded thread's Q points, global merge ----
-    for (int jj = tid; jj < cnt; jj += CS_THREADS) {
-      unsigned mbits = cmin[jj];
-      int bw = 0;
-#pragma unroll
-      for (int w = 1; w < NW; w++) {
-        const unsigned m = cmin[w * C3_TILE + jj];
-        if (m < mbits) { mbits = m; bw = w; }  // strict: the lowest warp among equal minima
-      }
-      const int tcand = bw * 32 + __ffs(cbal[bw * C3_TILE + jj]) - 1;
-      const float bx = sx[jj], by = sy[jj], bz = sz[jj];
-      int found = 0;
-#pragma unroll
-      for (int q = Q - 1; q >= 0; q--) {
-        const float d = dist2_ref(bx - ax[tcand * Q + q], by - ay[tcand * Q + q], bz - az[tcand * Q + q]);
-        if (__float_as_uint(d) == mbits) found = q;
-      }
-      const int ia = at * TA + tcand * Q + found;
-      atomicMin(&p.keys_b[(size_t)b * nb + ts + jj], ((u64)mbits << 32) | (unsigned)ia);
-    }
-  }
-
-  // ---- row side: first B point of the remembered group of GRAN steps that reproduces `best` -----------------
-  const int last_ts = t0 + ((t1 - t0 - 1) / C3_TILE) * C3_TILE;
-  constexpr int NC = CS_STEP * GRAN;
-#pragma unroll
-  for (int q = 0; q < Q; q++) {
-    const int i = at * TA + tid * Q + q;
-    const int base = t0 + cstep[q] * NC;
-    int found = 0;
-    if (base >= last_ts) {
-      const int off = base - last_ts;  // inside the staged tile (its padding sits at +inf)
-#pragma unroll
-      for (int e4 = NC / 4 - 1; e4 >= 0; e4--) {
-        const ulonglong2 Xc = *reinterpret_cast<const ulonglong2*>(&sx[off + e4 * 4]);
-        const ulonglong2 Yc = *reinterpret_cast<const ulonglong2*>(&sy[off + e4 * 4]);
-        const ulonglong2 Zc = *reinterpret_cast<const ulonglong2*>(&sz[off + e4 * 4]);
-        const u64 d01 = dist2x2(Xc.x, Yc.x, Zc.x, nqx[q], nqy[q], nqz[q]);
-        const u64 d23 = dist2x2(Xc.y, Yc.y, Zc.y, nqx[q], nqy[q], nqz[q]);
-        if (hi2(d23) == best[q]) found = e4 * 4 + 3;
-        if (lo2(d23) == best[q]) found = e4 * 4 + 2;
-        if (hi2(d01) == best[q]) found = e4 * 4 + 1;
-        if (lo2(d01) == best[q]) found = e4 * 4 + 0;
-      }
-    } else {
-      const float qx = -lo2(nqx[q]), qy = -lo2(nqy[q]), qz = -lo2(nqz[q]);
-      const float* tp = bcloud + (size_t)base * 3;
-      for (int e = NC - 1; e >= 0; e--)
-        if (dist2_ref(__ldg(tp + e * 3 + 0) - qx, __ldg(tp + e * 3 + 1) - qy, __ldg(tp + e * 3 + 2) - qz) == best[q]) found = e;
-    }
-    if (i >= na) continue;
-    atomicMin(&p.keys_a[(size_t)b * na + i], ((u64)__float_as_uint(best[q]) << 32) | (unsigned)(base + found));
-  }
-}
-
+// Measured and NOT kept (round 2, profiles/chamfer_lab_r2.jsonl variants 8-11): a "column store" version of the
+// pipelined kernel in which the holders of each warp minimum store it to per-warp shared-memory rows (predicated by
+// the ISETP that feeds the ballot) and lane 0 stores the four ballots with one 128-bit store, instead of routing
+// them to owner lanes (ISETP + 2 SEL per target) and merging the warps with a 64-bit shared atomicMin per 32
+// targets.  SASS per 4-target step: 171 -> 167 instructions, ALU pipe 68 -> 62 (53 with the argmin bookkeeping once
+// per 32 targets), +5 LSU.  Bit-identical, but SLOWER on every shape: C1 291 -> 297 us, 32 x 16384^2 2040 -> 2083 us;
+// with bookkeeping groups of 4 / 8 steps 318-324 / 406 us (the fully unrolled 20 KB loop body and the 16- / 32-candidate
+// re-evaluation cost more than the saved compares).  The scan is not bound by the ALU instruction count.
 // ------------------------------------------------------------------------------------------------
 // A-packed variant.  Same algorithm, other register layout: the two halves of every packed
 // operand are two DIFFERENT A points of the thread (a_2p, a_2p+1) and the streamed B point is
@@ -1017,16 +783,6 @@ static int launch_sym2(const SymParams& p, int grid, cudaStream_t stream) {
   return PS_OK;
 }
 
-template <int UNROLL, int GRAN>
-static int launch_sym3(const SymParams& p, int grid, cudaStream_t stream) {
-  const size_t smem = (size_t)3 * (C3_TILE + C3_PAD) * 4 + (size_t)2 * (CS_THREADS / 32) * C3_TILE * 4 + (size_t)3 * CS_THREADS * 8 * 4;
-  auto kern = chamfer_sym3_kernel<UNROLL, GRAN>;
-  PS_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  kern<<<grid, CS_THREADS, smem, stream>>>(p);
-  PS_LAUNCH_CHECK();
-  return PS_OK;
-}
-
 // Returns PS_OK when it handled the call, 1 when the shape is better served by the two-pass kernel.
 int chamfer_fwd_symmetric(const float* xyz1, const float* xyz2, float* dist1, float* dist2, int* idx1,
                           int* idx2, double* sums6, const ps_comm* comm, int B, int N, int M, int dev, cudaStream_t stream) {
@@ -1117,10 +873,6 @@ int chamfer_fwd_symmetric(const float* xyz1, const float* xyz2, float* dist1, fl
     else if (Q == 8 && variant == 5) rc = launch_sym2<2, 1>(p, grid, stream);
     else if (Q == 8 && variant == 6) rc = launch_sym2<4, 2>(p, grid, stream);
     else if (Q == 8 && variant == 7) rc = launch_sym2<2, 2>(p, grid, stream);
-    else if (Q == 8 && variant == 8) rc = launch_sym3<4, 2>(p, grid, stream);
-    else if (Q == 8 && variant == 9) rc = launch_sym3<4, 4>(p, grid, stream);
-    else if (Q == 8 && variant == 10) rc = launch_sym3<8, 8>(p, grid, stream);
-    else if (Q == 8 && variant == 11) rc = launch_sym3<8, 4>(p, grid, stream);
     else if (Q == 8) rc = launch_sym<8>(p, grid, stream);
     else if (Q == 4) rc = launch_sym<4>(p, grid, stream);
     else rc = launch_sym<2>(p, grid, stream);

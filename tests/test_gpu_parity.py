@@ -52,7 +52,8 @@ def test_chamfer_fwd_bwd_vs_oracle(B, N, M, dup):
     assert_close_rel(g2.cpu().numpy(), og2, what="gradxyz2")
 
 
-@pytest.mark.parametrize("sym,q", [("2", "16"), ("2", "8"), ("2", "4"), ("1", "8"), ("1", "4"), ("1", "2"), ("0", "8")])
+@pytest.mark.parametrize("sym,q", [("2", "16"), ("2", "8"), ("2", "4"), ("1", "8"), ("1", "4"), ("1", "2"), ("0", "8"),
+                                   ("6", "8"), ("3", "8"), ("7", "8")])
 @pytest.mark.parametrize("B,N,M,dup", [(2, 2048, 4096, 700), (3, 5000, 1300, 300), (1, 16384, 2048, 548),
                                        (2, 1024, 1024, 1000), (1, 2050, 257, 0), (1, 300, 9000, 100)])
 def test_chamfer_symmetric_and_two_pass_kernels_agree_with_oracle(B, N, M, dup, sym, q, monkeypatch):
@@ -64,6 +65,22 @@ def test_chamfer_symmetric_and_two_pass_kernels_agree_with_oracle(B, N, M, dup, 
     a, b = make_cloud(g, B, N, dup=min(dup, N - 1)), make_cloud(g, B, M, dup=min(dup, M - 1))
     n_shared = min(N, M) // 3
     b[:, :n_shared] = a[:, N - n_shared:]  # cross-cloud exact matches at different indices
+    d1, d2, i1, i2 = ps.chamfer_forward(a.to(DEV), b.to(DEV))
+    od1, od2, oi1, oi2 = O.chamfer_fwd(a.numpy(), b.numpy())
+    assert np.array_equal(i1.cpu().numpy(), oi1) and np.array_equal(i2.cpu().numpy(), oi2)
+    assert np.array_equal(d1.cpu().numpy(), od1) and np.array_equal(d2.cpu().numpy(), od2)
+
+
+@pytest.mark.parametrize("sym", ["1", "6", "3", "7"])
+@pytest.mark.parametrize("split", ["2304", "1100", "4608"])
+def test_chamfer_units_spanning_several_tiles(sym, split, monkeypatch):
+    """Units longer than one shared-memory tile (forced split length): the argmin group remembered by the scan may
+    lie in an earlier tile (re-evaluated from global memory), tiles end ragged, duplicates tie across tiles."""
+    monkeypatch.setenv("PS_CHAMFER_SYM", sym)
+    monkeypatch.setenv("PS_CHAMFER_SPLIT", split)
+    g = torch.Generator().manual_seed(77)
+    a, b = make_cloud(g, 2, 4096, dup=1500), make_cloud(g, 2, 4608, dup=3000)
+    b[:, 4000:4500] = a[:, 100:600]
     d1, d2, i1, i2 = ps.chamfer_forward(a.to(DEV), b.to(DEV))
     od1, od2, oi1, oi2 = O.chamfer_fwd(a.numpy(), b.numpy())
     assert np.array_equal(i1.cpu().numpy(), oi1) and np.array_equal(i2.cpu().numpy(), oi2)
@@ -118,17 +135,37 @@ def test_chamfer_host_async_keeps_several_steps_in_flight_bitwise():
         assert step.ticket != 0
         if pending is not None:
             got = pending.synchronize()
-            for h, w in zip(got, want[i - 1]):
+            for h, w in zip(got[:4], want[i - 1][:4]):
                 assert torch.equal(h, w)
+            for h, w in zip(got[4:], want[i - 1][4:]):  # the backward accumulates with atomics: order-dependent rounding
+                assert_close_rel(h.numpy(), w.numpy(), what="gradient (async)")
             assert torch.equal(pending.sums, want_sums[i - 1])
             done += 1
         pending = step
     # the last one through a stream wait: a kernel queued behind it sees the finished host buffer
     pending.wait()
     torch.cuda.current_stream().synchronize()
-    for h, w in zip(pending.out, want[-1]):
+    for h, w in zip(pending.out[:4], want[-1][:4]):
         assert torch.equal(h, w)
+    assert_close_rel(pending.out[5].numpy(), want[-1][5].numpy(), what="gradient (async, stream join)")
     assert done == NSTEPS - 1
+    # three in flight (four lanes): joined in submission order
+    import collections
+    q3, k = collections.deque(), 0
+    outs4 = outs + [[torch.empty_like(x).pin_memory() for x in outs[0]]]
+    for i, (a, b, ga, gb) in enumerate(clouds):
+        q3.append((i, ps.chamfer_host_async(a, b, ga, gb, out=outs4[i % 4])))
+        if len(q3) == 3:
+            j, st = q3.popleft()
+            for h, w in zip(st.synchronize()[:4], want[j][:4]):
+                assert torch.equal(h, w)
+            k += 1
+    while q3:
+        j, st = q3.popleft()
+        for h, w in zip(st.synchronize()[:4], want[j][:4]):
+            assert torch.equal(h, w)
+        k += 1
+    assert k == NSTEPS
     # forward only, library-allocated outputs, two in flight at once
     s1 = ps.chamfer_host_async(clouds[0][0], clouds[0][1])
     s2 = ps.chamfer_host_async(clouds[1][0], clouds[1][1])
