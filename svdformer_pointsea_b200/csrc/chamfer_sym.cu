@@ -28,7 +28,11 @@
 
 namespace ps {
 
-constexpr int CS_THREADS = 256;
+#ifndef PS_CS_THREADS
+#define PS_CS_THREADS 256  // A/B builds: -DPS_CS_THREADS=128 makes four 4-warp CTAs per SM instead of two 8-warp ones
+#endif
+constexpr int CS_THREADS = PS_CS_THREADS;
+constexpr int CS_PER_SM = 512 / CS_THREADS;  // resident CTAs per SM (128 registers per thread)
 constexpr int CS_TILE = 2048;  // B points per shared-memory tile
 constexpr int CS_STEP = 4;
 
@@ -161,7 +165,7 @@ __global__ void __launch_bounds__(256) sym_epilogue_kernel(const EpiParams p, co
 }
 
 template <int Q>
-__global__ void __launch_bounds__(CS_THREADS, 2) chamfer_sym_kernel(const SymParams p) {
+__global__ void __launch_bounds__(CS_THREADS, CS_PER_SM) chamfer_sym_kernel(const SymParams p) {
   constexpr int TA = CS_THREADS * Q;
   extern __shared__ __align__(16) unsigned char smem_raw[];
   float* sx = reinterpret_cast<float*>(smem_raw);
@@ -352,7 +356,7 @@ __global__ void __launch_bounds__(CS_THREADS, 2) chamfer_sym_kernel(const SymPar
 // single warp feeds both pipes at once.  Live distance registers stay at 32 (16 produced + 16 consumed).
 // GRAN: argmin bookkeeping once per GRAN steps (1 or 2): the final re-evaluation then looks at 4*GRAN candidates
 template <int Q, int UNROLL, int GRAN>
-__global__ void __launch_bounds__(CS_THREADS, 2) chamfer_sym2_kernel(const SymParams p) {
+__global__ void __launch_bounds__(CS_THREADS, CS_PER_SM) chamfer_sym2_kernel(const SymParams p) {
   static_assert(Q == 8, "the pipelined variant is written for 8 A points per thread");
   constexpr int TA = CS_THREADS * Q;
   extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -809,7 +813,7 @@ int chamfer_fwd_symmetric(const float* xyz1, const float* xyz2, float* dist1, fl
   // B-side split: enough units for >= 3 waves of the 2 resident CTAs per SM (measured on C1:
   // L=256 0.339 ms, L=512 0.330, L=1024 0.367, L=2048 0.375), but never below 256 targets per
   // unit so the per-unit fixed cost (A load, column pass, merge atomics) stays small.
-  const int slots = nsm * 2;
+  const int slots = nsm * CS_PER_SM;
   const long long base_units = (long long)B * p.natiles;
   int nsplit = (int)((3ll * slots + base_units - 1) / base_units);
   int max_split = small / 256 > 0 ? small / 256 : 1;

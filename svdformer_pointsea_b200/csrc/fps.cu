@@ -69,6 +69,7 @@ struct FpsArgs {
   int N, npoint;
   int L;     // log2(bs) of the reference launch
   int nper;  // ceil(N / bs)
+  const int* run_flag = nullptr;  // optional (B): a cloud whose flag is 0 has been sampled by fps_pruned_kernel already
 };
 
 // rank -> point index (may be >= N for the padding ranks of the last rows)
@@ -141,6 +142,7 @@ __global__ void __launch_bounds__(T, 1) fps_kernel(const FpsArgs a) {
   const unsigned C = CLUSTER ? cluster_nctarank() : 1u;
   const unsigned crank = CLUSTER ? cluster_ctarank() : 0u;
   const int b = CLUSTER ? (int)cluster_id_x() : (int)blockIdx.x;
+  if (a.run_flag && __ldg(a.run_flag + b) == 0) return;  // the whole cluster leaves together: nothing was armed yet
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int E = DIRECT ? WARPS * (int)C : (CLUSTER ? (int)C : WARPS);
   FpsEntry* wslots = slots + 2 * E;  // CTA-level staging (MODE 2)
@@ -432,6 +434,249 @@ __global__ void __launch_bounds__(FPS_GT, 1) fps_generic_kernel(const FpsArgs a,
   }
 }
 
+// ------------------------------------------------------------------------------------------------
+// Bucket-pruned FPS: ONE CTA per cloud, no cluster exchange, same samples bit for bit.
+//
+// An iteration of the register-resident kernel above is ~270 cycles of distance updates plus ~800 cycles of
+// cluster-wide exchange: the exchange cannot shrink, so the way out is to need no cluster.  What
+// forces four SMs per 16384-point cloud is the full update of every running minimum each iteration — yet a new
+// sample only lowers the minima of points closer to it than to every earlier sample, a handful after the first few
+// dozen iterations.  Here the points are sorted into BUCKETS of 32 spatial neighbours (counting sort by the Morton
+// index of a 16^3 grid over the cloud's bounding box), coordinates live in shared memory (192 KB for 16384 points),
+// the running minima in registers (lane l of a warp holds point l of each of the warp's FP_RPW buckets), and lane s
+// also keeps bucket s's bounding box, its maximum running minimum and the (rank, position) of that maximum.  Per
+// iteration every warp tests its buckets against the new sample — a bucket whose box is farther away than its
+// largest running minimum cannot change (fminf(d, t) == t for all its points; the bound carries a 2^-20 safety
+// margin over the rounding of both sides) — and only the AFFECTED buckets are updated (32 lanes = 32 points, two
+// REDUX for the bucket's new maximum).  The arg-max is then bucket maxima -> warp (two REDUX) -> 16 slots in shared
+// memory -> one __syncthreads -> every warp folds the 16 slots.  Buckets are dealt to warps round-robin so that the
+// few affected buckets of an iteration (spatial neighbours) land in different warps.
+// Selection order is unchanged: (running minimum desc, reference tie-break rank asc); skipped points (|p|^2 <= 1e-3)
+// are left out of the buckets altogether; the winner's index comes back from its rank (fps_rank_to_k).
+// Pruning cannot change a result, only the time: a cloud on which it does not bite (e.g. all points in one grid cell
+// next to a far outlier) is detected at iteration FP_CHECK by the number of bucket updates so far and handed to the
+// cluster kernel through run_flag (launched right behind, it returns at once for the clouds already done).
+constexpr int FP_MAXN = 16384;                      // 512 buckets: FP_RPW per warp, 512 / FP_RPW warps
+constexpr int FP_G = 16, FP_CELLS = FP_G * FP_G * FP_G;
+constexpr int FP_CHECK = 192;                       // iteration at which the pruning rate is judged
+
+__device__ __forceinline__ unsigned fp_spread4(unsigned v) { return (v & 1u) | ((v & 2u) << 2) | ((v & 4u) << 4) | ((v & 8u) << 6); }
+// order-preserving map float -> unsigned (for REDUX min / max over floats of either sign)
+__device__ __forceinline__ unsigned fp_ord(float f) { const unsigned u = __float_as_uint(f); return (u & 0x80000000u) ? ~u : (u | 0x80000000u); }
+__device__ __forceinline__ float fp_unord(unsigned k) { return __uint_as_float((k & 0x80000000u) ? (k & 0x7fffffffu) : ~k); }
+
+struct FpsPruneArgs {
+  unsigned short* inv;  // (B, FP_MAXN) scratch: sorted position -> point index
+  int* flag;            // (B): 0 = sampled here, 1 = hand the cloud to the cluster kernel
+  int check;            // 0: never give up (forced)
+  int max_updates;      // bucket updates allowed in the first FP_CHECK iterations
+};
+
+// FP_RPW: buckets per warp (16: 32 warps, 32: 16 warps); lane s < FP_RPW owns bucket s's box and maximum.
+// DISPATCH: how a warp reaches the code of an affected bucket (its running minima sit in registers, so every bucket
+// has its own copy of the update): 0 = one uniform test per bucket, 1 = jump table over the set bits of the mask,
+// 2 = no updates at all (timing of the arg-max skeleton only; results are wrong).
+// Measured (B200, B = 32, 16384 -> 2048, us per iteration; profiles/fps_pruned_r2.jsonl): skeleton 0.244 (16 warps) /
+// 0.351 (32 warps); with updates 0.835 (16 warps, jump table), 0.897 (tests), 0.809 / 0.784 (32 warps) on a uniform
+// cube, 0.586 on a sphere surface — against 0.546 for the 4-CTA cluster kernel.  A CPU simulation of the same
+// pruning (uniform cube) counts 18 affected buckets per iteration and 2.6 on the busiest warp: each bucket update
+// costs ~400 cycles of single-warp latency (bit scan + branch tree + LDC/BRX ~150, LDS + distance + two dependent
+// REDUX ~250), so the critical path is 480 + 2.6 x 400 cycles and the kernel only wins on THROUGHPUT (148 clouds:
+// 1.68 ms against 2.95 ms), which is where the launcher uses it.
+template <int FP_RPW, int DISPATCH>
+__global__ void __launch_bounds__(512 / FP_RPW * 32, 1) fps_pruned_kernel(const FpsArgs a, const FpsPruneArgs q) {
+  constexpr int FP_WARPS = 512 / FP_RPW;
+  constexpr int FP_T = FP_WARPS * 32;
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  float* sx = reinterpret_cast<float*>(smem_raw);
+  float* sy = sx + FP_MAXN;
+  float* sz = sy + FP_MAXN;
+  int* cnt = reinterpret_cast<int*>(sz + FP_MAXN);  // FP_CELLS counters / cursors
+  __shared__ unsigned red[6][FP_WARPS];
+  __shared__ int wtot[FP_WARPS];
+  __shared__ int2 slots[2][FP_WARPS];
+  __shared__ int aff_total;
+  const int b = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int N = a.N;
+  const float* cloud = a.xyz + (size_t)b * N * 3;
+  int* out = a.idx + (size_t)b * a.npoint;
+  float* oxyz = a.new_xyz ? a.new_xyz + (size_t)b * a.npoint * 3 : nullptr;
+  unsigned short* inv = q.inv + (size_t)b * FP_MAXN;
+  const float INF = __int_as_float(0x7f800000);
+
+  // ---- bounding box of the eligible points -------------------------------------------------------
+  unsigned bb[6] = {0xffffffffu, 0xffffffffu, 0xffffffffu, 0u, 0u, 0u};  // ordered keys: min x,y,z / max x,y,z
+  for (int k = tid; k < N; k += FP_T) {
+    const float x = __ldg(cloud + (size_t)k * 3 + 0), y = __ldg(cloud + (size_t)k * 3 + 1), z = __ldg(cloud + (size_t)k * 3 + 2);
+    if ((double)dist2_ref(x, y, z) <= 1e-3) continue;
+    const unsigned kx = fp_ord(x), ky = fp_ord(y), kz = fp_ord(z);
+    bb[0] = min(bb[0], kx); bb[1] = min(bb[1], ky); bb[2] = min(bb[2], kz);
+    bb[3] = max(bb[3], kx); bb[4] = max(bb[4], ky); bb[5] = max(bb[5], kz);
+  }
+#pragma unroll
+  for (int i = 0; i < 6; i++) {
+    const unsigned v = i < 3 ? __reduce_min_sync(0xffffffffu, bb[i]) : __reduce_max_sync(0xffffffffu, bb[i]);
+    if (lane == 0) red[i][warp] = v;
+  }
+  for (int c = tid; c < FP_CELLS; c += FP_T) cnt[c] = 0;
+  if (tid == 0) aff_total = 0;
+  __syncthreads();
+#pragma unroll
+  for (int i = 0; i < 6; i++) {
+    const unsigned v = lane < FP_WARPS ? red[i][lane] : (i < 3 ? 0xffffffffu : 0u);
+    bb[i] = i < 3 ? __reduce_min_sync(0xffffffffu, v) : __reduce_max_sync(0xffffffffu, v);
+  }
+  const float p0x = __ldg(cloud + 0), p0y = __ldg(cloud + 1), p0z = __ldg(cloud + 2);
+  if (bb[3] == 0u) {
+    // no eligible point at all: the reference's tree returns thread 0's initial besti = 0 every time
+    for (int j = tid; j < a.npoint; j += FP_T) { out[j] = 0; if (oxyz) { oxyz[j * 3 + 0] = p0x; oxyz[j * 3 + 1] = p0y; oxyz[j * 3 + 2] = p0z; } }
+    if (tid == 0) q.flag[b] = 0;
+    return;
+  }
+  const float lox = fp_unord(bb[0]), loy = fp_unord(bb[1]), loz = fp_unord(bb[2]);
+  const float ex = fp_unord(bb[3]) - lox, ey = fp_unord(bb[4]) - loy, ez = fp_unord(bb[5]) - loz;
+  const float gx = ex > 0.f ? (float)FP_G / ex : 0.f, gy = ey > 0.f ? (float)FP_G / ey : 0.f, gz = ez > 0.f ? (float)FP_G / ez : 0.f;
+  auto cell_of = [&](float x, float y, float z) {
+    const unsigned cx = min((unsigned)FP_G - 1u, (unsigned)max(0, (int)((x - lox) * gx)));
+    const unsigned cy = min((unsigned)FP_G - 1u, (unsigned)max(0, (int)((y - loy) * gy)));
+    const unsigned cz = min((unsigned)FP_G - 1u, (unsigned)max(0, (int)((z - loz) * gz)));
+    return (int)(fp_spread4(cx) | (fp_spread4(cy) << 1) | (fp_spread4(cz) << 2));
+  };
+
+  // ---- counting sort by grid cell (Morton order of the cells) ------------------------------------
+  for (int k = tid; k < N; k += FP_T) {
+    const float x = __ldg(cloud + (size_t)k * 3 + 0), y = __ldg(cloud + (size_t)k * 3 + 1), z = __ldg(cloud + (size_t)k * 3 + 2);
+    if ((double)dist2_ref(x, y, z) <= 1e-3) continue;
+    atomicAdd(&cnt[cell_of(x, y, z)], 1);
+  }
+  __syncthreads();
+  {
+    constexpr int PER = FP_CELLS / FP_T;  // 8 consecutive counters per thread
+    int v[PER], run = 0;
+#pragma unroll
+    for (int i = 0; i < PER; i++) { v[i] = cnt[tid * PER + i]; run += v[i]; }
+    int incl = run;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) { const int t = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += t; }
+    if (lane == 31) wtot[warp] = incl;
+    __syncthreads();
+    int wbase = 0;
+    for (int w = 0; w < warp; w++) wbase += wtot[w];
+    int base = wbase + incl - run;
+#pragma unroll
+    for (int i = 0; i < PER; i++) { cnt[tid * PER + i] = base; base += v[i]; }
+  }
+  int nvalid = 0;
+  for (int w = 0; w < FP_WARPS; w++) nvalid += wtot[w];
+  __syncthreads();
+  for (int k = tid; k < N; k += FP_T) {
+    const float x = __ldg(cloud + (size_t)k * 3 + 0), y = __ldg(cloud + (size_t)k * 3 + 1), z = __ldg(cloud + (size_t)k * 3 + 2);
+    if ((double)dist2_ref(x, y, z) <= 1e-3) continue;
+    const int pos = atomicAdd(&cnt[cell_of(x, y, z)], 1);
+    sx[pos] = x; sy[pos] = y; sz[pos] = z;
+    inv[pos] = (unsigned short)k;
+  }
+  __syncthreads();  // also orders this block's writes to `inv` before its reads below
+
+  // ---- per-lane state: running minima, ranks; per-bucket state in lane s ---------------------------
+  float t[FP_RPW];
+  unsigned rk2[FP_RPW / 2];
+  float blx = INF, bly = INF, blz = INF, bhx = -INF, bhy = -INF, bhz = -INF;
+  int bmax = (int)0x80000000;   // bits of the bucket's largest running minimum (signed compare), none: INT_MIN
+  unsigned bkey = 0xffffffffu;  // (rank << 14 | position) of that maximum, lowest rank among equals
+#pragma unroll
+  for (int s = 0; s < FP_RPW; s++) {
+    const int pos = (s * FP_WARPS + warp) * 32 + lane;
+    const bool valid = pos < nvalid;
+    unsigned rank = 0x3fffu;
+    float x = 0.f, y = 0.f, z = 0.f;
+    if (valid) { rank = fps_k_to_rank((int)inv[pos], a.L, a.nper); x = sx[pos]; y = sy[pos]; z = sz[pos]; }
+    t[s] = valid ? 1e10f : -1.0f;
+    if (s & 1) rk2[s / 2] |= rank << 16; else rk2[s / 2] = rank;
+    const unsigned any = __ballot_sync(0xffffffffu, valid);
+    const unsigned nx = __reduce_min_sync(0xffffffffu, valid ? fp_ord(x) : 0xffffffffu), ny = __reduce_min_sync(0xffffffffu, valid ? fp_ord(y) : 0xffffffffu);
+    const unsigned nz = __reduce_min_sync(0xffffffffu, valid ? fp_ord(z) : 0xffffffffu), mx = __reduce_max_sync(0xffffffffu, valid ? fp_ord(x) : 0u);
+    const unsigned my = __reduce_max_sync(0xffffffffu, valid ? fp_ord(y) : 0u), mz = __reduce_max_sync(0xffffffffu, valid ? fp_ord(z) : 0u);
+    if (lane == s && any) {
+      blx = fp_unord(nx); bly = fp_unord(ny); blz = fp_unord(nz); bhx = fp_unord(mx); bhy = fp_unord(my); bhz = fp_unord(mz);
+      bmax = __float_as_int(1e10f);  // every non-empty bucket is updated in the first iteration, which also sets bkey
+    }
+  }
+
+  float lx = p0x, ly = p0y, lz = p0z;
+  if (tid == 0 && a.npoint > 0) { out[0] = 0; if (oxyz) { oxyz[0] = p0x; oxyz[1] = p0y; oxyz[2] = p0z; } }
+  int updates = 0;
+  const float SHRINK = 1.0f - 9.5367431640625e-07f;  // 1 - 2^-20
+
+  for (int j = 1; j < a.npoint; j++) {
+    // ---- which of this warp's buckets can change: box distance (a lower bound) vs largest running minimum ----
+    const float dx = fmaxf(fmaxf(blx - lx, lx - bhx), 0.f), dy = fmaxf(fmaxf(bly - ly, ly - bhy), 0.f), dz = fmaxf(fmaxf(blz - lz, lz - bhz), 0.f);
+    const float lb = (dx * dx + dy * dy + dz * dz) * SHRINK;
+    unsigned mask = __ballot_sync(0xffffffffu, bmax >= 0 && !(lb > __int_as_float(bmax)));
+    updates += __popc(mask);
+    auto row = [&](const int s, float& ts) {  // s is a literal at every call site
+      const int pos = (s * FP_WARPS + warp) * 32 + lane;
+      const float d = dist2_ref(sx[pos] - lx, sy[pos] - ly, sz[pos] - lz);
+      const float tv = ts < 0.f ? ts : fminf(d, ts);  // padding lanes stay at -1
+      ts = tv;
+      const int tb = __float_as_int(tv);
+      const int m = __reduce_max_sync(0xffffffffu, tb);
+      const unsigned rank = (s & 1) ? (rk2[s / 2] >> 16) : (rk2[s / 2] & 0xffffu);
+      const unsigned key = tb == m ? ((rank << 14) | (unsigned)pos) : 0xffffffffu;
+      const unsigned kmin = __reduce_min_sync(0xffffffffu, key);
+      if (lane == s) { bmax = m; bkey = kmin; }
+    };
+    if (DISPATCH == 0) {
+      if (mask) {
+#pragma unroll
+        for (int s = 0; s < FP_RPW; s++)
+          if (mask & (1u << s)) row(s, t[s]);  // warp-uniform
+      }
+    } else if (DISPATCH == 1) {
+      while (mask) {
+        const int s = __ffs(mask) - 1;
+        mask &= mask - 1;
+#define FP_CASE(S) case S: if (S < FP_RPW) row(S, t[S < FP_RPW ? S : 0]); break;
+        switch (s) {
+          FP_CASE(0) FP_CASE(1) FP_CASE(2) FP_CASE(3) FP_CASE(4) FP_CASE(5) FP_CASE(6) FP_CASE(7)
+          FP_CASE(8) FP_CASE(9) FP_CASE(10) FP_CASE(11) FP_CASE(12) FP_CASE(13) FP_CASE(14) FP_CASE(15)
+          FP_CASE(16) FP_CASE(17) FP_CASE(18) FP_CASE(19) FP_CASE(20) FP_CASE(21) FP_CASE(22) FP_CASE(23)
+          FP_CASE(24) FP_CASE(25) FP_CASE(26) FP_CASE(27) FP_CASE(28) FP_CASE(29) FP_CASE(30) FP_CASE(31)
+        }
+#undef FP_CASE
+      }
+    }
+    // ---- arg-max: buckets -> warp -> block ----------------------------------------------------------
+    const int wm = __reduce_max_sync(0xffffffffu, bmax);
+    const unsigned wk = __reduce_min_sync(0xffffffffu, bmax == wm ? bkey : 0xffffffffu);
+    const int buf = j & 1;
+    if (lane == 0) {
+      slots[buf][warp] = make_int2(wm, (int)wk);
+      if (q.check && j == FP_CHECK) atomicAdd(&aff_total, updates);
+    }
+    __syncthreads();
+    const int2 sv = lane < FP_WARPS ? slots[buf][lane] : make_int2((int)0x80000000, -1);
+    const int gm = __reduce_max_sync(0xffffffffu, sv.x);
+    const unsigned gk = __reduce_min_sync(0xffffffffu, sv.x == gm ? (unsigned)sv.y : 0xffffffffu);
+    const int wpos = (int)(gk & 0x3fffu);
+    lx = sx[wpos]; ly = sy[wpos]; lz = sz[wpos];
+    if (tid == 0) out[j] = (int)gk;  // raw (rank, position); turned into the point index after the loop (off the critical path)
+    if (q.check && j == FP_CHECK) {
+      if (aff_total > q.max_updates) {  // uniform: no warp adds after this barrier
+        if (tid == 0) q.flag[b] = 1;
+        return;
+      }
+    }
+  }
+  __syncthreads();  // thread 0's writes to out[] are visible to the block
+  for (int j = 1 + tid; j < a.npoint; j += FP_T) {
+    const unsigned gk = (unsigned)out[j];
+    out[j] = fps_rank_to_k(gk >> 14, a.L, a.nper);
+    if (oxyz) { const int wpos = (int)(gk & 0x3fffu); oxyz[j * 3 + 0] = sx[wpos]; oxyz[j * 3 + 1] = sy[wpos]; oxyz[j * 3 + 2] = sz[wpos]; }
+  }
+  if (tid == 0) q.flag[b] = 0;
+}
+
 // opt_n_threads of the reference (include/cuda_utils.h:15-19), evaluated the same way
 // (double log ratio truncated) so bs matches even where the quotient is inexact.
 static int ref_block_log2(int n) {
@@ -584,7 +829,39 @@ extern "C" int ps_fps_sample(const float* xyz, int* idx, float* new_xyz, int B, 
   a.nper = ceil_div(N, 1 << a.L);
 
   FpsPlan pl;
-  if (!plan_fps(B, N, a.L, a.nper, nsm, dev, pl)) {
+  const bool planned = plan_fps(B, N, a.L, a.nper, nsm, dev, pl);
+
+  // Bucket-pruned single-CTA kernel (N <= 16384) where it wins: one SM per cloud at 0.6-0.85 us per iteration against
+  // 2-4 SMs per cloud at 0.55 us for the cluster kernel (B200, profiles/fps_pruned_r2.jsonl), i.e. when the batch needs
+  // two or more waves of clusters.  It leaves a per-cloud flag for the cluster kernel launched behind it, which only
+  // samples the clouds the pruning did not bite on.  PS_FPS_PRUNE=0 off, 1 forced for every N it accepts (no give-up).
+  ScratchGuard prune_mem;
+  {
+    int mode = -1;
+    if (const char* e = getenv("PS_FPS_PRUNE")) mode = atoi(e);
+    const bool wins = planned && N >= 8192 && npoint >= 2 * FP_CHECK && ceil_div(B, cluster_capacity(dev, pl.C, nsm)) >= 2;
+    const bool eligible = N <= FP_MAXN && npoint > 1 && (mode > 0 || (mode < 0 && wins));
+    if (eligible) {
+      const size_t inv_bytes = ((size_t)B * FP_MAXN * sizeof(unsigned short) + 255) & ~(size_t)255;
+      if (int rc = prune_mem.alloc(inv_bytes + (size_t)B * sizeof(int), dev, stream)) return rc;
+      FpsPruneArgs q;
+      q.inv = static_cast<unsigned short*>(prune_mem.ptr);
+      q.flag = reinterpret_cast<int*>(static_cast<char*>(prune_mem.ptr) + inv_bytes);
+      q.check = (mode > 0 || npoint <= FP_CHECK + 1) ? 0 : 1;
+      // an unpruned scan updates every bucket every iteration; a working pruning touches all of them in the first
+      // few iterations and a few per cent later (uniform cube: ~12 % of bucket x iteration pairs up to FP_CHECK)
+      q.max_updates = (int)(0.5 * FP_CHECK * ceil_div(N, 32));
+      const size_t smem = (size_t)3 * FP_MAXN * sizeof(float) + (size_t)FP_CELLS * sizeof(int);
+      auto kern = fps_pruned_kernel<32, 1>;
+      PS_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      kern<<<B, 512, smem, stream>>>(a, q);
+      PS_LAUNCH_CHECK();
+      if (!q.check) return prune_mem.release();
+      a.run_flag = q.flag;
+    }
+  }
+
+  if (!planned) {
     // beyond the register-resident kernels (N > 131072): one CTA per cloud with global scratch
     ScratchGuard temp_mem;
     if (int rc = temp_mem.alloc((size_t)B * N * sizeof(float), dev, stream)) return rc;

@@ -303,6 +303,50 @@ def test_fps_every_cluster_size(cluster, threads, monkeypatch):
     assert np.array_equal(got.cpu().numpy(), O.fps(x.numpy(), 100))
 
 
+@pytest.mark.parametrize("B,N,npoint,dup,no", [(3, 16384, 700, 0, 5), (2, 16384, 2048, 4000, 0), (2, 9999, 500, 1000, 30),
+                                               (2, 4096, 4096, 0, 0), (3, 1000, 128, 0, 0), (2, 33, 20, 5, 0), (1, 1, 1, 0, 0),
+                                               (2, 7, 7, 0, 0), (150, 2048, 96, 0, 1)])
+def test_fps_bucket_pruned_kernel_vs_oracle(B, N, npoint, dup, no, monkeypatch):
+    """fps_pruned_kernel forced for every shape it accepts (N <= 16384): duplicates (ties by rank), points inside
+    the skip ball (left out of the buckets), ragged last buckets, more clouds than SMs, npoint == N."""
+    monkeypatch.setenv("PS_FPS_PRUNE", "1")
+    g = torch.Generator().manual_seed(5200 + N + npoint)
+    x = make_cloud(g, B, N, dup=dup, near_origin=no)
+    got = ps.furthest_point_sample(x.to(DEV), npoint)
+    assert np.array_equal(got.cpu().numpy(), O.fps(x.numpy(), npoint))
+
+
+def test_fps_bucket_pruned_kernel_shapes_of_real_clouds_and_the_give_up_path(monkeypatch):
+    """(1) points on a thin surface and in tight clusters (where the pruning bites hardest, and bucket boxes are
+    degenerate in one axis); (2) clouds squeezed into one grid cell by a far outlier, or made of one repeated point:
+    forced, the pruned kernel ploughs on; by default (a batch of 150 clouds needs several waves of clusters, so the
+    launcher picks the pruned kernel) it gives up at its checkpoint and the cluster kernel behind it samples exactly
+    those clouds."""
+    g = torch.Generator().manual_seed(91)
+    N, B, M = 8192, 150, 400
+    sphere = torch.randn(1, N, 3, generator=g)
+    sphere = sphere / sphere.norm(dim=2, keepdim=True) * 0.4
+    plane = torch.rand(1, N, 3, generator=g) - 0.5
+    plane[..., 2] = 0.25
+    clusters = (torch.randint(0, 5, (1, N, 1), generator=g).float() - 2) * 0.2 + torch.randn(1, N, 3, generator=g) * 0.003
+    outlier = torch.randn(1, N, 3, generator=g) * 1e-3 + 0.3
+    outlier[0, 17] = torch.tensor([900.0, -700.0, 800.0])
+    same = torch.full((1, N, 3), 0.37)
+    kinds = [sphere, plane, clusters, outlier, same, make_cloud(g, 1, N, dup=3000, near_origin=7)]
+    clouds = torch.cat([kinds[i % len(kinds)] if i < 12 else kinds[i % len(kinds)].roll(i, 1) for i in range(B)], 0).contiguous()
+    want = O.fps(clouds.numpy(), M)
+    for mode in ("1", None, "0"):
+        if mode is None:
+            monkeypatch.delenv("PS_FPS_PRUNE", raising=False)
+        else:
+            monkeypatch.setenv("PS_FPS_PRUNE", mode)
+        got = ps.furthest_point_sample(clouds.to(DEV), M)
+        assert np.array_equal(got.cpu().numpy(), want), f"PS_FPS_PRUNE={mode}"
+    monkeypatch.delenv("PS_FPS_PRUNE", raising=False)
+    sub = ps.fps_subsample(clouds.to(DEV), M)  # fused coordinates output through the same kernels
+    assert torch.equal(sub.cpu(), torch.gather(clouds, 1, torch.from_numpy(want).long()[..., None].expand(-1, -1, 3)))
+
+
 def test_fps_generic_fallback_beyond_register_capacity():
     g = torch.Generator().manual_seed(77)
     x = make_cloud(g, 1, 140000, near_origin=4)
