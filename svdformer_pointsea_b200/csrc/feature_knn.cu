@@ -296,12 +296,16 @@ __device__ __forceinline__ void cp_async16(unsigned dst, const float* src, bool 
   asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(n) : "memory");
 }
 
-template <int VEC>
+// KC channels per stage.  UNION (single-pass shapes, npad == F8_TR): the distance block overlays the stage buffers —
+// it is only written after the last stage has been consumed — so KC = 16 fits two CTAs per SM (70 KB each) and the
+// per-stage costs (barrier, copy issue, the accumulator moves ptxas places at the loop's back edge: 35 IMAD.MOV on
+// the FP32 pipe per stage) are paid half as often.  The copy addresses are loop constants kept in registers.
+template <int VEC, int KC, bool UNION>
 __global__ void __launch_bounds__(FK_THREADS, 2) knn_feat8_kernel(const FkArgs a) {
   extern __shared__ __align__(16) float smem[];
-  float* dist = smem;                                 // 32 x npad
-  float* qs = dist + (size_t)F8_TQ * a.npad;          // 2 x F8_KC x 32
-  float* rs = qs + 2 * F8_KC * F8_TQ;                 // 2 x F8_KC x F8_TR
+  float* dist = smem;                                                   // 32 x npad
+  float* qs = UNION ? smem : dist + (size_t)F8_TQ * a.npad;             // 2 x KC x 32
+  float* rs = qs + 2 * KC * F8_TQ;                                      // 2 x KC x F8_TR
   __shared__ float bufd[FK_WARPS][32];
   __shared__ int bufi[FK_WARPS][32];
   const int b = blockIdx.y, q0 = blockIdx.x * F8_TQ, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -317,35 +321,48 @@ __global__ void __launch_bounds__(FK_THREADS, 2) knn_feat8_kernel(const FkArgs a
     const int q = q0 + qg * 8 + i;
     qn[i] = q < S ? __ldg(a.qq + (size_t)b * S + q) : 0.f;
   }
+  // copy plan of this thread (constant over the stages): references as KC x F8_TR, queries as KC x 32
+  constexpr int NRV = KC * F8_TR / 4 / FK_THREADS;  // 16-byte reference copies per thread and stage (VEC)
+  constexpr int NRS = KC * F8_TR / FK_THREADS;      // 4-byte copies otherwise
+  constexpr int NQC = KC * F8_TQ / FK_THREADS;      // query copies
+  const int rv_kc = tid / (F8_TR / 4), rv_r = (tid % (F8_TR / 4)) * 4;  // copy j: channel rv_kc + j * (FK_THREADS * 4 / F8_TR)
+  const int rs_kc = tid / F8_TR, rs_r = tid % F8_TR;                    // only when FK_THREADS >= F8_TR is false: see below
+  const int qc_kc = tid / F8_TQ, qc_q = tid % F8_TQ;                    // copy j: channel qc_kc + j * (FK_THREADS / F8_TQ)
+  const bool q_ok = q0 + qc_q < S;
+  const float* q_src = xq + (q_ok ? (size_t)(q0 + qc_q) * a.snq : 0);
+  const unsigned q_dst = smem_u32(qs + qc_kc * F8_TQ + qc_q);
+  const unsigned rv_dst = smem_u32(rs + rv_kc * F8_TR + rv_r);
   auto load = [&](int r0, int c0, int buf) {
-    float* rb = rs + buf * F8_KC * F8_TR;
-    float* qb = qs + buf * F8_KC * F8_TQ;
+    const unsigned boff_r = (unsigned)(buf * KC * F8_TR * 4), boff_q = (unsigned)(buf * KC * F8_TQ * 4);
     if (VEC) {  // references contiguous along r (channel-major tensors, N % 4 == 0, 16-byte aligned rows)
+      const bool r_ok = r0 + rv_r < N;
+      const float* src = xr + (r_ok ? (size_t)(r0 + rv_r) : 0);
 #pragma unroll
-      for (int j = 0; j < F8_KC * F8_TR / 4 / FK_THREADS; j++) {
-        const int i = tid + j * FK_THREADS;
-        const int kc = i / (F8_TR / 4), r = (i % (F8_TR / 4)) * 4;
-        const bool ok = c0 + kc < C && r0 + r < N;
-        cp_async16(smem_u32(rb + kc * F8_TR + r), xr + (ok ? (size_t)(r0 + r) + (size_t)(c0 + kc) * a.scr : 0), ok);
+      for (int j = 0; j < NRV; j++) {
+        const int kc = rv_kc + j * (FK_THREADS * 4 / F8_TR);
+        const bool ok = r_ok && c0 + kc < C;
+        cp_async16(rv_dst + boff_r + (unsigned)(j * (FK_THREADS * 4 / F8_TR) * F8_TR * 4), src + (ok ? (size_t)(c0 + kc) * a.scr : 0), ok);
       }
     } else {
 #pragma unroll
-      for (int j = 0; j < F8_KC * F8_TR / FK_THREADS; j++) {
+      for (int j = 0; j < NRS; j++) {
         const int i = tid + j * FK_THREADS;
         const int kc = i / F8_TR, r = i % F8_TR;
         const bool ok = c0 + kc < C && r0 + r < N;
-        cp_async4(smem_u32(rb + kc * F8_TR + r), xr + (ok ? (size_t)(r0 + r) * a.snr + (size_t)(c0 + kc) * a.scr : 0), ok);
+        cp_async4(smem_u32(rs + kc * F8_TR + r) + boff_r, xr + (ok ? (size_t)(r0 + r) * a.snr + (size_t)(c0 + kc) * a.scr : 0), ok);
       }
     }
-    {
-      const int kc = tid / F8_TQ, q = tid % F8_TQ;  // F8_KC * F8_TQ == FK_THREADS
-      const bool ok = c0 + kc < C && q0 + q < S;
-      cp_async4(smem_u32(qb + kc * F8_TQ + q), xq + (ok ? (size_t)(q0 + q) * a.snq + (size_t)(c0 + kc) * a.scq : 0), ok);
+#pragma unroll
+    for (int j = 0; j < NQC; j++) {
+      const int kc = qc_kc + j * (FK_THREADS / F8_TQ);
+      const bool ok = q_ok && c0 + kc < C;
+      cp_async4(q_dst + boff_q + (unsigned)(j * (FK_THREADS / F8_TQ) * F8_TQ * 4), q_src + (ok ? (size_t)(c0 + kc) * a.scq : 0), ok);
     }
     asm volatile("cp.async.commit_group;" ::: "memory");
   };
+  (void)rs_kc; (void)rs_r;
 
-  const int nstage = (C + F8_KC - 1) / F8_KC;
+  const int nstage = (C + KC - 1) / KC;
   for (int r0 = 0; r0 < npad; r0 += F8_TR) {
     u64 acc2[8][4];
 #pragma unroll
@@ -354,13 +371,13 @@ __global__ void __launch_bounds__(FK_THREADS, 2) knn_feat8_kernel(const FkArgs a
       for (int j = 0; j < 4; j++) acc2[i][j] = 0ull;
     load(r0, 0, 0);
     for (int st = 0; st < nstage; st++) {
-      const int c0 = st * F8_KC;
-      const int kcn = min(F8_KC, C - c0);
+      const int c0 = st * KC;
+      const int kcn = min(KC, C - c0);
       asm volatile("cp.async.wait_group 0;" ::: "memory");
       __syncthreads();  // stage st has landed for everyone; everyone is done with stage st-1 (the other buffer)
-      if (st + 1 < nstage) load(r0, c0 + F8_KC, (st + 1) & 1);
-      const float* rb = rs + (st & 1) * F8_KC * F8_TR + rh * 256 + lane * 4;
-      const float* qb = qs + (st & 1) * F8_KC * F8_TQ + qg * 8;
+      if (st + 1 < nstage) load(r0, c0 + KC, (st + 1) & 1);
+      const float* rb = rs + (st & 1) * KC * F8_TR + rh * 256 + lane * 4;
+      const float* qb = qs + (st & 1) * KC * F8_TQ + qg * 8;
       auto step = [&](int kc) {
         const ulonglong2 r0v = *reinterpret_cast<const ulonglong2*>(rb + kc * F8_TR);
         const ulonglong2 r1v = *reinterpret_cast<const ulonglong2*>(rb + kc * F8_TR + 128);
@@ -376,13 +393,14 @@ __global__ void __launch_bounds__(FK_THREADS, 2) knn_feat8_kernel(const FkArgs a
           acc2[i][3] = fma2(qd, r1v.y, acc2[i][3]);
         }
       };
-      if (kcn == F8_KC) {
+      if (kcn == KC) {
 #pragma unroll
-        for (int kc = 0; kc < F8_KC; kc++) step(kc);
+        for (int kc = 0; kc < KC; kc++) step(kc);
       } else {
         for (int kc = 0; kc < kcn; kc++) step(kc);  // no padded product enters the chain
       }
     }
+    if (UNION) __syncthreads();  // every warp is done with the last stage before the distance block overwrites it
     // dist = ((-2 * dot) + |q|^2) + |r|^2 ; padding columns at +inf
 #pragma unroll
     for (int h = 0; h < 2; h++) {
@@ -491,16 +509,25 @@ extern "C" int ps_knn_feat(const float* xr, const float* xq, int* idx, int B, in
   if (const char* e = getenv("PS_KNN_FEAT8")) use8 = use8 && atoi(e) != 0;
   if (use8) {
     a.npad = (N + F8_TR - 1) / F8_TR * F8_TR;
-    const size_t smem = (size_t)F8_TQ * a.npad * 4 + (size_t)2 * F8_KC * F8_TQ * 4 + (size_t)2 * F8_KC * F8_TR * 4;
     const bool vec = a.snr == 1 && (N & 3) == 0 && (a.scr & 3) == 0 && (a.sbr & 3) == 0 && (reinterpret_cast<uintptr_t>(xr) & 15) == 0;
     const dim3 grid8(ceil_div(S, F8_TQ), B);
-    if (vec) {
-      PS_CUDA(cudaFuncSetAttribute(knn_feat8_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-      knn_feat8_kernel<1><<<grid8, FK_THREADS, smem, stream>>>(a);
-    } else {
-      PS_CUDA(cudaFuncSetAttribute(knn_feat8_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-      knn_feat8_kernel<0><<<grid8, FK_THREADS, smem, stream>>>(a);
-    }
+    // single-pass shapes: stages of 16 channels under the distance block (C=256 N=512: 0.166 -> see profiles/feature_knn_r2.jsonl)
+    bool uni = a.npad == F8_TR && C >= 32;
+    if (const char* e = getenv("PS_KNN_FEAT_UNION")) uni = uni && atoi(e) != 0;
+#define PS_F8(VECV, KCV, UNI)                                                                                          \
+  {                                                                                                                    \
+    const size_t stages = (size_t)2 * KCV * (F8_TQ + F8_TR) * 4, block = (size_t)F8_TQ * a.npad * 4;                   \
+    const size_t smem = UNI ? (stages > block ? stages : block) : stages + block;                                      \
+    auto kern = knn_feat8_kernel<VECV, KCV, UNI>;                                                                      \
+    PS_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));                       \
+    kern<<<grid8, FK_THREADS, smem, stream>>>(a);                                                                      \
+  }
+    // two-pass shapes (N <= 1024) hold one CTA per SM either way (128 KB distance block): 16-channel stages fit beside it
+    const bool wide = !uni && C >= 32 && (size_t)F8_TQ * a.npad * 4 + (size_t)2 * 16 * (F8_TQ + F8_TR) * 4 <= 200 * 1024;
+    if (uni) { if (vec) PS_F8(1, 16, true) else PS_F8(0, 16, true) }
+    else if (wide) { if (vec) PS_F8(1, 16, false) else PS_F8(0, 16, false) }
+    else { if (vec) PS_F8(1, 8, false) else PS_F8(0, 8, false) }
+#undef PS_F8
     PS_LAUNCH_CHECK();
     return norms_mem.release();
   }
