@@ -126,3 +126,24 @@ def test_next_row_surface_and_cpu_rejection():
 def test_pipelined_sums_and_numa_helper_never_raise_without_a_gpu():
     from svdformer_pointsea_b200.dist import bind_to_gpu_numa_node
     assert bind_to_gpu_numa_node(0) is None or isinstance(bind_to_gpu_numa_node(0), set)
+
+
+def test_host_buffer_entry_points_validate_before_touching_a_device():
+    """chamfer_host / chamfer_host_async: shape and dtype errors are raised on the host (they do not need a GPU),
+    and without a CUDA device both refuse to run (no CPU path)."""
+    import inspect
+    assert list(inspect.signature(ps.chamfer_host_async).parameters) == ["xyz1", "xyz2", "graddist1", "graddist2", "out", "chunk",
+                                                                          "device", "sums_out", "comm"]
+    a, b = torch.zeros(2, 8, 3), torch.zeros(2, 9, 3)
+    for fn in (ps.chamfer_host, ps.chamfer_host_async):
+        with pytest.raises(ps.PointSeaError, match="expects"):
+            fn(a, torch.zeros(3, 9, 3))
+        with pytest.raises(ps.PointSeaError, match="both graddist1 and graddist2"):
+            fn(a, b, graddist1=torch.zeros(2, 8))
+        with pytest.raises(ps.PointSeaError, match="contiguous"):
+            fn(a.double(), b)
+        if not torch.cuda.is_available():
+            with pytest.raises(ps.PointSeaError, match="needs a CUDA device"):
+                fn(a, b)
+    step = ps.HostStep(0, 0, (a,), None, None)  # an empty submission: joining it is a no-op that needs no library call
+    assert step.ticket == 0
