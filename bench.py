@@ -447,8 +447,8 @@ def run_ours(args):
                   "host clouds + upstream gradients in; dist, idx, gradients AND the loss sums out (world-wide sums at N > 1: the "
                   "peer-memory exchange is a kernel inside the same graph); per step one CUDA graph launch (chunked H2D / kernels / "
                   "D2H on four streams); %d steps in flight: step i is submitted, then the host joins step i-%d and reads its loss, "
-                  "so upload + kernels of the younger steps overlap the download of the older ones (with a communicator the steps "
-                  "do not overlap)" % (DEPTH, DEPTH - 1),
+                  "so upload + kernels of the younger steps overlap the download of the older ones (with a communicator each of the "
+                  "library's lanes exchanges on its own channel, so the steps overlap at N > 1 too)" % (DEPTH, DEPTH - 1),
            "timing": f"median of 3 blocks of {args.steps} steps; a block = CUDA events around all of its steps on the submitting stream "
                      f"(max over ranks); every input byte crosses PCIe inside its own step, {OSETS} rotating pinned buffer sets, nothing "
                      "is reused across steps (no L2 flush needed)",

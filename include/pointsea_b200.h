@@ -165,7 +165,8 @@ int ps_chamfer_host_full(const float* xyz1, const float* xyz2, float* dist1, flo
  * following steps overlap the download of step i; up to four steps may be in flight.  *ticket (never 0 for a non-empty call) names the step for
  * ps_chamfer_host_wait: wait_stream != 0 makes `stream` wait for the step's last output byte, block != 0 blocks the
  * calling thread until then.  The buffers of a step must not be reused before it has been waited for.  With a
- * communicator the steps do not overlap (every rank must see the exchanges in the same order). */
+ * communicator every lane exchanges on its own channel of it, so the steps still overlap; every rank must then
+ * submit the same sequence of steps (the i-th submissions of all ranks meet in one exchange). */
 int ps_chamfer_host_submit(const float* xyz1, const float* xyz2, float* dist1, float* dist2, int* idx1, int* idx2,
                            const float* graddist1, const float* graddist2, float* gradxyz1, float* gradxyz2,
                            double* sums6, ps_comm* comm, int B, int N, int M, int chunk, int dev, void* stream,

@@ -258,7 +258,8 @@ def chamfer_host_async(xyz1, xyz2, graddist1=None, graddist2=None, out=None, chu
                 consume(pending.popleft().synchronize())
 
     Same arguments and results as `chamfer_host` (bit-identical); the buffers of a step must not be reused before
-    its `synchronize()` / `wait()`.  With `comm` the steps run one after the other."""
+    its `synchronize()` / `wait()`.  With `comm` every lane exchanges on its own channel of the communicator: all ranks
+    must submit the same sequence of steps."""
     B, N, M, index, out, gp = _host_args("chamfer_host_async", xyz1, xyz2, graddist1, graddist2, out, device, sums_out, comm)
     ticket = ctypes.c_longlong(0)
     rc = L.load().ps_chamfer_host_submit(L.ptr(xyz1), L.ptr(xyz2), L.ptr(out[0]), L.ptr(out[1]), L.ptr(out[2]), L.ptr(out[3]),

@@ -20,6 +20,23 @@ __global__ void __launch_bounds__(32) comm_publish_kernel(const CommDev c, const
   comm_publish(c, vals, n);
 }
 
+CommDev comm_channel(const ps_comm* comm, int ch) {
+  CommDev d = comm->d;
+  if (ch > 0 && ch < COMM_CHANNELS) {
+    for (int r = 0; r < comm->world; r++)
+      if (d.peer[r]) d.peer[r] += (size_t)ch * COMM_DEPTH * comm->world;
+    d.pub_seq = comm->counters + 2 * ch;
+    d.wait_seq = comm->counters + 2 * ch + 1;
+  }
+  return d;
+}
+
+int comm_allreduce_launch(const ps_comm* comm, int ch, const double* in, double* out, int n, cudaStream_t stream) {
+  comm_allreduce_kernel<<<1, 32, 0, stream>>>(comm_channel(comm, ch), in, out, n);
+  PS_LAUNCH_CHECK();
+  return PS_OK;
+}
+
 int comm_publish_launch(const ps_comm* comm, const double* in, int n, cudaStream_t stream) {
   comm_publish_kernel<<<1, 32, 0, stream>>>(comm->d, in, n);
   PS_LAUNCH_CHECK();
@@ -46,12 +63,12 @@ extern "C" int ps_comm_create(int rank, int world, int dev, ps_comm** out) {
   if (!guard.ok) return set_error(PS_ERR_CUDA, "ps_comm_create: cannot select device %d", dev);
   ps_comm* c = new ps_comm();
   c->rank = rank; c->world = world; c->dev = dev;
-  const size_t bytes = sizeof(CommSlot) * COMM_DEPTH * world;
+  const size_t bytes = sizeof(CommSlot) * COMM_CHANNELS * COMM_DEPTH * world;
   // plain cudaMalloc (not a pool allocation): CUDA IPC can only export such memory
   cudaError_t e = cudaMalloc((void**)&c->mailbox, bytes);
   if (e == cudaSuccess) e = cudaMemset(c->mailbox, 0, bytes);
-  if (e == cudaSuccess) e = cudaMalloc((void**)&c->counters, 64);
-  if (e == cudaSuccess) e = cudaMemset(c->counters, 0, 64);
+  if (e == cudaSuccess) e = cudaMalloc((void**)&c->counters, 128);
+  if (e == cudaSuccess) e = cudaMemset(c->counters, 0, 128);
   if (e == cudaSuccess) e = cudaDeviceSynchronize();
   if (e != cudaSuccess) {
     if (c->mailbox) cudaFree(c->mailbox);
@@ -61,7 +78,7 @@ extern "C" int ps_comm_create(int rank, int world, int dev, ps_comm** out) {
   }
   memset(&c->d, 0, sizeof(c->d));
   c->d.rank = rank; c->d.world = world;
-  c->d.pub_seq = c->counters; c->d.wait_seq = c->counters + 1; c->d.err = reinterpret_cast<int*>(c->counters + 2);
+  c->d.pub_seq = c->counters; c->d.wait_seq = c->counters + 1; c->d.err = reinterpret_cast<int*>(c->counters + 2 * COMM_CHANNELS);
   c->d.peer[rank] = c->mailbox;
   c->connected = world == 1;
   *out = c;
@@ -132,11 +149,13 @@ extern "C" int ps_comm_allreduce(ps_comm* c, const double* in, double* out, int 
 extern "C" int ps_comm_status(ps_comm* c, long long* published, long long* consumed, int* timed_out) {
   PS_REQUIRE(c != nullptr, "ps_comm_status: null communicator");
   DeviceGuard guard(c->dev);
-  unsigned long long h[3] = {0, 0, 0};
+  unsigned long long h[2 * COMM_CHANNELS + 1] = {0};
   PS_CUDA(cudaMemcpy(h, c->counters, sizeof(h), cudaMemcpyDeviceToHost));  // synchronises: diagnostics only
-  if (published) *published = (long long)h[0];
-  if (consumed) *consumed = (long long)h[1];
-  if (timed_out) *timed_out = (int)(h[2] & 0xffffffffu);
+  long long pub = 0, con = 0;
+  for (int ch = 0; ch < COMM_CHANNELS; ch++) { pub += (long long)h[2 * ch]; con += (long long)h[2 * ch + 1]; }
+  if (published) *published = pub;  // all channels
+  if (consumed) *consumed = con;
+  if (timed_out) *timed_out = (int)(h[2 * COMM_CHANNELS] & 0xffffffffu);
   return PS_OK;
 }
 

@@ -9,9 +9,13 @@
 // NVLink) adds the world's payloads in rank order, so every rank gets bit-identical sums.  No host call, no
 // stream other than the caller's: the whole step is replayable as one CUDA graph.
 //
-// Mailbox = DEPTH x world slots.  Step s uses row s % DEPTH.  A rank can run at most one publish ahead of the
-// slowest rank's wait (its own wait of step s needs everybody's publish of s), so DEPTH = 4 leaves slack.
-// The per-rank sequence counters live in device memory and are advanced by the kernels themselves.
+// Mailbox = CHANNELS x DEPTH x world slots.  Step s of a channel uses row s % DEPTH.  A rank can run at most one
+// publish ahead of the slowest rank's wait (its own wait of step s needs everybody's publish of s), so DEPTH = 4
+// leaves slack.  The per-rank sequence counters live in device memory and are advanced by the kernels themselves.
+// CHANNELS: independent instances of the protocol (own rows, own counters) inside one communicator.  Exchanges of
+// one channel must be issued in the same order on every rank; exchanges of different channels may interleave
+// freely.  Channel 0 serves everything stream-ordered; channels 1.. belong to the lanes of the asynchronous
+// host-buffer steps (host_pipeline.cu), which run concurrently on every rank.
 #pragma once
 #include "common.cuh"
 
@@ -20,6 +24,7 @@ namespace ps {
 constexpr int COMM_MAX_WORLD = 16;
 constexpr int COMM_MAX_N = 30;  // doubles per message
 constexpr int COMM_DEPTH = 4;
+constexpr int COMM_CHANNELS = 5;
 constexpr unsigned long long COMM_TIMEOUT_NS = 4000000000ull;  // a lost peer raises an error instead of hanging the GPU
 
 struct __align__(16) CommSlot {
@@ -88,6 +93,9 @@ __device__ __forceinline__ void comm_wait_reduce(const CommDev& c, double* out, 
 }  // namespace ps
 
 namespace ps {
+// device view of channel `ch` of a communicator (channel 0: comm->d itself)
+CommDev comm_channel(const ::ps_comm* comm, int ch);
+int comm_allreduce_launch(const ::ps_comm* comm, int ch, const double* in, double* out, int n, cudaStream_t stream);
 // stand-alone halves of the exchange for producers that cannot publish from their own last block
 int comm_publish_launch(const ::ps_comm* comm, const double* in, int n, cudaStream_t stream);
 int comm_wait_launch(const ::ps_comm* comm, double* out, int n, cudaStream_t stream);
@@ -100,7 +108,7 @@ int chamfer_fwd_impl(const float* xyz1, const float* xyz2, float* dist1, float* 
 struct ps_comm {
   int rank = 0, world = 1, dev = 0;
   ps::CommSlot* mailbox = nullptr;     // our own (cudaMalloc)
-  unsigned long long* counters = nullptr;  // [0] pub_seq, [1] wait_seq, [2] err (as int)
+  unsigned long long* counters = nullptr;  // [2c] pub_seq, [2c+1] wait_seq of channel c, [2*COMM_CHANNELS] err (as int)
   void* opened[ps::COMM_MAX_WORLD] = {nullptr};  // cudaIpcOpenMemHandle results (to close)
   ps::CommDev d;
   bool connected = false;

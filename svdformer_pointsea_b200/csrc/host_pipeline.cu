@@ -41,6 +41,7 @@ namespace ps {
 constexpr int SLOTS = 3;
 constexpr int MAX_CHUNKS = 64;
 constexpr int LANES = 4;
+static_assert(LANES + 1 <= COMM_CHANNELS, "every lane needs its own communicator channel");
 
 struct Lane {
   GraphCache graphs;
@@ -153,6 +154,7 @@ struct PipeArgs {
   float *dev_g1 = nullptr, *dev_g2 = nullptr;
   double* h_sums = nullptr;
   ps_comm* comm = nullptr;  // with h_sums: the sums are exchanged with the peers and h_sums receives the world-wide ones
+  int channel = 0;          // the communicator's channel: 0 stream-ordered calls, 1 + lane for submissions
   size_t o_x1, o_x2, o_d1, o_d2, o_i1, o_i2, o_gd1, o_gd2, o_g1, o_g2;
 };
 
@@ -213,7 +215,7 @@ static int enqueue_pipeline(Lane& hp, const PipeArgs& a, cudaStream_t origin) {
     }
     // the path's single collective, after the last chunk's kernels: publish + wait over peer memory
     if (a.h_sums && a.comm && c == a.nchunks - 1)
-      if (int rc = ps_comm_allreduce(a.comm, hp.d_sums, hp.d_sums + 6, 6, hp.s_bwd)) return rc;
+      if (int rc = comm_allreduce_launch(a.comm, a.channel, hp.d_sums, hp.d_sums + 6, 6, hp.s_bwd)) return rc;
     PS_CUDA(cudaEventRecord(hp.ev_run[s], hp.s_bwd));
 
     // download: distances and indices as soon as the forward is done, gradients after the backward
@@ -260,11 +262,9 @@ static int host_pipeline_call(const float* xyz1, const float* xyz2, float* dist1
     PS_CUDA(cudaEventRecord(hp.ev_sub, stream));
     stream = hp.s_launch;
     PS_CUDA(cudaStreamWaitEvent(stream, hp.ev_sub, 0));
-    // the exchange kernels of consecutive steps must run in the same order on every rank: with a communicator the
-    // lanes take turns (no overlap between steps)
-    if (comm)
-      for (int o = 0; o < LANES; o++)
-        if (o != li && hpp->lane[o].ready) PS_CUDA(cudaStreamWaitEvent(stream, hpp->lane[o].ev_last, 0));
+    // with a communicator every lane exchanges on its own channel (1 + lane): the steps of one lane run in
+    // submission order on every rank, and lanes never wait for each other — provided every rank submits the same
+    // sequence of steps, as SPMD ranks do
     *ticket = (long long)(((++hp.calls) << 8) | (unsigned)(li + 1));
   }
 
@@ -274,6 +274,7 @@ static int host_pipeline_call(const float* xyz1, const float* xyz2, float* dist1
   a.dist1 = dist1; a.dist2 = dist2; a.gradxyz1 = gradxyz1; a.gradxyz2 = gradxyz2;
   a.idx1 = idx1; a.idx2 = idx2;
   a.dev_g1 = dev_g1; a.dev_g2 = dev_g2; a.h_sums = h_sums; a.comm = comm;
+  a.channel = (comm && ticket) ? 1 + li : 0;
   a.B = B; a.N = N; a.M = M; a.chunk = chunk; a.dev = dev; a.with_bwd = with_bwd;
   // slot layout (all sub-buffers 256-byte aligned so the vectorised kernels see aligned clouds)
   const size_t n1 = (size_t)chunk * N, n2 = (size_t)chunk * M;
@@ -423,7 +424,7 @@ extern "C" int ps_chamfer_host_stats(int dev, long long* hits, long long* update
 // prefetches the next batch while the previous results are read): the call is ordered behind the current position
 // of `stream`, runs on one of the library's lanes (in turn) and does NOT join `stream` again.  *ticket identifies
 // it for ps_chamfer_host_wait.  Consecutive submissions overlap: upload and kernels of step i+1 with the download of
-// step i.  With a communicator the steps run one after the other (the peers must see the exchanges in one order).
+// step i.  With a communicator each lane exchanges on its own channel: every rank must submit the same sequence.
 extern "C" int ps_chamfer_host_submit(const float* xyz1, const float* xyz2, float* dist1, float* dist2, int* idx1, int* idx2,
                                       const float* graddist1, const float* graddist2, float* gradxyz1, float* gradxyz2,
                                       double* sums6, ps_comm* comm, int B, int N, int M, int chunk, int dev, void* stream,

@@ -212,13 +212,31 @@ def _ipc_worker(rank, world, port, q):
     hs = torch.empty(6, dtype=torch.float64).pin_memory()
     ps.chamfer_host_step(sa.cpu().pin_memory(), sb.cpu().pin_memory(), sga.cpu().pin_memory(), sgb.cpu().pin_memory(),
                          sums_out=hs, comm=comm)
+    # asynchronous host steps with the collective: three in flight, each lane on its own channel of the communicator
+    import collections
+    h_in = [t.cpu().pin_memory() for t in (sa, sb, sga, sgb)]
+    sets = [([torch.empty(sa.size(0), N).pin_memory(), torch.empty(sa.size(0), M).pin_memory(),
+              torch.empty(sa.size(0), N, dtype=torch.int32).pin_memory(), torch.empty(sa.size(0), M, dtype=torch.int32).pin_memory(),
+              torch.empty(sa.size(0), N, 3).pin_memory(), torch.empty(sa.size(0), M, 3).pin_memory()],
+             torch.empty(6, dtype=torch.float64).pin_memory()) for _ in range(4)]
+    pend, async_sums = collections.deque(), []
+    for i in range(11):
+        pend.append(ps.chamfer_host_async(*h_in, out=sets[i % 4][0], sums_out=sets[i % 4][1], comm=comm))
+        if len(pend) == 3:
+            st = pend.popleft()
+            st.synchronize()
+            async_sums.append(st.sums.numpy().copy())
+    while pend:
+        st = pend.popleft()
+        st.synchronize()
+        async_sums.append(st.sums.numpy().copy())
     # the autograd loss over the peer-memory collective vs the NCCL one
     P = [(shard_batch(a)[:, :256].to(dev)).requires_grad_(True), shard_batch(a)[:, :512].to(dev), shard_batch(a).to(dev)]
     gt = shard_batch(b).to(dev)
     l_peer, _ = get_loss_sharded(P, gt, comm=comm)
     l_nccl, _ = get_loss_sharded(P, gt)
     torch.cuda.synchronize()
-    q.put((rank, [o.cpu().numpy() for o in outs], hs.numpy().copy(), float(l_peer), float(l_nccl), comm.status()))
+    q.put((rank, [o.cpu().numpy() for o in outs], hs.numpy().copy(), float(l_peer), float(l_nccl), comm.status(), async_sums))
     dist.barrier()
     comm.close()
     dist.destroy_process_group()
@@ -243,8 +261,11 @@ def test_peer_comm_over_cuda_ipc_between_processes():
     a, b = make_cloud(g, B, N).cuda(), make_cloud(g, B, M).cuda()
     d1, d2, _, _ = ps.chamfer_forward(a, b)
     want = ps.chamfer_sums(d1, d2).cpu().numpy()
-    for rank, outs, hs, l_peer, l_nccl, st in res:
+    for rank, outs, hs, l_peer, l_nccl, st, async_sums in res:
         assert not st["timed_out"]
+        assert len(async_sums) == 11
+        for v in async_sums:
+            assert np.array_equal(v, res[0][6][0]) and np.allclose(v, want, rtol=1e-12, atol=0)
         for o in outs:
             assert np.array_equal(o, res[0][1][0])  # identical bits on both ranks, every replay
             assert np.allclose(o, want, rtol=1e-12, atol=0)
