@@ -47,6 +47,7 @@
 // fp32 bit patterns are compared as signed integers.
 #include "common.cuh"
 
+#include <atomic>
 #include <cmath>
 #include <cstdlib>
 
@@ -742,10 +743,10 @@ __global__ void __launch_bounds__(256, 1) fps_capacity_probe_kernel(int* p) {
   if (p) p[0] = probe_smem[0];
 }
 static int cluster_capacity(int dev, int c, int nsm) {
-  static int cache[64][5] = {{0}};
+  static std::atomic<int> cache[64][5];  // zero-initialised; concurrent first calls compute the same value
   int slot = 0;
   while ((1 << slot) < c) slot++;
-  if (dev >= 0 && dev < 64 && cache[dev][slot]) return cache[dev][slot];
+  if (dev >= 0 && dev < 64) { const int c0 = cache[dev][slot].load(std::memory_order_relaxed); if (c0) return c0; }
   int cap = nsm / c;
   if (c > 1) {
     const int smem = 120 * 1024;  // forces one CTA per SM
@@ -765,7 +766,7 @@ static int cluster_capacity(int dev, int c, int nsm) {
     else cudaGetLastError();
   }
   if (cap < 1) cap = 1;
-  if (dev >= 0 && dev < 64) cache[dev][slot] = cap;
+  if (dev >= 0 && dev < 64) cache[dev][slot].store(cap, std::memory_order_relaxed);
   return cap;
 }
 
