@@ -26,7 +26,7 @@ partial 2048 points vs ground truth 16384 points, fp32, synthetic `rand - 0.5` c
            each device-timed, each next to the REFERENCE'S OWN CUDA KERNEL (oracle/_ref, compiled unmodified
            for sm_100a; baseline leg only, never on the product path) timed in the same run: `ref_cuda_ms`,
            `speedup_vs_ref_cuda`.
-  roofline = dominant kernel chamfer_sym_kernel<8> (+ its fill and epilogue launches): algorithmic 8 flop per
+  roofline = dominant kernel chamfer_sym2_kernel<8,4,2> (+ its fill and epilogue launches): algorithmic 8 flop per
            pair evaluation over the forward's device time against the fp32 FFMA2 peak measured live in this run
            (MEASURED_PEAKS.json carries no fp32 figure); executed_* count each pair once (the kernel evaluates
            it once for both directions).  roofline_hbm = group forward against MEASURED_PEAKS.json hbm_gbs.
@@ -504,7 +504,7 @@ def run_ours(args):
         "gpu_launches": int(launches), "launches_note": "kernels inside the replayed graph(s) of the last timed block; ONE cudaGraphLaunch per step",
         "host_issue_ms_per_step": round(statistics.median(host_ms_blocks), 4), "reduce": reduce_mode,
         "clocks": clocks,
-        "roofline": {"kernel": "chamfer_sym_kernel<8> (+ key fill and epilogue launches): forward, both directions in one pass", "bound": "fp32",
+        "roofline": {"kernel": "chamfer_sym2_kernel<8,4,2> (+ key fill and epilogue launches): forward, both directions in one pass", "bound": "fp32",
                      "achieved": round(pairs_per_step * FLOP_PER_PAIR / (fwd_avg_ms * 1e-3) / 1e12, 2),
                      "peak": round(fp32_peak, 2), "unit": "TFLOP/s",
                      "frac": round(pairs_per_step * FLOP_PER_PAIR / (fwd_avg_ms * 1e-3) / 1e12 / fp32_peak, 4),

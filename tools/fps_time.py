@@ -5,7 +5,8 @@ import numpy as np, torch
 import svdformer_pointsea_b200 as ps
 from oracle import oracle as O
 g = torch.Generator().manual_seed(0)
-for B, N, m in ((32, 16384, 2048), (32, 8192, 1024), (32, 4096, 512), (32, 2048, 512), (32, 2304, 512), (32, 512, 128), (4, 16384, 2048), (8, 131072, 2048)):
+for B, N, m in ((32, 16384, 2048), (32, 8192, 1024), (32, 4096, 512), (32, 2048, 512), (32, 2304, 512), (32, 1024, 256), (32, 512, 128), (4, 16384, 2048),
+                (8, 131072, 2048)):
     x = (torch.rand(B, N, 3, generator=g) - 0.5).cuda()
     for _ in range(2): idx = ps.furthest_point_sample(x, m)
     torch.cuda.synchronize()
