@@ -771,7 +771,7 @@ static int cluster_capacity(int dev, int c, int nsm) {
 }
 
 // Per-iteration cost model in SM cycles, cost = base + slope * PP (PP = point pairs per thread), fitted to B200
-// measurements at B = 32 (tools/fps_time2.py with PS_FPS_CLUSTER / PS_FPS_THREADS forced; profiles/fps_r1_notes.md):
+// measurements at B = 32 (tools/fps_time.py with PS_FPS_CLUSTER / PS_FPS_THREADS forced; profiles/fps_r1_notes.md):
 // one warp per scheduler cannot hide its own dependency chains, so the per-pair cost is ~20 cycles rather than
 // the ~7 issue slots it needs, and every configuration carries 550-800 cycles of exchange + reduction latency.
 //   C=1 T=128: 565 + 23.5 PP     C=1 T=256: 725 + 43 PP
