@@ -180,6 +180,38 @@ def test_chamfer_host_async_keeps_several_steps_in_flight_bitwise():
     assert e.ticket == 0 and e.synchronize()[0].numel() == 0
 
 
+def test_chamfer_host_async_mixed_shapes_many_steps():
+    """A longer run of the asynchronous pair as a race guard: four steps in flight, shapes changing from step to step
+    (the lanes' staging slots grow, cached graphs are evicted and retargeted), fresh output buffers half of the
+    time; every distance and index is compared with the stream-ordered call."""
+    import collections
+    g = torch.Generator().manual_seed(77)
+    shapes = [(4, 512, 3000), (7, 2048, 1024), (2, 300, 300), (5, 1500, 6000)]
+    data, want = [], []
+    for B, N, M in shapes:
+        a, b = make_cloud(g, B, N, dup=N // 5).pin_memory(), make_cloud(g, B, M).pin_memory()
+        data.append((a, b))
+        want.append(tuple(x.clone() for x in ps.chamfer_host(a, b)))
+    outs = [[[torch.empty(B, N).pin_memory(), torch.empty(B, M).pin_memory(), torch.empty(B, N, dtype=torch.int32).pin_memory(),
+              torch.empty(B, M, dtype=torch.int32).pin_memory()] for _ in range(5)] for B, N, M in shapes]
+    order = torch.randint(0, len(shapes), (120,), generator=g).tolist()
+    pend, checked = collections.deque(), 0
+    for i, k in enumerate(order):
+        out = outs[k][i % 5] if i % 2 else None
+        pend.append((k, ps.chamfer_host_async(data[k][0], data[k][1], out=out)))
+        if len(pend) == 4:
+            kk, st = pend.popleft()
+            for h, w in zip(st.synchronize(), want[kk]):
+                assert torch.equal(h, w), f"step {checked} shape {shapes[kk]}"
+            checked += 1
+    while pend:
+        kk, st = pend.popleft()
+        for h, w in zip(st.synchronize(), want[kk]):
+            assert torch.equal(h, w)
+        checked += 1
+    assert checked == len(order)
+
+
 def test_chamfer_host_rejects_device_tensors_and_bad_shapes():
     a = torch.zeros(2, 8, 3, device=DEV)
     with pytest.raises(ps.PointSeaError):
