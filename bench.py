@@ -17,8 +17,9 @@ partial 2048 points vs ground truth 16384 points, fp32, synthetic `rand - 0.5` c
   e2e    = the same step through the host-buffer API (chamfer_host_async -> ps_chamfer_host_submit / _wait): clouds
            and upstream gradients come from PINNED HOST buffers (depth + 1 sets in rotation, as a prefetching
            loader would hand them out), and EVERY output goes back to the host — dist, idx, gradients and the loss
-           sums (world-wide at N > 1: the peer exchange is a kernel inside the same graph).  Three steps are in
-           flight (--e2e-depth): step i is submitted, then the host joins step i-2 and reads its loss.
+           sums (world-wide at N > 1: the peer exchange is one more kernel of the step).  Four steps are in flight
+           (--e2e-depth): step i is submitted, then the host joins step i-3 and reads its loss; a step's uploads and
+           downloads run on its lane's copy streams, its kernels on the one stream that serves all lanes in order.
            `e2e.per_call` is one call at a time (the latency of a single chamfer_host call); `e2e.loss_readback`
            leaves the gradients on the device and reads back only the loss sums; `e2e.fresh_buffers` hands out a
            NEW address set every step (the cached graph is retargeted in place).
@@ -445,10 +446,11 @@ def run_ours(args):
            "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h_full, "ms_per_step": round(e2e_ms, 4),
            "api": "svdformer_pointsea_b200.chamfer_host_async(..., sums_out, comm) -> ps_chamfer_host_submit / ps_chamfer_host_wait: pinned "
                   "host clouds + upstream gradients in; dist, idx, gradients AND the loss sums out (world-wide sums at N > 1: the "
-                  "peer-memory exchange is a kernel inside the same graph); per step one CUDA graph launch (chunked H2D / kernels / "
-                  "D2H on four streams); %d steps in flight: step i is submitted, then the host joins step i-%d and reads its loss, "
-                  "so upload + kernels of the younger steps overlap the download of the older ones (with a communicator each of the "
-                  "library's lanes exchanges on its own channel, so the steps overlap at N > 1 too)" % (DEPTH, DEPTH - 1),
+                  "peer-memory exchange is one more kernel of the step); a step = uploads on its lane's copy stream -> its kernels, "
+                  "replayed as one CUDA graph on the stream that serves ALL lanes in submission order (one step at a time, each with "
+                  "the whole GPU) -> downloads on the lane's copy stream; %d steps in flight: step i is submitted, then the host joins "
+                  "step i-%d and reads its loss, so the copy engines work on the neighbouring steps while the SMs work on this one"
+                  % (DEPTH, DEPTH - 1),
            "timing": f"median of 3 blocks of {args.steps} steps; a block = CUDA events around all of its steps on the submitting stream "
                      f"(max over ranks); every input byte crosses PCIe inside its own step, {OSETS} rotating pinned buffer sets, nothing "
                      "is reused across steps (no L2 flush needed)",
@@ -903,7 +905,7 @@ def main():
     ap.add_argument("--repeats", type=int, default=7, help="how many times the K-step block is timed (median reported)")
     ap.add_argument("--scaling", default="weak", choices=["weak", "strong"])
     ap.add_argument("--workload", default="c5", choices=["c1", "c5", "c4loss"], help="--scaling strong: which fixed-size workload to split")
-    ap.add_argument("--e2e-depth", type=int, default=3, help="steps in flight in the e2e loop (1-4; 1 = one call at a time)")
+    ap.add_argument("--e2e-depth", type=int, default=4, help="steps in flight in the e2e loop (1-4; 1 = one call at a time)")
     ap.add_argument("--e2e-chunk", type=int, default=0, help="clouds per pipeline chunk of the host-buffer call (0: library default)")
     ap.add_argument("--reduce", default="peer", choices=["peer", "nccl_graph", "pipelined", "inline"],
                     help="how the per-step reduction of the loss sums runs when N > 1 (A/B); default: peer-memory exchange inside the step's graph")

@@ -161,8 +161,9 @@ int ps_chamfer_host_full(const float* xyz1, const float* xyz2, float* dist1, flo
 /* Asynchronous pair for loops that keep several steps in flight (the reference's evaluation loops read one batch
  * from the loader while the previous one is on the GPU, core/eval_pcn.py:44-60): ps_chamfer_host_submit is
  * ps_chamfer_host_full ordered BEHIND the current position of `stream` but not joined back into it — it runs on one
- * of the library's four lanes (own streams, staging slots and graphs; taken in turn), so upload and kernels of the
- * following steps overlap the download of step i; up to four steps may be in flight.  *ticket (never 0 for a non-empty call) names the step for
+ * of the library's four lanes (own copy streams and staging slots; taken in turn): its uploads and downloads run on the
+ * lane's copy streams, its kernels — replayed as one graph — on the one stream that serves all lanes in submission
+ * order, so the copies of the neighbouring steps overlap the kernels of step i; up to four steps may be in flight.  *ticket (never 0 for a non-empty call) names the step for
  * ps_chamfer_host_wait: wait_stream != 0 makes `stream` wait for the step's last output byte, block != 0 blocks the
  * calling thread until then.  The buffers of a step must not be reused before it has been waited for.  With a
  * communicator every lane exchanges on its own channel of it, so the steps still overlap; every rank must then

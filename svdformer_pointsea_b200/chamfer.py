@@ -247,14 +247,15 @@ class HostStep(object):
 def chamfer_host_async(xyz1, xyz2, graddist1=None, graddist2=None, out=None, chunk=0, device=None, sums_out=None, comm=None):
     """`chamfer_host` for loops that keep more than one step in flight: returns a `HostStep` at once.
 
-    The step is ordered behind the current stream of `device` but runs on one of the library's four lanes, so the
-    upload and the kernels of the next submissions overlap the download of this one (a loader that prefetches the
-    next batches while the results of an earlier one are read back; up to four steps in flight):
+    The step is ordered behind the current stream of `device` but runs on one of the library's four lanes: uploads
+    and downloads on the lane's copy streams, the kernels (one replayed graph) on the stream that serves all lanes in
+    submission order — so the copies of the neighbouring steps overlap the kernels of this one (a loader that
+    prefetches the next batches while the results of an earlier one are read back; up to four steps in flight):
 
         pending = collections.deque()
         for i, batch in enumerate(loader):         # pinned host tensors, DEPTH + 1 buffer sets in rotation
             pending.append(chamfer_host_async(*batch, out=outs[i % (DEPTH + 1)], sums_out=sums[i % (DEPTH + 1)]))
-            if len(pending) == DEPTH:              # DEPTH = 3: the loop runs at the speed of the busiest resource
+            if len(pending) == DEPTH:              # DEPTH = 4: the loop runs at the speed of the busiest resource
                 consume(pending.popleft().synchronize())
 
     Same arguments and results as `chamfer_host` (bit-identical); the buffers of a step must not be reused before

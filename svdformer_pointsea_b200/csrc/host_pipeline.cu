@@ -22,13 +22,18 @@
 //
 // LANES: a call occupies the staging slots of its lane from its first upload to its last download, so calls on
 // one lane run back to back.  The asynchronous entry points (ps_chamfer_host_submit / ps_chamfer_host_wait)
-// alternate between LANES independent lanes, each with its own streams, slots, events and graph cache and its
-// own launch stream: step i+1 uploads and computes while step i still downloads (PCIe is full duplex, the two
-// copy engines and the SMs are three separate resources), which is what a loader that prefetches the next batches
-// does.  With D steps in flight the loop's period is max(busiest resource, (step latency + host turn-around) / D):
-// measured on C1, one call at a time 0.55 ms, D = 2 0.46 ms (a step's latency grows when it shares the GPU), D = 3
-// reaches the compute bound; LANES = 4 leaves one lane free while three are busy.  The stream-ordered entry points keep their contract ("complete when `stream` reaches the call") and
-// always use lane 0.
+// alternate between LANES independent lanes, each with its own copy streams, slots and events, which is what a
+// loader that prefetches the next batches does: PCIe is full duplex and the two copy engines and the SMs are three
+// separate resources.  Two shapes of an asynchronous step were measured on C1 (one call at a time: 0.554 ms):
+//   * "lanes": the chunked multi-stream graph of the stream-ordered call, one per lane on the lane's own launch
+//     stream — 0.419 / 0.392 / 0.397 ms with 2 / 3 / 4 steps in flight.  Kernels of different steps run side by
+//     side, and the three small forward launches of a chunked step cost 0.375 ms of kernels instead of 0.33;
+//   * "FIFO" (the default, submit_fifo): a step = uploads on the lane's copy stream -> ALL its kernels as one graph
+//     on the stream that serves every lane in submission order (one step at a time, each with the whole GPU) ->
+//     downloads on the lane's copy stream, chained by events — 0.428 / 0.342 / **0.335 ms** with 2 / 3 / 4 steps in
+//     flight, within 8 % of the 0.309 ms the same kernels take on device-resident buffers.
+// PS_HOST_ASYNC=lanes selects the first.  The stream-ordered entry points keep their contract ("complete when
+// `stream` reaches the call") and always use lane 0 and the chunked graph.
 #include "comm.cuh"
 #include "graph_cache.cuh"
 
@@ -49,6 +54,7 @@ struct Lane {
   cudaStream_t s_launch = nullptr;  // launch stream of the asynchronous entry points
   cudaEvent_t ev_last = nullptr;    // end of the most recent call on this lane (any caller stream)
   cudaEvent_t ev_sub = nullptr;     // the submitting stream's position at ps_chamfer_host_submit
+  cudaEvent_t ev_cmp = nullptr;     // end of the kernels of the lane's latest submission (FIFO mode)
   unsigned long long calls = 0;
   bool ready = false;
   cudaStream_t s_in = nullptr, s_run = nullptr, s_bwd = nullptr, s_out = nullptr;
@@ -62,6 +68,8 @@ struct HostPipe {
   std::mutex mu;
   Lane lane[LANES];
   unsigned long long submits = 0;
+  cudaStream_t s_compute = nullptr;  // FIFO mode: the kernels of ALL lanes' submissions, one step after the other
+  GraphCache cgraphs;                // their graphs (kernels only; the copies around them are plain async copies)
 };
 
 static HostPipe* pipe_for(int dev) {
@@ -86,6 +94,7 @@ static int pipe_init(Lane& hp, int hp_dev) {
   PS_CUDA(cudaStreamCreateWithFlags(&hp.s_launch, cudaStreamNonBlocking));
   PS_CUDA(cudaEventCreateWithFlags(&hp.ev_last, cudaEventDisableTiming));
   PS_CUDA(cudaEventCreateWithFlags(&hp.ev_sub, cudaEventDisableTiming));
+  PS_CUDA(cudaEventCreateWithFlags(&hp.ev_cmp, cudaEventDisableTiming));
   PS_CUDA(cudaEventCreateWithFlags(&hp.ev_begin, cudaEventDisableTiming));
   PS_CUDA(cudaEventCreateWithFlags(&hp.ev_end, cudaEventDisableTiming));
   PS_CUDA(cudaMalloc(&hp.d_sums, 12 * sizeof(double)));
@@ -236,6 +245,87 @@ static int enqueue_pipeline(Lane& hp, const PipeArgs& a, cudaStream_t origin) {
   return PS_OK;
 }
 
+// Submission in FIFO mode.  With several steps in flight the chunked multi-stream graph of enqueue_pipeline is the wrong
+// shape: its purpose — overlapping the copies of a step with its own kernels — is now served by the OTHER steps, while
+// its price stays (three small forward launches instead of one: 0.375 ms of kernels per C1 step instead of 0.33), and
+// kernels of different steps that run side by side delay each other's downloads.  Here a step is three stages:
+//     uploads (lane's copy stream)  ->  kernels (ONE stream shared by all lanes: strictly one step after the other,
+//     each with the whole GPU, replayed as a graph)  ->  downloads (lane's copy stream)
+// chained by events, so the copy engines work on the neighbouring steps while the SMs work on this one.
+static int submit_fifo(HostPipe& P, Lane& L, const PipeArgs& a, int channel, cudaStream_t caller) {
+#define COPY(...) PS_CUDA(cudaMemcpyAsync(__VA_ARGS__))
+  if (!P.s_compute) PS_CUDA(cudaStreamCreateWithFlags(&P.s_compute, cudaStreamNonBlocking));
+  char* base = static_cast<char*>(L.slot[0]);
+  float* d_x1 = reinterpret_cast<float*>(base + a.o_x1);
+  float* d_x2 = reinterpret_cast<float*>(base + a.o_x2);
+  float* d_d1 = reinterpret_cast<float*>(base + a.o_d1);
+  float* d_d2 = reinterpret_cast<float*>(base + a.o_d2);
+  int* d_i1 = reinterpret_cast<int*>(base + a.o_i1);
+  int* d_i2 = reinterpret_cast<int*>(base + a.o_i2);
+  float* d_gd1 = reinterpret_cast<float*>(base + a.o_gd1);
+  float* d_gd2 = reinterpret_cast<float*>(base + a.o_gd2);
+  float* d_g1 = reinterpret_cast<float*>(base + a.o_g1);
+  float* d_g2 = reinterpret_cast<float*>(base + a.o_g2);
+  const size_t c1 = (size_t)a.B * a.N, c2 = (size_t)a.B * a.M;
+
+  // uploads: behind the submitting stream's position and behind the lane's previous step (its slot is free again)
+  PS_CUDA(cudaEventRecord(L.ev_sub, caller));
+  PS_CUDA(cudaStreamWaitEvent(L.s_in, L.ev_sub, 0));
+  PS_CUDA(cudaStreamWaitEvent(L.s_in, L.ev_last, 0));
+  COPY(d_x1, a.xyz1, c1 * 12, cudaMemcpyHostToDevice, L.s_in);
+  COPY(d_x2, a.xyz2, c2 * 12, cudaMemcpyHostToDevice, L.s_in);
+  if (a.with_bwd) {
+    COPY(d_gd1, a.graddist1, c1 * 4, cudaMemcpyHostToDevice, L.s_in);
+    COPY(d_gd2, a.graddist2, c2 * 4, cudaMemcpyHostToDevice, L.s_in);
+  }
+  PS_CUDA(cudaEventRecord(L.ev_in[0], L.s_in));
+
+  // kernels: forward (+ sums from its epilogue), backward, the exchange on the lane's channel
+  PS_CUDA(cudaStreamWaitEvent(P.s_compute, L.ev_in[0], 0));
+  auto kernels = [&](cudaStream_t s) -> int {
+    if (int rc = chamfer_fwd_impl(d_x1, d_x2, d_d1, d_d2, d_i1, d_i2, a.h_sums ? L.d_sums : nullptr, nullptr, a.B, a.N, a.M, a.dev, s,
+                                  "ps_chamfer_host_submit"))
+      return rc;
+    if (a.with_bwd)
+      if (int rc = ps_chamfer_bwd(d_x1, d_x2, d_gd1, d_gd2, d_i1, d_i2, d_g1, d_g2, a.B, a.N, a.M, a.dev, s)) return rc;
+    if (a.h_sums && a.comm) return comm_allreduce_launch(a.comm, channel, L.d_sums, L.d_sums + 6, 6, s);
+    return PS_OK;
+  };
+  bool use_graph = true;
+  if (const char* e = getenv("PS_HOST_GRAPH")) use_graph = atoi(e) != 0;
+  int rc = PS_OK;
+  GraphCache::Entry* hit = nullptr;
+  if (use_graph) {
+    GraphKey key;
+    key.ptr(base);
+    key.begin_shape();
+    key.ptr(a.comm);
+    key.val(a.B); key.val(a.N); key.val(a.M); key.val(a.with_bwd); key.val(a.h_sums != nullptr); key.val(channel);
+    hit = P.cgraphs.get(key, L.s_cap, kernels, &rc);
+    if (rc != PS_OK) return rc;
+  }
+  if (hit) {
+    PS_CUDA(cudaGraphLaunch(hit->exec, P.s_compute));
+    launch_counter() += hit->kernels;
+  } else if (int rc2 = kernels(P.s_compute)) {
+    return rc2;
+  }
+  PS_CUDA(cudaEventRecord(L.ev_cmp, P.s_compute));
+
+  // downloads
+  PS_CUDA(cudaStreamWaitEvent(L.s_out, L.ev_cmp, 0));
+  if (a.dist1) COPY(a.dist1, d_d1, c1 * 4, cudaMemcpyDeviceToHost, L.s_out);
+  if (a.dist2) COPY(a.dist2, d_d2, c2 * 4, cudaMemcpyDeviceToHost, L.s_out);
+  if (a.idx1) COPY(a.idx1, d_i1, c1 * 4, cudaMemcpyDeviceToHost, L.s_out);
+  if (a.idx2) COPY(a.idx2, d_i2, c2 * 4, cudaMemcpyDeviceToHost, L.s_out);
+  if (a.with_bwd && a.gradxyz1) COPY(a.gradxyz1, d_g1, c1 * 12, cudaMemcpyDeviceToHost, L.s_out);
+  if (a.with_bwd && a.gradxyz2) COPY(a.gradxyz2, d_g2, c2 * 12, cudaMemcpyDeviceToHost, L.s_out);
+  if (a.h_sums) COPY(a.h_sums, L.d_sums + (a.comm ? 6 : 0), 6 * sizeof(double), cudaMemcpyDeviceToHost, L.s_out);
+  PS_CUDA(cudaEventRecord(L.ev_last, L.s_out));
+  return PS_OK;
+#undef COPY
+}
+
 static void drop_graphs(Lane& hp) { hp.graphs.drop(); }
 
 }  // namespace ps
@@ -268,7 +358,12 @@ static int host_pipeline_call(const float* xyz1, const float* xyz2, float* dist1
     *ticket = (long long)(((++hp.calls) << 8) | (unsigned)(li + 1));
   }
 
+  // submissions: FIFO mode (one chunk, kernels of all lanes on one stream) unless PS_HOST_ASYNC=lanes asks for the
+  // chunked multi-stream graph per lane
+  bool fifo = ticket != nullptr;
+  if (const char* e = getenv("PS_HOST_ASYNC")) fifo = fifo && e[0] != 'l';
   PipeArgs a;
+  if (fifo) chunk = B;
   make_plan(B, chunk, a.sizes, &a.nchunks, &chunk);
   a.xyz1 = xyz1; a.xyz2 = xyz2; a.graddist1 = graddist1; a.graddist2 = graddist2;
   a.dist1 = dist1; a.dist2 = dist2; a.gradxyz1 = gradxyz1; a.gradxyz2 = gradxyz2;
@@ -300,6 +395,8 @@ static int host_pipeline_call(const float* xyz1, const float* xyz2, float* dist1
     for (int i = 0; i < SLOTS; i++) PS_CUDA(cudaMalloc(&hp.slot[i], off));
     hp.slot_bytes = off;
   }
+
+  if (fifo) return submit_fifo(*hpp, hp, a, a.channel, static_cast<cudaStream_t>(stream_));
 
   bool use_graph = true;
   if (const char* e = getenv("PS_HOST_GRAPH")) use_graph = atoi(e) != 0;
