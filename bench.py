@@ -461,7 +461,8 @@ def run_ours(args):
            "steps_in_flight": DEPTH, "host_buffer_sets": OSETS, "chunk": args.e2e_chunk, "numa_bound_cpus": (len(numa_cpus) if numa_cpus else None),
            "loss_readback": {"value": round(pairs_per_step * world / (loss_ms * 1e-3) / 1e9, 2), "ms_per_step": round(loss_ms, 4),
                              "d2h_bytes_per_step": 48,
-                             "note": "chamfer_host_step: gradients stay in device buffers for the optimizer, only the six loss sums are read back"}}
+                             "note": "chamfer_host_step, ONE CALL AT A TIME (compare with per_call, not with value): gradients stay in device buffers "
+                                     "for the optimizer, only the six loss sums are read back"}}
     if world == 1 and not args.quick:
         # a loader that never reuses a buffer: 2*cache-size address sets, every call re-captures and RETARGETS a cached graph
         nfresh = 16
@@ -480,7 +481,7 @@ def run_ours(args):
         e2e["fresh_buffers"] = {"ms_per_step": round(sum(fr) / len(fr), 4), "address_sets": nfresh,
                                 "graph_updates": st1["updates"] - st0["updates"], "graph_instantiations": st1["instantiations"] - st0["instantiations"],
                                 "note": "a new host-buffer address set every step: the call is re-captured and the cached executable "
-                                        "updated in place (cudaGraphExecUpdate); full readback as in e2e.value"}
+                                        "updated in place (cudaGraphExecUpdate); full readback, one call at a time (compare with per_call)"}
         ser = timed_pipelined(e2e_serial, max(3, args.steps // 4), 3, flush)
         e2e["serial_ms_per_step"] = round(sum(ser) / len(ser), 4)
         e2e["serial_note"] = "same work as copy-in, device entry points, copy-out on one stream (no overlap)"
