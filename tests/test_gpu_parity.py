@@ -212,6 +212,37 @@ def test_chamfer_host_async_mixed_shapes_many_steps():
     assert checked == len(order)
 
 
+def test_chamfer_host_async_pageable_buffers_small_clouds_and_sums():
+    """Corners of the asynchronous pair: pageable (non-pinned) host tensors (the copies then stage synchronously, the
+    results must still be right), clouds small enough for the two-pass forward kernel, loss sums with and without the
+    backward, and both submission modes (PS_HOST_ASYNC=lanes: the chunked graph per lane)."""
+    import os
+    g = torch.Generator().manual_seed(31)
+    for mode in ("fifo", "lanes"):
+        os.environ["PS_HOST_ASYNC"] = mode
+        try:
+            for B, N, M, bwd in ((3, 200, 150, True), (2, 64, 900, False), (4, 1024, 3000, True)):
+                a, b = make_cloud(g, B, N), make_cloud(g, B, M)  # pageable
+                ga, gb = torch.randn(B, N, generator=g), torch.randn(B, M, generator=g)
+                ws = torch.empty(6, dtype=torch.float64).pin_memory()
+                want = ps.chamfer_host(a, b, ga if bwd else None, gb if bwd else None, sums_out=ws)
+                s1 = torch.empty(6, dtype=torch.float64)  # pageable as well
+                s2 = torch.empty(6, dtype=torch.float64).pin_memory()
+                st1 = ps.chamfer_host_async(a, b, ga if bwd else None, gb if bwd else None, sums_out=s1)
+                st2 = ps.chamfer_host_async(a.pin_memory(), b.pin_memory(), sums_out=s2)
+                o1, o2 = st1.synchronize(), st2.synchronize()
+                for h, w in zip(o1[:4], want[:4]):
+                    assert torch.equal(h, w)
+                for h, w in zip(o2[:4], want[:4]):
+                    assert torch.equal(h, w)
+                if bwd:
+                    assert_close_rel(o1[4].numpy(), want[4].numpy(), what="gradxyz1 (async, pageable)")
+                    assert_close_rel(o1[5].numpy(), want[5].numpy(), what="gradxyz2 (async, pageable)")
+                assert torch.allclose(s1, ws, rtol=1e-13, atol=0) and torch.allclose(s2, ws, rtol=1e-13, atol=0)
+        finally:
+            os.environ.pop("PS_HOST_ASYNC", None)
+
+
 def test_chamfer_host_rejects_device_tensors_and_bad_shapes():
     a = torch.zeros(2, 8, 3, device=DEV)
     with pytest.raises(ps.PointSeaError):
