@@ -263,17 +263,55 @@ def combine_chamfer(means, name, sqrt=True):
     return (m1 + m2) / 2 if sqrt else m1 + m2
 
 
-def _sharded_terms(pcds_pred, gt, sqrt, partial=None):
+_SIDE_STREAMS = {}
+
+
+def _side_stream(device):
+    """One cached side stream per device for work that is independent of the main stream's next kernels."""
+    key = torch.device(device).index
+    if key not in _SIDE_STREAMS:
+        _SIDE_STREAMS[key] = torch.cuda.Stream(device=device)
+    return _SIDE_STREAMS[key]
+
+
+def _sharded_terms(pcds_pred, gt, sqrt, partial=None, overlap_fps=None):
+    """The Chamfer terms of get_loss / get_loss_PM on this rank's shard, as named (sum, count) pairs.
+
+    The two FPS calls that thin the ground truth (gt -> |P1| -> |Pc| points, utils/loss_utils.py:40-41) are a serial
+    chain of ~2500 latency-bound iterations on a quarter of the SMs' issue slots, and the largest Chamfer term
+    (P2 vs the full gt) does not depend on them: with `overlap_fps` (default: on CUDA, outside stream capture) the FPS
+    chain runs on a side stream while the main stream computes that term.  Values are unchanged."""
     from .chamfer import chamfer_3DFunction
     from .pointnet2_utils import fps_subsample
 
     Pc, P1, P2 = pcds_pred
-    gt_1 = fps_subsample(gt, P1.shape[1])
-    gt_c = fps_subsample(gt_1, Pc.shape[1])
+    if overlap_fps is None:  # PS_LOSS_OVERLAP=0 keeps everything on the current stream (A/B measurements)
+        import os
+        overlap_fps = gt.is_cuda and os.environ.get("PS_LOSS_OVERLAP", "1") != "0" and not torch.cuda.is_current_stream_capturing()
     sums = LossSums(gt.device)
-    for name, (p, q) in {"cdc": (Pc, gt_c), "cd1": (P1, gt_1), "cd2": (P2, gt)}.items():
+
+    def term(name, p, q):
         d1, d2, _, _ = chamfer_3DFunction.apply(p.contiguous(), q.contiguous())
         chamfer_loss_terms(sums, name, d1, d2, sqrt)
+
+    if overlap_fps:
+        cur, side = torch.cuda.current_stream(gt.device), _side_stream(gt.device)
+        side.wait_stream(cur)
+        with torch.cuda.stream(side), torch.no_grad():
+            gt_1 = fps_subsample(gt, P1.shape[1])
+            gt_c = fps_subsample(gt_1, Pc.shape[1])
+        term("cd2", P2, gt)  # meanwhile, on the main stream
+        cur.wait_stream(side)
+        for t in (gt_1, gt_c):
+            t.record_stream(cur)
+        term("cdc", Pc, gt_c)
+        term("cd1", P1, gt_1)
+    else:
+        gt_1 = fps_subsample(gt, P1.shape[1])
+        gt_c = fps_subsample(gt_1, Pc.shape[1])
+        term("cdc", Pc, gt_c)
+        term("cd1", P1, gt_1)
+        term("cd2", P2, gt)
     if partial is not None:  # chamfer_single_side(_sqrt)(partial, P2): the dist1 side only (utils/loss_utils.py:22-31)
         d1, _, _, _ = chamfer_3DFunction.apply(partial.contiguous(), P2.contiguous())
         sums.add("pm.d1", torch.sqrt(d1) if sqrt else d1)
