@@ -374,6 +374,120 @@ __global__ void __launch_bounds__(T, 1) fps_kernel(const FpsArgs a) {
   if (CLUSTER) { cluster_arrive_release(); cluster_wait_acquire(); }  // no CTA exits while peers may still write to it
 }
 
+// ------------------------------------------------------------------------------------------------
+// Small clouds (N <= 4096: the FPS calls inside the models — 2048 -> 512, 512 -> 128, sample_and_group_knn): ONE CTA
+// of T = 128 .. 512 threads per cloud with a lean arg-max.  fps_kernel<PP,T,0> pays ~565-725 cycles per iteration before
+// any distance work (two REDUX + ballot, five payload shuffles, a 32-byte entry per warp, a second round of the same
+// after the barrier); here a warp publishes only (distance bits, rank) — 8 bytes — and the winner's coordinates are
+// looked up in the CTA's own shared-memory copy of the cloud by its rank, as fps_pruned_kernel does: two REDUX, one
+// store, one barrier, one load, two REDUX, three broadcast loads.  Same dealing of points to threads in rank order,
+// same selection (distance desc, rank asc), same -1 convention for skipped / padding points as fps_kernel.
+template <int PP, int T>
+__global__ void __launch_bounds__(T, 1) fps_small_kernel(const FpsArgs a) {
+  constexpr int P = 2 * PP;
+  constexpr int WARPS = T / 32;
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  float* px = reinterpret_cast<float*>(smem_raw);  // [P][T]: point i of thread t at i * T + t
+  float* py = px + P * T;
+  float* pz = py + P * T;
+  __shared__ int2 slots[2][WARPS];
+  const int b = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  if (a.run_flag && __ldg(a.run_flag + b) == 0) return;
+  const int N = a.N;
+  const float* cloud = a.xyz + (size_t)b * N * 3;
+  int* out = a.idx + (size_t)b * a.npoint;
+  float* oxyz = a.new_xyz ? a.new_xyz + (size_t)b * a.npoint * 3 : nullptr;
+  const unsigned rank0 = (unsigned)tid * P;  // this thread owns ranks [rank0, rank0 + P)
+  const unsigned R = (unsigned)a.nper << a.L;
+
+  u64 x2[PP], y2[PP], z2[PP];
+  float t[P];
+#pragma unroll
+  for (int i = 0; i < P; i++) {
+    float xv = 0.f, yv = 0.f, zv = 0.f;
+    t[i] = -1.0f;
+    if (rank0 + i < R) {
+      const int k = fps_rank_to_k(rank0 + i, a.L, a.nper);
+      if (k < N) {
+        xv = __ldg(cloud + (size_t)k * 3 + 0);
+        yv = __ldg(cloud + (size_t)k * 3 + 1);
+        zv = __ldg(cloud + (size_t)k * 3 + 2);
+        t[i] = ((double)dist2_ref(xv, yv, zv) <= 1e-3) ? -1.0f : 1e10f;
+      }
+    }
+    px[i * T + tid] = xv; py[i * T + tid] = yv; pz[i * T + tid] = zv;
+    if (i & 1) {
+      x2[i / 2] = pack2(lo2(x2[i / 2]), xv); y2[i / 2] = pack2(lo2(y2[i / 2]), yv); z2[i / 2] = pack2(lo2(z2[i / 2]), zv);
+    } else {
+      x2[i / 2] = pack2(xv, 0.f); y2[i / 2] = pack2(yv, 0.f); z2[i / 2] = pack2(zv, 0.f);
+    }
+  }
+  const float p0x = __ldg(cloud + 0), p0y = __ldg(cloud + 1), p0z = __ldg(cloud + 2);
+  float lx = p0x, ly = p0y, lz = p0z;
+  if (tid == 0 && a.npoint > 0) out[0] = 0;
+  __syncthreads();
+
+  for (int j = 1; j < a.npoint; j++) {
+    const u64 nlx = pack2(-lx, -lx), nly = pack2(-ly, -ly), nlz = pack2(-lz, -lz);
+    float run[PP];
+    float best = -1.0f;
+#pragma unroll
+    for (int i = 0; i < PP; i++) {
+      const u64 d = dist2x2(x2[i], y2[i], z2[i], nlx, nly, nlz);
+      t[2 * i] = fminf(lo2(d), t[2 * i]);
+      t[2 * i + 1] = fminf(hi2(d), t[2 * i + 1]);  // padding / skipped points stay at -1
+      best = max3(best, t[2 * i], t[2 * i + 1]);
+      run[i] = best;
+    }
+    int bp = 0;
+    float e0 = t[0];
+#pragma unroll
+    for (int i = PP - 1; i >= 0; i--)
+      if (run[i] == best) { bp = i; e0 = t[2 * i]; }
+    const unsigned rk = rank0 + (unsigned)(2 * bp + (e0 == best ? 0 : 1));
+    const int tb = __float_as_int(best);
+    const int wm = __reduce_max_sync(0xffffffffu, tb);
+    const unsigned wk = __reduce_min_sync(0xffffffffu, tb == wm ? rk : 0xffffffffu);
+    const int buf = j & 1;
+    if (lane == 0) slots[buf][warp] = make_int2(wm, (int)wk);
+    __syncthreads();
+    const int2 sv = lane < WARPS ? slots[buf][lane] : make_int2((int)0x80000000, -1);
+    const int gm = __reduce_max_sync(0xffffffffu, sv.x);
+    unsigned gk = __reduce_min_sync(0xffffffffu, sv.x == gm ? (unsigned)sv.y : 0xffffffffu);
+    if (gm < 0) {  // no eligible point anywhere: the reference's tree returns thread 0's besti = 0
+      gk = 0xffffffffu;
+      lx = p0x; ly = p0y; lz = p0z;
+    } else {
+      const unsigned wt = gk / (unsigned)P, wi = gk % (unsigned)P;
+      lx = px[wi * T + wt]; ly = py[wi * T + wt]; lz = pz[wi * T + wt];
+    }
+    if (tid == 0) out[j] = (int)gk;  // raw rank; turned into the point index after the loop
+  }
+  __syncthreads();
+  for (int j = tid; j < a.npoint; j += T) {
+    const unsigned gk = j ? (unsigned)out[j] : 0u;
+    int k = 0;
+    float ox = p0x, oy = p0y, oz = p0z;
+    if (j && gk != 0xffffffffu) {
+      k = fps_rank_to_k(gk, a.L, a.nper);
+      const unsigned wt = gk / (unsigned)P, wi = gk % (unsigned)P;
+      ox = px[wi * T + wt]; oy = py[wi * T + wt]; oz = pz[wi * T + wt];
+    }
+    out[j] = k;
+    if (oxyz) { oxyz[j * 3 + 0] = ox; oxyz[j * 3 + 1] = oy; oxyz[j * 3 + 2] = oz; }
+  }
+}
+
+template <int PP, int T>
+static int launch_fps_small(const FpsArgs& a, int B, cudaStream_t stream) {
+  const size_t smem = (size_t)3 * 2 * PP * T * sizeof(float);
+  auto kern = fps_small_kernel<PP, T>;
+  if (smem + 1024 > 48 * 1024) PS_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));  // + static slots
+  kern<<<B, T, smem, stream>>>(a);
+  PS_LAUNCH_CHECK();
+  return PS_OK;
+}
+
 // Generic fallback for clouds too large for the register-resident kernel: one CTA per cloud,
 // running min distances in a global scratch array (still the exact reference order).
 constexpr int FPS_GT = 512;
@@ -859,6 +973,22 @@ extern "C" int ps_fps_sample(const float* xyz, int* idx, float* new_xyz, int B, 
       PS_LAUNCH_CHECK();
       if (!q.check) return prune_mem.release();
       a.run_flag = q.flag;
+    }
+  }
+
+  // small clouds: one CTA per cloud with the lean arg-max (fps_small_kernel); PS_FPS_SMALL=0 keeps the cluster planner
+  {
+    const long long R = (long long)a.nper << a.L;
+    bool small = R <= 4096 && a.run_flag == nullptr;
+    if (const char* e = getenv("PS_FPS_SMALL")) small = small && atoi(e) != 0;
+    if (getenv("PS_FPS_CLUSTER") || getenv("PS_FPS_THREADS")) small = false;  // a forced plan means the cluster kernels
+    if (small) {
+      const int T = R <= 1024 ? 128 : (R <= 2048 ? 256 : 512);
+      int PP = 1;
+      while (2ll * PP * T < R) PP *= 2;
+      if (T == 128) return PP == 1 ? launch_fps_small<1, 128>(a, B, stream) : (PP == 2 ? launch_fps_small<2, 128>(a, B, stream) : launch_fps_small<4, 128>(a, B, stream));
+      if (T == 256) return PP <= 2 ? launch_fps_small<2, 256>(a, B, stream) : launch_fps_small<4, 256>(a, B, stream);
+      return PP <= 2 ? launch_fps_small<2, 512>(a, B, stream) : launch_fps_small<4, 512>(a, B, stream);
     }
   }
 
