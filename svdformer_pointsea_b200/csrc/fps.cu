@@ -375,6 +375,186 @@ __global__ void __launch_bounds__(T, 1) fps_kernel(const FpsArgs a) {
 }
 
 // ------------------------------------------------------------------------------------------------
+// Lean exchange for small clusters (2-4 CTAs, N <= 16384): fps_kernel MODE 1 with 8-byte messages.
+//
+// In MODE 1 a warp's candidate travels with its coordinates (32 bytes, two st.async.v4 per destination, five payload
+// shuffles before, two LDS.128 + four shuffles after the final reduce), because a CTA only holds its own points.  A
+// 16384-point cloud is 192 KB: every CTA of the cluster can hold ALL of it in shared memory, ordered by rank — then a
+// candidate is just (distance bits, rank), one st.async.v2 per destination, and the winner's coordinates are a local
+// broadcast load.  Same protocol otherwise (two slot buffers, byte-counting mbarrier on the destination, every warp
+// reduces the E candidates redundantly), same dealing of ranks to threads, same selection order.
+__device__ __forceinline__ void st_async_v2(unsigned raddr, unsigned rbar, unsigned a, unsigned b) {
+  asm volatile("st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.v2.b32 [%0], {%1, %2}, [%3];"
+               ::"r"(raddr), "r"(a), "r"(b), "r"(rbar) : "memory");
+}
+
+template <int PP, int T>
+__global__ void __launch_bounds__(T, 1) fps_lean_kernel(const FpsArgs a, int Rpad) {
+  constexpr int P = 2 * PP;
+  constexpr int WARPS = T / 32;
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  float* ax = reinterpret_cast<float*>(smem_raw);  // the whole cloud by rank
+  float* ay = ax + Rpad;
+  float* az = ay + Rpad;
+  u64* mbar = reinterpret_cast<u64*>(az + Rpad);
+  int2* slots = reinterpret_cast<int2*>(mbar + 2);  // [2][E]
+  const unsigned C = cluster_nctarank();
+  const unsigned crank = cluster_ctarank();
+  const int b = (int)cluster_id_x();
+  if (a.run_flag && __ldg(a.run_flag + b) == 0) return;  // the whole cluster leaves together: nothing was armed yet
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int E = WARPS * (int)C;
+  const int N = a.N;
+  const float* cloud = a.xyz + (size_t)b * N * 3;
+  int* out = a.idx + (size_t)b * a.npoint;
+  float* oxyz = a.new_xyz ? a.new_xyz + (size_t)b * a.npoint * 3 : nullptr;
+  const int g = (int)crank * T + tid;
+  const unsigned rank0 = (unsigned)g * P;
+  const unsigned R = (unsigned)a.nper << a.L;
+
+  for (unsigned r = tid; r < (unsigned)Rpad; r += T) {
+    float xv = 0.f, yv = 0.f, zv = 0.f;
+    if (r < R) {
+      const int k = fps_rank_to_k(r, a.L, a.nper);
+      if (k < N) { xv = __ldg(cloud + (size_t)k * 3 + 0); yv = __ldg(cloud + (size_t)k * 3 + 1); zv = __ldg(cloud + (size_t)k * 3 + 2); }
+    }
+    ax[r] = xv; ay[r] = yv; az[r] = zv;
+  }
+  if (tid == 0) {
+    fps_mbar_init(smem_u32(&mbar[0]), 1);
+    fps_mbar_init(smem_u32(&mbar[1]), 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    fps_mbar_expect_tx(smem_u32(&mbar[0]), (unsigned)E * 8u);
+    fps_mbar_expect_tx(smem_u32(&mbar[1]), (unsigned)E * 8u);
+  }
+  __syncthreads();
+  u64 x2[PP], y2[PP], z2[PP];
+  float t[P];
+#pragma unroll
+  for (int i = 0; i < P; i++) {
+    const unsigned r = rank0 + i;
+    float xv = 0.f, yv = 0.f, zv = 0.f;
+    t[i] = -1.0f;
+    if (r < R && fps_rank_to_k(r, a.L, a.nper) < N) {
+      xv = ax[r]; yv = ay[r]; zv = az[r];
+      t[i] = ((double)dist2_ref(xv, yv, zv) <= 1e-3) ? -1.0f : 1e10f;
+    }
+    if (i & 1) {
+      x2[i / 2] = pack2(lo2(x2[i / 2]), xv); y2[i / 2] = pack2(lo2(y2[i / 2]), yv); z2[i / 2] = pack2(lo2(z2[i / 2]), zv);
+    } else {
+      x2[i / 2] = pack2(xv, 0.f); y2[i / 2] = pack2(yv, 0.f); z2[i / 2] = pack2(zv, 0.f);
+    }
+  }
+  const float p0x = __ldg(cloud + 0), p0y = __ldg(cloud + 1), p0z = __ldg(cloud + 2);
+  float lx = p0x, ly = p0y, lz = p0z;
+  if (g == 0 && a.npoint > 0) out[0] = 0;
+  cluster_arrive_release(); cluster_wait_acquire();  // peers resident, mbarriers armed
+  // lane c pushes the warp's candidate to slot (crank*WARPS+warp) of CTA c: the remote addresses of both buffers are
+  // loop constants
+  unsigned ra[2] = {0u, 0u}, rb[2] = {0u, 0u};
+  if ((unsigned)lane < C) {
+    const unsigned e = crank * WARPS + warp;
+#pragma unroll
+    for (int u = 0; u < 2; u++) {
+      ra[u] = mapa_shared(smem_u32(&slots[u * E + e]), (unsigned)lane);
+      rb[u] = mapa_shared(smem_u32(&mbar[u]), (unsigned)lane);
+    }
+  }
+
+  for (int j = 1; j < a.npoint; j++) {
+    const u64 nlx = pack2(-lx, -lx), nly = pack2(-ly, -ly), nlz = pack2(-lz, -lz);
+    float run[PP];
+    float best = -1.0f;
+#pragma unroll
+    for (int i = 0; i < PP; i++) {
+      const u64 d = dist2x2(x2[i], y2[i], z2[i], nlx, nly, nlz);
+      t[2 * i] = fminf(lo2(d), t[2 * i]);
+      t[2 * i + 1] = fminf(hi2(d), t[2 * i + 1]);  // padding / skipped points stay at -1
+      best = max3(best, t[2 * i], t[2 * i + 1]);
+      run[i] = best;
+    }
+    int bp = 0;
+    float e0 = t[0];
+#pragma unroll
+    for (int i = PP - 1; i >= 0; i--)
+      if (run[i] == best) { bp = i; e0 = t[2 * i]; }
+    const unsigned rk = rank0 + (unsigned)(2 * bp + (e0 == best ? 0 : 1));
+    const int tb = __float_as_int(best);
+    const int wm = __reduce_max_sync(0xffffffffu, tb);
+    const unsigned wk = __reduce_min_sync(0xffffffffu, tb == wm ? rk : 0xffffffffu);
+    const int buf = j & 1;
+    if ((unsigned)lane < C) st_async_v2(ra[buf], rb[buf], (unsigned)wm, wk);
+    const unsigned parity = (unsigned)((j - 1) >> 1) & 1u;
+    while (!fps_mbar_try_wait(smem_u32(&mbar[buf]), parity)) {}
+    if (tid == 0) fps_mbar_expect_tx(smem_u32(&mbar[buf]), (unsigned)E * 8u);  // re-arm for iteration j + 2 (see fps_kernel)
+    int2 sv = lane < E ? slots[buf * E + lane] : make_int2((int)0x80000000, -1);
+    if (E > 32) {  // 16 CTAs of 128 threads: two candidates per lane
+      const int2 s2 = lane + 32 < E ? slots[buf * E + 32 + lane] : make_int2((int)0x80000000, -1);
+      if (fps_better(s2.x, (unsigned)s2.y, sv.x, (unsigned)sv.y)) sv = s2;
+    }
+    const int gm = __reduce_max_sync(0xffffffffu, sv.x);
+    unsigned gk = __reduce_min_sync(0xffffffffu, sv.x == gm ? (unsigned)sv.y : 0xffffffffu);
+    if (gm < 0) {  // no eligible point anywhere: the reference's tree returns thread 0's besti = 0
+      gk = 0xffffffffu;
+      lx = p0x; ly = p0y; lz = p0z;
+    } else {
+      lx = ax[gk]; ly = ay[gk]; lz = az[gk];
+    }
+    if (g == 0) out[j] = (int)gk;  // raw rank; turned into the point index after the loop
+  }
+  cluster_arrive_release(); cluster_wait_acquire();  // no CTA exits while peers may still write to it
+  if (crank == 0) {
+    __syncthreads();
+    for (int j = tid; j < a.npoint; j += T) {
+      const unsigned gk = j ? (unsigned)out[j] : 0u;
+      int k = 0;
+      float ox = p0x, oy = p0y, oz = p0z;
+      if (j && gk != 0xffffffffu) { k = fps_rank_to_k(gk, a.L, a.nper); ox = ax[gk]; oy = ay[gk]; oz = az[gk]; }
+      out[j] = k;
+      if (oxyz) { oxyz[j * 3 + 0] = ox; oxyz[j * 3 + 1] = oy; oxyz[j * 3 + 2] = oz; }
+    }
+  }
+}
+
+template <int PP, int T>
+static int launch_fps_lean(const FpsArgs& a, int B, int C, cudaStream_t stream) {
+  const int R = a.nper << a.L;
+  const int Rpad = (R + 3) & ~3;
+  const int E = (T / 32) * C;
+  const size_t smem = (size_t)3 * Rpad * sizeof(float) + 16 + (size_t)2 * E * sizeof(int2);
+  auto kern = fps_lean_kernel<PP, T>;
+  PS_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  if (C > 8) PS_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(B * C);
+  cfg.blockDim = dim3(T);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = stream;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeClusterDimension;
+  at[0].val.clusterDim.x = C;
+  at[0].val.clusterDim.y = 1;
+  at[0].val.clusterDim.z = 1;
+  cfg.attrs = at;
+  cfg.numAttrs = 1;
+  PS_CUDA(cudaLaunchKernelEx(&cfg, kern, a, Rpad));
+  PS_LAUNCH_CHECK();
+  return PS_OK;
+}
+
+template <int T>
+static int dispatch_lean(int PP, const FpsArgs& a, int B, int C, cudaStream_t s) {
+  switch (PP) {
+    case 1: return launch_fps_lean<1, T>(a, B, C, s);
+    case 2: return launch_fps_lean<2, T>(a, B, C, s);
+    case 4: return launch_fps_lean<4, T>(a, B, C, s);
+    case 8: return launch_fps_lean<8, T>(a, B, C, s);
+    case 16: return launch_fps_lean<16, T>(a, B, C, s);
+  }
+  return set_error(PS_ERR_UNSUPPORTED, "ps_fps: no kernel for %d point pairs per thread", PP);
+}
+
+// ------------------------------------------------------------------------------------------------
 // Small clouds (N <= 4096: the FPS calls inside the models — 2048 -> 512, 512 -> 128, sample_and_group_knn): ONE CTA
 // of T = 128 .. 512 threads per cloud with a lean arg-max.  fps_kernel<PP,T,0> pays ~565-725 cycles per iteration before
 // any distance work (two REDUX + ballot, five payload shuffles, a 32-byte entry per warp, a second round of the same
@@ -846,7 +1026,7 @@ static int dispatch_pp(int PP, const FpsArgs& a, int B, int C, cudaStream_t s) {
   return set_error(PS_ERR_UNSUPPORTED, "ps_fps: no kernel for %d point pairs per thread", PP);
 }
 
-struct FpsPlan { int C, T, PP; };
+struct FpsPlan { int C, T, PP; double cost; };  // cost: modelled SM cycles per iteration, waves included
 
 // How many clusters of `c` CTAs (one CTA per SM, as every fps_kernel configuration runs) the device
 // keeps resident at once: clusters must sit inside one GPC, so this is less than SMs / c for the
@@ -893,13 +1073,28 @@ static int cluster_capacity(int dev, int c, int nsm) {
 //   C=4 T=128: 800 + 16.7 PP     C=4 T=256: 860 + 33 PP
 //   C=8      : (T/128) * (13 PP + 90) + 940   (two-level exchange; B=4 N=16384 measured 1132 cycles at PP=8)
 //   C=16     : (T/128) * (13 PP + 90) + 1300  (only reachable when the cloud needs 16 CTAs)
-static double fps_iter_cost(int c, int t, int pp) {
+// Lean 8-byte exchange (fps_lean_kernel; clouds that fit every CTA's shared memory, N <= 16384; second session of round
+// 2, tools/fps_sweep.sh): C=2: 550 + 20 PP, C=4: 560 + 20 PP (PP=16: 880 = 0.449 us; PP=8: 720 = 0.366 us),
+// C=8: 600 + 20 PP (PP=8: 757), C=16: 810 + 20 PP (PP=4: 892); T=256 doubles the per-pair term and adds ~70.
+static bool fps_lean_fits(int c, int t, long long R, bool poll) {
+  return c >= 2 && (t / 32) * c <= 64 && !poll && (size_t)3 * (size_t)R * sizeof(float) <= 200 * 1024;
+}
+static double fps_iter_cost(int c, int t, int pp, bool lean = false) {
+  if (lean) {
+    const double base = c == 2 ? 550.0 : (c == 4 ? 560.0 : (c == 8 ? 600.0 : 810.0));
+    return base + (t / 128) * 20.0 * pp + (t == 256 ? 70.0 : 0.0);
+  }
   if (c == 1) return t == 128 ? 565.0 + 23.5 * pp : 725.0 + 43.0 * pp;
   if (c == 2) return t == 128 ? 758.0 + 19.7 * pp : 800.0 + 38.0 * pp;
   if (c == 4) return t == 128 ? 800.0 + 16.7 * pp : 860.0 + 33.0 * pp;
   return (t / 128) * (13.0 * pp + 90.0) + (c == 8 ? 940.0 : 1300.0);
 }
-static bool plan_fps(int B, int N, int L, int nper, int nsm, int dev, FpsPlan& best) {
+static bool fps_lean_enabled(bool poll) {
+  bool lean = !poll;
+  if (const char* e = getenv("PS_FPS_LEAN")) lean = lean && atoi(e) != 0;
+  return lean;
+}
+static bool plan_fps(int B, int N, int L, int nper, int nsm, int dev, bool lean_on, FpsPlan& best) {
   const long long R = (long long)nper << L;
   int force_c = 0, force_t = 0;
   if (const char* e = getenv("PS_FPS_CLUSTER")) force_c = atoi(e);
@@ -914,8 +1109,8 @@ static bool plan_fps(int B, int N, int L, int nper, int nsm, int dev, FpsPlan& b
       while ((long long)2 * pp * c * t < R) pp *= 2;
       if (pp > 16) continue;
       const int waves = ceil_div(B, cluster_capacity(dev, c, nsm));  // clusters that do not fit wait for a free GPC slot
-      const double cost = waves * fps_iter_cost(c, t, pp);
-      if (cost < best_cost - 1e-9) { best_cost = cost; best = {c, t, pp}; found = true; }
+      const double cost = waves * fps_iter_cost(c, t, pp, lean_on && fps_lean_fits(c, t, R, false));
+      if (cost < best_cost - 1e-9) { best_cost = cost; best = {c, t, pp, cost}; found = true; }
     }
   }
   return found;
@@ -943,18 +1138,24 @@ extern "C" int ps_fps_sample(const float* xyz, int* idx, float* new_xyz, int B, 
   a.L = ref_block_log2(N);
   a.nper = ceil_div(N, 1 << a.L);
 
+  // exchange for small clusters: tag polling on plain remote stores (MODE 3) or st.async + mbarrier (lean / MODE 1)
+  bool poll = false;
+  if (const char* e = getenv("PS_FPS_EXCHANGE")) poll = (e[0] == 'p');
+  const bool lean_on = fps_lean_enabled(poll);
   FpsPlan pl;
-  const bool planned = plan_fps(B, N, a.L, a.nper, nsm, dev, pl);
+  const bool planned = plan_fps(B, N, a.L, a.nper, nsm, dev, lean_on, pl);
 
   // Bucket-pruned single-CTA kernel (N <= 16384) where it wins: one SM per cloud at 0.6-0.85 us per iteration against
-  // 2-4 SMs per cloud at 0.55 us for the cluster kernel (B200, profiles/fps_pruned_r2.jsonl), i.e. when the batch needs
-  // two or more waves of clusters.  It leaves a per-cloud flag for the cluster kernel launched behind it, which only
-  // samples the clouds the pruning did not bite on.  PS_FPS_PRUNE=0 off, 1 forced for every N it accepts (no give-up).
+  // 2-4 SMs per cloud at 0.45 us for the cluster kernel (B200, profiles/fps_pruned_r2.jsonl), i.e. when the batch needs
+  // so many waves of clusters that the planner's best estimate exceeds the pruned kernel's ~1700 cycles per iteration.  It leaves a per-cloud flag for the cluster kernel launched behind it, which only
+  // samples the clouds the pruning did not bite on.  PS_FPS_PRUNE=0 off, 1 forced for every N it accepts (no give-up), 2 as 1
+  // but with the give-up path.
   ScratchGuard prune_mem;
   {
     int mode = -1;
     if (const char* e = getenv("PS_FPS_PRUNE")) mode = atoi(e);
-    const bool wins = planned && N >= 8192 && npoint >= 2 * FP_CHECK && ceil_div(B, cluster_capacity(dev, pl.C, nsm)) >= 2;
+    // ~1650 cycles per iteration for the pruned kernel on a uniform cube (fewer on surfaces), one SM per cloud
+    const bool wins = planned && N >= 8192 && npoint >= 2 * FP_CHECK && pl.cost > 1700.0 * ceil_div(B, nsm);
     const bool eligible = N <= FP_MAXN && npoint > 1 && (mode > 0 || (mode < 0 && wins));
     if (eligible) {
       const size_t inv_bytes = ((size_t)B * FP_MAXN * sizeof(unsigned short) + 255) & ~(size_t)255;
@@ -962,7 +1163,7 @@ extern "C" int ps_fps_sample(const float* xyz, int* idx, float* new_xyz, int B, 
       FpsPruneArgs q;
       q.inv = static_cast<unsigned short*>(prune_mem.ptr);
       q.flag = reinterpret_cast<int*>(static_cast<char*>(prune_mem.ptr) + inv_bytes);
-      q.check = (mode > 0 || npoint <= FP_CHECK + 1) ? 0 : 1;
+      q.check = (mode == 1 || npoint <= FP_CHECK + 1) ? 0 : 1;  // PS_FPS_PRUNE=2: pruned kernel first whatever the planner says, give-up path on
       // an unpruned scan updates every bucket every iteration; a working pruning touches all of them in the first
       // few iterations and a few per cent later (uniform cube: ~12 % of bucket x iteration pairs up to FP_CHECK)
       q.max_updates = (int)(0.5 * FP_CHECK * ceil_div(N, 32));
@@ -1000,9 +1201,9 @@ extern "C" int ps_fps_sample(const float* xyz, int* idx, float* new_xyz, int B, 
     PS_LAUNCH_CHECK();
     return temp_mem.release();
   }
-  // exchange for small clusters: tag polling on plain remote stores (MODE 3) or st.async + mbarrier (MODE 1)
-  bool poll = false;
-  if (const char* e = getenv("PS_FPS_EXCHANGE")) poll = (e[0] == 'p');
+  // lean 8-byte exchange where every CTA of the cluster can hold the whole cloud (PS_FPS_LEAN=0: the 32-byte messages)
+  if (lean_on && fps_lean_fits(pl.C, pl.T, (long long)a.nper << a.L, poll))
+    return pl.T == 128 ? dispatch_lean<128>(pl.PP, a, B, pl.C, stream) : dispatch_lean<256>(pl.PP, a, B, pl.C, stream);
   if (pl.T == 128) {
     if (pl.C == 1) return dispatch_pp<128, 0>(pl.PP, a, B, pl.C, stream);
     if (pl.C <= 4) return poll ? dispatch_pp<128, 3>(pl.PP, a, B, pl.C, stream) : dispatch_pp<128, 1>(pl.PP, a, B, pl.C, stream);

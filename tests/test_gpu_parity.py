@@ -382,9 +382,9 @@ def test_fps_bucket_pruned_kernel_vs_oracle(B, N, npoint, dup, no, monkeypatch):
 def test_fps_bucket_pruned_kernel_shapes_of_real_clouds_and_the_give_up_path(monkeypatch):
     """(1) points on a thin surface and in tight clusters (where the pruning bites hardest, and bucket boxes are
     degenerate in one axis); (2) clouds squeezed into one grid cell by a far outlier, or made of one repeated point:
-    forced, the pruned kernel ploughs on; by default (a batch of 150 clouds needs several waves of clusters, so the
-    launcher picks the pruned kernel) it gives up at its checkpoint and the cluster kernel behind it samples exactly
-    those clouds."""
+    forced (PS_FPS_PRUNE=1), the pruned kernel ploughs on; with its give-up path on (=2, what the launcher does when
+    it picks the pruned kernel for a batch of many waves) it hands exactly those clouds to the cluster kernel behind
+    it; unset / 0: the planner's own choice and the cluster kernels alone."""
     g = torch.Generator().manual_seed(91)
     N, B, M = 8192, 150, 400
     sphere = torch.randn(1, N, 3, generator=g)
@@ -398,7 +398,7 @@ def test_fps_bucket_pruned_kernel_shapes_of_real_clouds_and_the_give_up_path(mon
     kinds = [sphere, plane, clusters, outlier, same, make_cloud(g, 1, N, dup=3000, near_origin=7)]
     clouds = torch.cat([kinds[i % len(kinds)] if i < 12 else kinds[i % len(kinds)].roll(i, 1) for i in range(B)], 0).contiguous()
     want = O.fps(clouds.numpy(), M)
-    for mode in ("1", None, "0"):
+    for mode in ("1", "2", None, "0"):
         if mode is None:
             monkeypatch.delenv("PS_FPS_PRUNE", raising=False)
         else:
@@ -717,13 +717,15 @@ def test_repeatability_as_a_race_guard():
 
 
 @pytest.mark.parametrize("cluster,threads,exchange", [(c, t, e) for c in (1, 2, 4, 8, 16) for t in (128, 256)
-                                                     for e in (("async", "poll") if 1 < c <= 4 else ("async",))])
+                                                     for e in (("lean", "async", "poll") if 1 < c <= 4 else ("async",))])
 def test_fps_exchange_race_guard_over_the_forced_plan_matrix(monkeypatch, cluster, threads, exchange):
-    """Every exchange protocol of the FPS kernel (single CTA, st.async + mbarrier all-to-all, the two-level variant for
-    8 / 16 CTAs, and the polling variant on plain remote stores), at both thread counts: 12 back-to-back runs on two
-    streams with duplicates (ties on every iteration) must equal the oracle bit for bit, every time."""
+    """Every exchange protocol of the FPS kernel (single CTA, st.async + mbarrier all-to-all with 8-byte ("lean") and
+    32-byte messages, the two-level variant for 8 / 16 CTAs, and the polling variant on plain remote stores), at both
+    thread counts: 12 back-to-back runs on two streams with duplicates (ties on every iteration) must equal the oracle
+    bit for bit, every time."""
     monkeypatch.setenv("PS_FPS_CLUSTER", str(cluster))
     monkeypatch.setenv("PS_FPS_THREADS", str(threads))
+    monkeypatch.setenv("PS_FPS_LEAN", "1" if exchange == "lean" else "0")
     if exchange == "poll":
         monkeypatch.setenv("PS_FPS_EXCHANGE", "poll")
     N = {1: 2048, 2: 4096, 4: 8192, 8: 16384, 16: 16384}[cluster]
