@@ -44,6 +44,7 @@ _SIGNATURES = {
     "ps_chamfer_sums": [_P, _P, _P, ctypes.c_longlong, ctypes.c_longlong, _c_int, _P],
     "ps_fps": [_P, _P, _c_int, _c_int, _c_int, _c_int, _P],
     "ps_fps_sample": [_P, _P, _P, _c_int, _c_int, _c_int, _c_int, _P],
+    "ps_fps_sample_ex": [_P, _P, _P, _c_int, _c_int, _c_int, _c_int, _c_int, _P],
     "ps_gather_fwd": [_P, _P, _P, _c_int, _c_int, _c_int, _c_int, _c_int, _P],
     "ps_gather_bwd": [_P, _P, _P, _c_int, _c_int, _c_int, _c_int, _c_int, _P],
     "ps_group_fwd": [_P, _P, _P, _c_int, _c_int, _c_int, _c_int, _c_int, _c_int, _P],

@@ -1125,6 +1125,11 @@ extern "C" int ps_fps(const float* xyz, int* idx, int B, int N, int npoint, int 
 }
 
 extern "C" int ps_fps_sample(const float* xyz, int* idx, float* new_xyz, int B, int N, int npoint, int dev, void* stream_) {
+  return ps_fps_sample_ex(xyz, idx, new_xyz, B, N, npoint, 0, dev, stream_);
+}
+
+extern "C" int ps_fps_sample_ex(const float* xyz, int* idx, float* new_xyz, int B, int N, int npoint, int flags, int dev,
+                                void* stream_) {
   PS_REQUIRE(B >= 0 && N > 0 && npoint >= 0, "ps_fps: bad sizes B=%d N=%d npoint=%d", B, N, npoint);
   if (B == 0 || npoint == 0) return PS_OK;
   PS_REQUIRE(xyz && idx, "ps_fps: null pointer");
@@ -1141,7 +1146,10 @@ extern "C" int ps_fps_sample(const float* xyz, int* idx, float* new_xyz, int B, 
   // exchange for small clusters: tag polling on plain remote stores (MODE 3) or st.async + mbarrier (lean / MODE 1)
   bool poll = false;
   if (const char* e = getenv("PS_FPS_EXCHANGE")) poll = (e[0] == 'p');
-  const bool lean_on = fps_lean_enabled(poll);
+  // PS_FPS_CORUN: the caller runs another kernel next to this one (the sharded losses put the FPS chain under a Chamfer
+  // term): the lean exchange keeps the whole cloud in every CTA's shared memory (192 KB at 16384 points) and would push
+  // the neighbour's CTAs off the SM, so the 32-byte messages (64 KB per CTA) are used instead
+  const bool lean_on = fps_lean_enabled(poll) && !(flags & PS_FPS_CORUN);
   FpsPlan pl;
   const bool planned = plan_fps(B, N, a.L, a.nper, nsm, dev, lean_on, pl);
 

@@ -282,7 +282,7 @@ def _sharded_terms(pcds_pred, gt, sqrt, partial=None, overlap_fps=None):
     (P2 vs the full gt) does not depend on them: with `overlap_fps` (default: on CUDA, outside stream capture) the FPS
     chain runs on a side stream while the main stream computes that term.  Values are unchanged."""
     from .chamfer import chamfer_3DFunction
-    from .pointnet2_utils import fps_subsample
+    from .pointnet2_utils import fps_subsample, fps_sample_raw
 
     Pc, P1, P2 = pcds_pred
     if overlap_fps is None:  # PS_LOSS_OVERLAP=0 keeps everything on the current stream (A/B measurements)
@@ -298,8 +298,10 @@ def _sharded_terms(pcds_pred, gt, sqrt, partial=None, overlap_fps=None):
         cur, side = torch.cuda.current_stream(gt.device), _side_stream(gt.device)
         side.wait_stream(cur)
         with torch.cuda.stream(side), torch.no_grad():
-            gt_1 = fps_subsample(gt, P1.shape[1])
-            gt_c = fps_subsample(gt_1, Pc.shape[1])
+            # corun: leave the SMs' shared memory to the Chamfer term that runs next to the chain
+            corun = os.environ.get("PS_LOSS_CORUN", "1") != "0"
+            gt_1 = fps_sample_raw(gt.contiguous(), P1.shape[1], corun=corun)[1]
+            gt_c = fps_sample_raw(gt_1, Pc.shape[1], corun=corun)[1]
         term("cd2", P2, gt)  # meanwhile, on the main stream
         cur.wait_stream(side)
         for t in (gt_1, gt_c):

@@ -283,9 +283,13 @@ def query_knn(nsample, xyz, new_xyz, include_self=True):
     return knn_raw(xyz.contiguous(), new_xyz.contiguous(), nsample, pad)
 
 
-def fps_sample_raw(xyz, npoint):
+PS_FPS_CORUN = 1  # include/pointsea_b200.h
+
+
+def fps_sample_raw(xyz, npoint, corun=False):
     """(idx (B,npoint) int32, new_xyz (B,npoint,3)) from ONE kernel: the FPS kernel writes the
-    coordinates of every selected point as it goes (ps_fps_sample)."""
+    coordinates of every selected point as it goes (ps_fps_sample).  `corun`: another kernel runs next to this one
+    (PS_FPS_CORUN: the launcher leaves most of each SM's shared memory to it); the samples are the same."""
     L.require(xyz, "xyz", torch.float32, 3)
     if xyz.size(2) != 3:
         raise L.PointSeaError(f"xyz must be (B,N,3), got {tuple(xyz.shape)}")
@@ -294,8 +298,8 @@ def fps_sample_raw(xyz, npoint):
     B, N, _ = xyz.shape
     idx = torch.empty(B, npoint, device=xyz.device, dtype=torch.int32)
     new_xyz = torch.empty(B, npoint, 3, device=xyz.device, dtype=torch.float32)
-    L.check(L.load().ps_fps_sample(L.ptr(xyz), L.ptr(idx), L.ptr(new_xyz), B, N, npoint, dev, L.stream_ptr(dev)),
-            "ps_fps_sample")
+    L.check(L.load().ps_fps_sample_ex(L.ptr(xyz), L.ptr(idx), L.ptr(new_xyz), B, N, npoint, PS_FPS_CORUN if corun else 0, dev,
+                                      L.stream_ptr(dev)), "ps_fps_sample_ex")
     return idx, new_xyz
 
 

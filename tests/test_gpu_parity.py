@@ -379,6 +379,21 @@ def test_fps_bucket_pruned_kernel_vs_oracle(B, N, npoint, dup, no, monkeypatch):
     assert np.array_equal(got.cpu().numpy(), O.fps(x.numpy(), npoint))
 
 
+@pytest.mark.parametrize("B,N,npoint", [(32, 16384, 300), (4, 16384, 2048), (32, 2048, 512), (3, 5000, 77), (150, 8192, 400)])
+def test_fps_corun_hint_changes_the_kernel_not_the_samples(B, N, npoint):
+    """ps_fps_sample_ex(PS_FPS_CORUN): the variant that leaves the SMs' shared memory to a neighbouring kernel returns
+    the same indices and coordinates as the default plan and as the oracle."""
+    from svdformer_pointsea_b200.pointnet2_utils import fps_sample_raw
+    g = torch.Generator().manual_seed(640 + N)
+    x = make_cloud(g, B, N, dup=N // 10, near_origin=3)
+    xd = x.to(DEV)
+    i0, p0 = fps_sample_raw(xd, npoint)
+    i1, p1 = fps_sample_raw(xd, npoint, corun=True)
+    assert torch.equal(i0, i1) and torch.equal(p0, p1)
+    assert np.array_equal(i1[:2].cpu().numpy(), O.fps(x[:2].numpy(), npoint))
+    assert torch.equal(p1, torch.gather(xd, 1, i1.long().unsqueeze(-1).expand(-1, -1, 3)))
+
+
 def test_fps_bucket_pruned_kernel_shapes_of_real_clouds_and_the_give_up_path(monkeypatch):
     """(1) points on a thin surface and in tight clusters (where the pruning bites hardest, and bucket boxes are
     degenerate in one axis); (2) clouds squeezed into one grid cell by a far outlier, or made of one repeated point:
