@@ -522,8 +522,9 @@ def run_ours(args):
                      "structural_ceiling_frac": round(8.0 / 12.0, 4),
                      "fwd_ms": round(fwd_avg_ms, 4), "fwd_ms_min": round(min(fwd_ms), 4),
                      "gpair_per_s_fwd": round(pairs_per_step / (fwd_avg_ms * 1e-3) / 1e9, 1),
-                     "traffic": 11826000 if wl == "c1" else None, "traffic_unit": "bytes per launch (dram read+write)",
-                     "traffic_source": "ncu --set full capture of chamfer_sym_kernel<8> at the C1 shape: profiles/ncu_full_r1_table.txt"},
+                     "traffic": 11844000 if wl == "c1" else None, "traffic_unit": "bytes per launch (dram read+write)",
+                     "traffic_source": "ncu --set full capture of chamfer_sym2_kernel<8,4,2> at the C1 shape (dram read 11.844 MB, write 0: "
+                                       "the results leave through L2 in the epilogue launch): profiles/ncu_full_r2_table.txt"},
     }
     if comm_note:
         result["reduce_note"] = comm_note

@@ -188,8 +188,9 @@ int ps_fps(const float* xyz, int* idx, int B, int N, int npoint, int dev, void* 
 int ps_fps_sample(const float* xyz, int* idx, float* new_xyz, int B, int N, int npoint, int dev,
                   void* stream);
 /* ps_fps_sample with hints.  PS_FPS_CORUN: another kernel runs next to this one on the same GPU (the sharded losses put
- * the FPS chain on a side stream under a Chamfer term): the launcher then picks the variant that leaves most of each
- * SM's shared memory to the neighbour.  The samples do not depend on the flags. */
+ * the FPS chain on a side stream under a Chamfer term): when the batch's clusters would cover the GPU, the launcher
+ * picks the variant that leaves most of each SM's shared memory to the neighbour.  The samples do not depend on the
+ * flags. */
 #define PS_FPS_CORUN 1
 int ps_fps_sample_ex(const float* xyz, int* idx, float* new_xyz, int B, int N, int npoint, int flags, int dev,
                      void* stream);

@@ -1146,12 +1146,18 @@ extern "C" int ps_fps_sample_ex(const float* xyz, int* idx, float* new_xyz, int 
   // exchange for small clusters: tag polling on plain remote stores (MODE 3) or st.async + mbarrier (lean / MODE 1)
   bool poll = false;
   if (const char* e = getenv("PS_FPS_EXCHANGE")) poll = (e[0] == 'p');
-  // PS_FPS_CORUN: the caller runs another kernel next to this one (the sharded losses put the FPS chain under a Chamfer
-  // term): the lean exchange keeps the whole cloud in every CTA's shared memory (192 KB at 16384 points) and would push
-  // the neighbour's CTAs off the SM, so the 32-byte messages (64 KB per CTA) are used instead
-  const bool lean_on = fps_lean_enabled(poll) && !(flags & PS_FPS_CORUN);
+  bool lean_on = fps_lean_enabled(poll);
   FpsPlan pl;
-  const bool planned = plan_fps(B, N, a.L, a.nper, nsm, dev, lean_on, pl);
+  bool planned = plan_fps(B, N, a.L, a.nper, nsm, dev, lean_on, pl);
+  // PS_FPS_CORUN: the caller runs another kernel next to this one (the sharded losses put the FPS chain under a Chamfer
+  // term).  The lean exchange keeps the whole cloud in every CTA's shared memory (192 KB at 16384 points), i.e. it owns
+  // its SMs.  That is the better neighbour while it leaves SMs over (C4 loss part, shard of 8 clouds: 1.56 against
+  // 1.94 ms; 16 clouds: a tie); a batch whose clusters cover the GPU starves the neighbour instead (32 clouds: 3.58
+  // against 3.29 ms), so there the 32-byte messages (64 KB per CTA, shares its SMs) are used (tools/c4loss_time.py)
+  if ((flags & PS_FPS_CORUN) && lean_on && planned && B > 16 && 2 * pl.C * B > nsm) {
+    lean_on = false;
+    planned = plan_fps(B, N, a.L, a.nper, nsm, dev, lean_on, pl);
+  }
 
   // Bucket-pruned single-CTA kernel (N <= 16384) where it wins: one SM per cloud at 0.6-0.85 us per iteration against
   // 2-4 SMs per cloud at 0.45 us for the cluster kernel (B200, profiles/fps_pruned_r2.jsonl), i.e. when the batch needs
