@@ -15,6 +15,7 @@ DDP: the backward of the reduction is then scaled by the world size, so the DDP 
 gradient.  INTEGRATION.md section "Multi-GPU" says the same.
 """
 import ctypes
+import os
 
 import torch
 import torch.distributed as dist
@@ -279,15 +280,15 @@ def _sharded_terms(pcds_pred, gt, sqrt, partial=None, overlap_fps=None):
 
     The two FPS calls that thin the ground truth (gt -> |P1| -> |Pc| points, utils/loss_utils.py:40-41) are a serial
     chain of ~2500 latency-bound iterations on a quarter of the SMs' issue slots, and the largest Chamfer term
-    (P2 vs the full gt) does not depend on them: with `overlap_fps` (default: on CUDA, outside stream capture) the FPS
-    chain runs on a side stream while the main stream computes that term.  Values are unchanged."""
+    (P2 vs the full gt) does not depend on them: with `overlap_fps` (default: on CUDA) the FPS chain runs on a side
+    stream while the main stream computes that term.  Values are unchanged."""
     from .chamfer import chamfer_3DFunction
     from .pointnet2_utils import fps_subsample, fps_sample_raw
 
     Pc, P1, P2 = pcds_pred
     if overlap_fps is None:  # PS_LOSS_OVERLAP=0 keeps everything on the current stream (A/B measurements)
-        import os
-        overlap_fps = gt.is_cuda and os.environ.get("PS_LOSS_OVERLAP", "1") != "0" and not torch.cuda.is_current_stream_capturing()
+        overlap_fps = gt.is_cuda and os.environ.get("PS_LOSS_OVERLAP", "1") != "0"
+    capturing = gt.is_cuda and torch.cuda.is_current_stream_capturing()
     sums = LossSums(gt.device)
 
     def term(name, p, q):
@@ -303,9 +304,10 @@ def _sharded_terms(pcds_pred, gt, sqrt, partial=None, overlap_fps=None):
             gt_1 = fps_sample_raw(gt.contiguous(), P1.shape[1], corun=corun)[1]
             gt_c = fps_sample_raw(gt_1, Pc.shape[1], corun=corun)[1]
         term("cd2", P2, gt)  # meanwhile, on the main stream
-        cur.wait_stream(side)
-        for t in (gt_1, gt_c):
-            t.record_stream(cur)
+        cur.wait_stream(side)  # (inside a stream capture the fork and this join become edges of the graph)
+        if not capturing:  # a capture's private pool never hands the blocks to anyone else
+            for t in (gt_1, gt_c):
+                t.record_stream(cur)
         term("cdc", Pc, gt_c)
         term("cd1", P1, gt_1)
     else:
@@ -336,3 +338,69 @@ def get_loss_PM_sharded(pcds_pred, partial, gt, sqrt=True, group=None, comm=None
     means = _sharded_terms(pcds_pred, gt, sqrt, partial=partial).reduce(group, comm, grad_reduce)
     cdc, cd1, cd2 = (combine_chamfer(means, n, sqrt) for n in ("cdc", "cd1", "cd2"))
     return cdc + cd1 + cd2 + means["pm.d1"], [cdc, cd1, cd2]
+
+
+class GraphedLoss:
+    """get_loss_sharded / get_loss_PM_sharded, forward AND backward, as one replayed CUDA graph.
+
+    The eager loss is ~100 small launches around the five big kernels (three Chamfer terms, two FPS calls): square
+    roots, sums, the concatenation for the single all-reduce, and the same again backwards — 0.45 ms of host time per
+    step, which is what a rank of an 8-GPU run waits for once its shard is down to 4 clouds.  Shapes are fixed per
+    training run, so the step is captured once (the FPS chain still forks onto the side stream: fork and join become
+    graph edges; with `comm`, the peer-memory exchange is one more kernel node) and replayed:
+
+        step = GraphedLoss([Pc.shape, P1.shape, P2.shape], gt.shape, sqrt=True, comm=comm)
+        loss, (cdc, cd1, cd2), (gPc, gP1, gP2) = step([Pc, P1, P2], gt)     # copies in, one graph launch
+        torch.autograd.backward([Pc, P1, P2], [gPc, gP1, gP2])              # continue into the model
+
+    The returned tensors are the graph's static outputs: consume (or clone) them before the next call.  Every rank of
+    `comm` must call the same number of times (the exchange is part of the graph).  Reference: utils/loss_utils.py:33-85.
+    """
+
+    def __init__(self, pred_shapes, gt_shape, sqrt=True, alpha1=1, alpha2=1, comm=None, grad_reduce="sum",
+                 partial_shape=None, device=None, warmup=2):
+        if not torch.cuda.is_available():
+            raise L.PointSeaError("GraphedLoss needs a CUDA device (the eager get_loss_sharded runs anywhere)")
+        self.device = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
+        mk = lambda shape: torch.zeros(tuple(shape), device=self.device, dtype=torch.float32)
+        self.preds = [mk(sh).requires_grad_(True) for sh in pred_shapes]
+        self.gt = mk(gt_shape)
+        self.partial = mk(partial_shape) if partial_shape is not None else None
+        g = torch.Generator().manual_seed(7)  # warm-up on spread-out points: all-zero clouds are one big tie
+        with torch.no_grad():
+            for t in self.preds + [self.gt] + ([self.partial] if self.partial is not None else []):
+                t.copy_(torch.rand(t.shape, generator=g) - 0.5)
+
+        def run():
+            if self.partial is None:
+                loss, terms = get_loss_sharded(self.preds, self.gt, sqrt=sqrt, alpha1=alpha1, alpha2=alpha2, comm=comm,
+                                               grad_reduce=grad_reduce)
+            else:
+                loss, terms = get_loss_PM_sharded(self.preds, self.partial, self.gt, sqrt=sqrt, comm=comm, grad_reduce=grad_reduce)
+            grads = torch.autograd.grad(loss, self.preds)
+            return loss, terms, grads
+
+        side = torch.cuda.Stream(device=self.device)
+        side.wait_stream(torch.cuda.current_stream(self.device))
+        with torch.cuda.stream(side):
+            for _ in range(max(1, warmup)):  # function attributes, pools, plans: outside the capture
+                run()
+        torch.cuda.current_stream(self.device).wait_stream(side)
+        torch.cuda.synchronize(self.device)
+        self.graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(self.graph):
+            self.loss, self.terms, self.grads = run()
+        self.calls = 0
+
+    def __call__(self, pcds_pred, gt, partial=None):
+        with torch.no_grad():
+            for dst, src in zip(self.preds, pcds_pred):
+                dst.copy_(src, non_blocking=True)
+            self.gt.copy_(gt, non_blocking=True)
+            if self.partial is not None:
+                if partial is None:
+                    raise L.PointSeaError("this GraphedLoss was captured with a partial cloud (get_loss_PM)")
+                self.partial.copy_(partial, non_blocking=True)
+        self.graph.replay()
+        self.calls += 1
+        return self.loss, self.terms, self.grads

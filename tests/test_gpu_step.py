@@ -109,6 +109,36 @@ def test_step_inside_a_torch_cuda_graph():
     assert torch.equal(step.sums_local, want)
 
 
+@pytest.mark.parametrize("with_partial", [False, True])
+def test_graphed_loss_replays_get_loss_forward_and_backward(with_partial):
+    """GraphedLoss = get_loss_sharded / get_loss_PM_sharded + autograd.grad captured once (FPS chain forked onto the
+    side stream inside the capture) and replayed on NEW clouds: loss, terms and gradients match the eager call."""
+    _ps()
+    from svdformer_pointsea_b200.dist import GraphedLoss, get_loss_sharded, get_loss_PM_sharded
+    dev = torch.device("cuda:0")
+    B = 3
+    g = torch.Generator().manual_seed(77)
+    shapes = [(B, 128, 3), (B, 512, 3), (B, 4096, 3)]
+    step = GraphedLoss(shapes, (B, 4096, 3), sqrt=True, partial_shape=(B, 1024, 3) if with_partial else None)
+    for it in range(3):
+        preds = [make_cloud(g, B, sh[1]).to(dev).requires_grad_(True) for sh in shapes]
+        gt = make_cloud(g, B, 4096, dup=300, near_origin=4).to(dev)
+        part = make_cloud(g, B, 1024).to(dev) if with_partial else None
+        if with_partial:
+            want, wt = get_loss_PM_sharded(preds, part, gt, sqrt=True)
+        else:
+            want, wt = get_loss_sharded(preds, gt, sqrt=True)
+        wg = torch.autograd.grad(want, preds)
+        loss, terms, grads = step(preds, gt, part)
+        torch.cuda.synchronize()
+        assert abs(float(loss) - float(want)) <= 1e-6 * abs(float(want))
+        for a, b in zip(terms, wt):
+            assert abs(float(a) - float(b)) <= 1e-6 * abs(float(b))
+        for a, b in zip(grads, wg):
+            assert float((a - b).abs().max()) <= 1e-5 * float(b.abs().max())
+    assert step.calls == 3
+
+
 def _local_comms(devs):
     from svdformer_pointsea_b200.dist import PeerComm
     return PeerComm.local(devs)
@@ -235,8 +265,18 @@ def _ipc_worker(rank, world, port, q):
     gt = shard_batch(b).to(dev)
     l_peer, _ = get_loss_sharded(P, gt, comm=comm)
     l_nccl, _ = get_loss_sharded(P, gt)
+    # the same loss, forward + backward, captured once with the exchange inside and replayed on new clouds
+    from svdformer_pointsea_b200.dist import GraphedLoss
+    P3 = [p.detach().clone().requires_grad_(True) for p in P]
+    l_eager, _ = get_loss_sharded(P3, gt, comm=comm)
+    g_eager = torch.autograd.grad(l_eager, P3)
+    graphed = GraphedLoss([p.shape for p in P3], gt.shape, comm=comm)
+    for _ in range(3):
+        l_graph, _, g_graph = graphed(P3, gt)
+    gerr = max(float((a_ - b_).abs().max() / b_.abs().max()) for a_, b_ in zip(g_graph, g_eager))
     torch.cuda.synchronize()
-    q.put((rank, [o.cpu().numpy() for o in outs], hs.numpy().copy(), float(l_peer), float(l_nccl), comm.status(), async_sums))
+    q.put((rank, [o.cpu().numpy() for o in outs], hs.numpy().copy(), float(l_peer), float(l_nccl), comm.status(), async_sums,
+           float(l_eager), float(l_graph), gerr))
     dist.barrier()
     comm.close()
     dist.destroy_process_group()
@@ -261,8 +301,9 @@ def test_peer_comm_over_cuda_ipc_between_processes():
     a, b = make_cloud(g, B, N).cuda(), make_cloud(g, B, M).cuda()
     d1, d2, _, _ = ps.chamfer_forward(a, b)
     want = ps.chamfer_sums(d1, d2).cpu().numpy()
-    for rank, outs, hs, l_peer, l_nccl, st, async_sums in res:
+    for rank, outs, hs, l_peer, l_nccl, st, async_sums, l_eager, l_graph, gerr in res:
         assert not st["timed_out"]
+        assert abs(l_graph - l_eager) <= 1e-6 * abs(l_eager) and l_graph == res[0][8] and gerr < 1e-5
         assert len(async_sums) == 11
         for v in async_sums:
             assert np.array_equal(v, res[0][6][0]) and np.allclose(v, want, rtol=1e-12, atol=0)

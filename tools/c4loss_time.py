@@ -4,7 +4,7 @@ import sys, os, os.path as osp, json
 sys.path.insert(0, osp.dirname(osp.dirname(osp.abspath(__file__))))
 import torch
 import svdformer_pointsea_b200 as ps
-from svdformer_pointsea_b200.dist import get_loss_sharded
+from svdformer_pointsea_b200.dist import get_loss_sharded, GraphedLoss
 from svdformer_pointsea_b200.pointnet2_utils import fps_sample_raw
 
 dev = torch.device("cuda:0")
@@ -43,5 +43,6 @@ for B in [int(a) for a in sys.argv[1:]] or [32, 4]:
         x = fps_sample_raw(gt, 2048, corun=corun)[1]
         fps_sample_raw(x, 512, corun=corun)[1]
 
-    print(json.dumps({"B": B, "env": env, "loss_ms": timed(step), "cd2_alone_ms": timed(cd2), "fps_chain_ms": timed(lambda: chain(False)),
+    graphed = GraphedLoss([p.shape for p in preds], gt.shape, sqrt=True)
+    print(json.dumps({"B": B, "env": env, "loss_ms": timed(step), "graphed_loss_ms": timed(lambda: graphed(preds, gt)), "cd2_alone_ms": timed(cd2), "fps_chain_ms": timed(lambda: chain(False)),
                       "fps_chain_corun_ms": timed(lambda: chain(True))}), flush=True)
