@@ -131,7 +131,7 @@ def test_graphed_loss_replays_get_loss_forward_and_backward(with_partial):
         wg = torch.autograd.grad(want, preds)
         loss, terms, grads = step(preds, gt, part)
         torch.cuda.synchronize()
-        assert abs(float(loss) - float(want)) <= 1e-6 * abs(float(want))
+        assert abs(float(loss.detach()) - float(want.detach())) <= 1e-6 * abs(float(want.detach()))
         for a, b in zip(terms, wt):
             assert abs(float(a) - float(b)) <= 1e-6 * abs(float(b))
         for a, b in zip(grads, wg):
