@@ -34,7 +34,8 @@ partial 2048 points vs ground truth 16384 points, fp32, synthetic `rand - 0.5` c
   cpu_baseline = pure-PyTorch re-expression on the host cores (oracle/oracle.py), bounded sample.
 `--scaling strong` fixes the TOTAL work and splits it over the ranks: `--workload c5` (BASELINE configs[4]:
 B=8 clouds of 131072 points, Chamfer fwd+bwd + FPS -> 16384) or `--workload c4loss` (the loss part of configs[3]:
-B=32, get_loss = 2 FPS + 3 Chamfer terms + one collective).
+B=32, get_loss = 2 FPS + 3 Chamfer terms + one collective; forward + backward captured once and replayed through
+dist.GraphedLoss, the eager autograd call timed beside it as `eager`).
 `--impl reference` times the CPU expression alone (the reference has no CPU kernel of its own;
 metrics/CD/chamfer_python.py is its pure-torch restatement) on the same config/metric, full B=32 per step.
 """
