@@ -483,7 +483,9 @@ __global__ void __launch_bounds__(T, 1) fps_lean_kernel(const FpsArgs a, int Rpa
     const int wm = __reduce_max_sync(0xffffffffu, tb);
     const unsigned wk = __reduce_min_sync(0xffffffffu, tb == wm ? rk : 0xffffffffu);
     const int buf = j & 1;
-    if ((unsigned)lane < C) st_async_v2(ra[buf], rb[buf], (unsigned)wm, wk);
+    // (selects, not ra[buf]: a dynamically indexed register array lives in local memory, and its two loads sat in
+    // front of the remote store in every iteration)
+    if ((unsigned)lane < C) st_async_v2(buf ? ra[1] : ra[0], buf ? rb[1] : rb[0], (unsigned)wm, wk);
     const unsigned parity = (unsigned)((j - 1) >> 1) & 1u;
     while (!fps_mbar_try_wait(smem_u32(&mbar[buf]), parity)) {}
     if (tid == 0) fps_mbar_expect_tx(smem_u32(&mbar[buf]), (unsigned)E * 8u);  // re-arm for iteration j + 2 (see fps_kernel)
