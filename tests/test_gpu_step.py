@@ -133,7 +133,7 @@ def test_graphed_loss_replays_get_loss_forward_and_backward(with_partial):
         torch.cuda.synchronize()
         assert abs(float(loss.detach()) - float(want.detach())) <= 1e-6 * abs(float(want.detach()))
         for a, b in zip(terms, wt):
-            assert abs(float(a) - float(b)) <= 1e-6 * abs(float(b))
+            assert abs(float(a.detach()) - float(b.detach())) <= 1e-6 * abs(float(b.detach()))
         for a, b in zip(grads, wg):
             assert float((a - b).abs().max()) <= 1e-5 * float(b.abs().max())
     assert step.calls == 3
