@@ -1133,6 +1133,7 @@ extern "C" int ps_fps_sample(const float* xyz, int* idx, float* new_xyz, int B, 
 extern "C" int ps_fps_sample_ex(const float* xyz, int* idx, float* new_xyz, int B, int N, int npoint, int flags, int dev,
                                 void* stream_) {
   PS_REQUIRE(B >= 0 && N > 0 && npoint >= 0, "ps_fps: bad sizes B=%d N=%d npoint=%d", B, N, npoint);
+  PS_REQUIRE((flags & ~PS_FPS_CORUN) == 0, "ps_fps: unknown flags 0x%x", flags);
   if (B == 0 || npoint == 0) return PS_OK;
   PS_REQUIRE(xyz && idx, "ps_fps: null pointer");
   DeviceGuard guard(dev);

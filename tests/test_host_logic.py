@@ -147,3 +147,18 @@ def test_host_buffer_entry_points_validate_before_touching_a_device():
                 fn(a, b)
     step = ps.HostStep(0, 0, (a,), None, None)  # an empty submission: joining it is a no-op that needs no library call
     assert step.ticket == 0
+
+
+def test_fps_flags_and_graphed_loss_fail_on_the_host_before_any_device_work():
+    """ps_fps_sample_ex rejects flag bits it does not know (argument check, no device needed); GraphedLoss has no CPU
+    path and says so."""
+    import ctypes
+    from svdformer_pointsea_b200 import _lib as L
+    from svdformer_pointsea_b200.dist import GraphedLoss
+    lib = L.load()
+    rc = lib.ps_fps_sample_ex(None, None, None, 1, 8, 2, 0x40, 0, None)
+    assert rc != 0 and b"unknown flags" in lib.ps_last_error()
+    assert lib.ps_fps_sample_ex(None, None, None, 0, 8, 2, 1, 0, None) == 0  # empty batch: nothing to do, PS_FPS_CORUN accepted
+    if not torch.cuda.is_available():
+        with pytest.raises(ps.PointSeaError, match="CUDA device"):
+            GraphedLoss([(1, 8, 3), (1, 16, 3), (1, 32, 3)], (1, 32, 3))
