@@ -302,14 +302,20 @@ def _sharded_terms(pcds_pred, gt, sqrt, partial=None, overlap_fps=None):
             # corun: leave the SMs' shared memory to the Chamfer term that runs next to the chain
             corun = os.environ.get("PS_LOSS_CORUN", "1") != "0"
             gt_1 = fps_sample_raw(gt.contiguous(), P1.shape[1], corun=corun)[1]
+            have_1 = torch.cuda.Event()
+            have_1.record(side)
             gt_c = fps_sample_raw(gt_1, Pc.shape[1], corun=corun)[1]
         term("cd2", P2, gt)  # meanwhile, on the main stream
-        cur.wait_stream(side)  # (inside a stream capture the fork and this join become edges of the graph)
+        if os.environ.get("PS_LOSS_CD1_EARLY", "1") == "0":  # A/B: join the whole chain first
+            cur.wait_stream(side)
+        cur.wait_event(have_1)  # (inside a stream capture the fork and the joins become edges of the graph)
         if not capturing:  # a capture's private pool never hands the blocks to anyone else
-            for t in (gt_1, gt_c):
-                t.record_stream(cur)
+            gt_1.record_stream(cur)
+        term("cd1", P1, gt_1)  # under the second FPS call
+        cur.wait_stream(side)
+        if not capturing:
+            gt_c.record_stream(cur)
         term("cdc", Pc, gt_c)
-        term("cd1", P1, gt_1)
     else:
         gt_1 = fps_subsample(gt, P1.shape[1])
         gt_c = fps_subsample(gt_1, Pc.shape[1])
