@@ -288,6 +288,7 @@ def _sharded_terms(pcds_pred, gt, sqrt, partial=None, overlap_fps=None):
     Pc, P1, P2 = pcds_pred
     if overlap_fps is None:  # PS_LOSS_OVERLAP=0 keeps everything on the current stream (A/B measurements)
         overlap_fps = gt.is_cuda and os.environ.get("PS_LOSS_OVERLAP", "1") != "0"
+    overlap_fps = bool(overlap_fps) and gt.is_cuda and not gt.requires_grad  # the side-stream chain runs without autograd
     capturing = gt.is_cuda and torch.cuda.is_current_stream_capturing()
     sums = LossSums(gt.device)
 
