@@ -387,16 +387,17 @@ class GraphedLoss:
             grads = torch.autograd.grad(loss, self.preds)
             return loss, terms, grads
 
-        side = torch.cuda.Stream(device=self.device)
-        side.wait_stream(torch.cuda.current_stream(self.device))
-        with torch.cuda.stream(side):
-            for _ in range(max(1, warmup)):  # function attributes, pools, plans: outside the capture
-                run()
-        torch.cuda.current_stream(self.device).wait_stream(side)
-        torch.cuda.synchronize(self.device)
-        self.graph = torch.cuda.CUDAGraph()
-        with torch.cuda.graph(self.graph):
-            self.loss, self.terms, self.grads = run()
+        with torch.cuda.device(self.device):
+            side = torch.cuda.Stream(device=self.device)
+            side.wait_stream(torch.cuda.current_stream(self.device))
+            with torch.cuda.stream(side):
+                for _ in range(max(1, warmup)):  # function attributes, pools, plans: outside the capture
+                    run()
+            torch.cuda.current_stream(self.device).wait_stream(side)
+            torch.cuda.synchronize(self.device)
+            self.graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(self.graph):
+                self.loss, self.terms, self.grads = run()
         self.calls = 0
 
     def __call__(self, pcds_pred, gt, partial=None):
@@ -408,6 +409,7 @@ class GraphedLoss:
                 if partial is None:
                     raise L.PointSeaError("this GraphedLoss was captured with a partial cloud (get_loss_PM)")
                 self.partial.copy_(partial, non_blocking=True)
-        self.graph.replay()
+        with torch.cuda.device(self.device):
+            self.graph.replay()
         self.calls += 1
         return self.loss, self.terms, self.grads
